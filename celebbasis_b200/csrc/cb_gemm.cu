@@ -1,0 +1,559 @@
+// cb_gemm — tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0      : TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulator in TMEM)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> alpha/bias/act/residual -> HBM)
+// Convolutions never materialise im2col: each (tap, 64-channel) k-iteration loads a SHIFTED
+// [box_i][box_h][box_w][64ch] box of the NHWC image straight into the K-major A tile; padding is
+// the TMA out-of-bounds zero fill, stride-2 is the tensor-map traversal stride.
+// Two CTAs are resident per SM (3-stage ring each) so one tile's epilogue overlaps the
+// other's MMA main loop.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cb_common.cuh"
+
+namespace cb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+
+struct GemmParams {
+    int M, N, K;
+    int kchunks, taps, kw;
+    int ksteps_last;  // MMA k-steps (of 16) in the last 64-chunk of each tap
+    int conv;
+    int out_h, out_w, img_n;
+    int box_w, box_h, box_i;
+    int tiles_w, tiles_h;
+    int stride, pad_top, pad_left;
+    int b_tap_rows, flip_taps;
+    void* D;
+    int d_dtype;
+    long long ldd, d_bs;
+    int d_transposed;
+    int vec_ok;
+    const float* bias;
+    int bias_row_div;
+    long long ldbias;
+    const void* R;
+    int r_dtype;
+    long long ldr, r_bs;
+    float alpha;
+    int act;
+    unsigned idesc;
+    unsigned a_bytes, b_bytes;
+};
+
+template <int BN>
+struct TileCfg {
+    static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case CB_ACT_SILU: return silu_f(v);
+        case CB_ACT_GELU: return gelu_f(v);
+        case CB_ACT_QUICK_GELU: return quick_gelu_f(v);
+        default: return v;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __half22float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&f)[8]) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+__device__ __forceinline__ float load_any(const void* base, int dtype, long long idx) {
+    if (dtype == CB_F32) return reinterpret_cast<const float*>(base)[idx];
+    if (dtype == CB_F16) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+__device__ __forceinline__ void store_any(void* base, int dtype, long long idx, float v) {
+    if (dtype == CB_F32) reinterpret_cast<float*>(base)[idx] = v;
+    else if (dtype == CB_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+// Epilogue for one 32-column chunk held by one thread (one output row).
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], bool row_valid,
+                                               long long grow, long long brow, int col0, int bz) {
+    if (!row_valid) return;
+    const int ncols = min(32, p.N - col0);
+    if (ncols <= 0) return;
+    const bool fast = p.vec_ok && ncols == 32 && !p.d_transposed;
+    if (fast) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
+            const int col = col0 + g * 8;
+            if (p.bias) {
+                float b[8];
+                load8<float>(p.bias + brow * p.ldbias + col, b);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += b[j];
+            }
+            if (p.act != CB_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+            }
+            if (p.R) {
+                float r[8];
+                const long long ridx = (long long)bz * p.r_bs + grow * p.ldr + col;
+                if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
+                else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, r);
+                else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += r[j];
+            }
+            const long long didx = (long long)bz * p.d_bs + grow * p.ldd + col;
+            if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
+            else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
+            else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < ncols) {
+                const int col = col0 + j;
+                float v = __uint_as_float(acc[j]) * p.alpha;
+                if (p.bias) v += p.bias[brow * p.ldbias + col];
+                v = apply_act(v, p.act);
+                if (p.R) v += load_any(p.R, p.r_dtype, (long long)bz * p.r_bs + grow * p.ldr + col);
+                const long long didx = p.d_transposed ? ((long long)bz * p.d_bs + (long long)col * p.ldd + grow)
+                                                      : ((long long)bz * p.d_bs + grow * p.ldd + col);
+                store_any(p.D, p.d_dtype, didx, v);
+            }
+        }
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, BN <= 160 ? 2 : 1)
+cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmParams p) {
+    using Cfg = TileCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1 KiB alignment
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    // barriers: full[kStages], empty[kStages], tmem_full; then the TMEM base address word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m_tile = blockIdx.y;
+    const int bz = blockIdx.z;
+
+    // tile origin
+    int m0 = 0, ow0 = 0, oh0 = 0, img0 = 0;
+    if (p.conv) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int ti = m_tile / (p.tiles_w * p.tiles_h);
+        ow0 = tw * p.box_w;
+        oh0 = th * p.box_h;
+        img0 = ti * p.box_i;
+    } else {
+        m0 = m_tile * BM;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int kiters = p.taps * p.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), p.a_bytes + p.b_bytes);
+                const int tap = it / p.kchunks;
+                const int kc = it - tap * p.kchunks;
+                const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
+                const uint32_t b_dst = a_dst + Cfg::kABytes;
+                const int tap_b = p.flip_taps ? (p.taps - 1 - tap) : tap;
+                if (p.conv) {
+                    const int r = tap / p.kw, sx = tap - r * p.kw;
+                    tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, ow0 * p.stride + sx - p.pad_left,
+                                oh0 * p.stride + r - p.pad_top, img0);
+                } else if (A_MN) {
+                    tma_load_4d(a_dst, &tmA, full_bar(s), m0, kc * BK, bz, 0);
+                    tma_load_4d(a_dst + 8192, &tmA, full_bar(s), m0 + 64, kc * BK, bz, 0);
+                } else {
+                    tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, m0, bz, 0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_3d(b_dst + j * 8192, &tmB, full_bar(s), n0 + j * 64,
+                                    tap_b * p.b_tap_rows + kc * BK, bz);
+                } else {
+                    tma_load_3d(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + n0, bz);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
+                const uint32_t b_src = a_src + Cfg::kABytes;
+                const int kc = it % p.kchunks;
+                const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : (BK / 16);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adesc = A_MN ? umma_smem_desc_sw128(a_src + k * 2048, 8192, 1024)
+                                                : umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
+                    const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
+                                                : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
+                    umma_f16(tmem_base, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above retire
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;
+        bool row_valid;
+        long long grow;
+        if (p.conv) {
+            const int per_img = p.box_h * p.box_w;
+            const int bi = r / per_img;
+            const int rem = r - bi * per_img;
+            const int bh = rem / p.box_w;
+            const int bw = rem - bh * p.box_w;
+            const int img = img0 + bi, oh = oh0 + bh, ow = ow0 + bw;
+            row_valid = (bi < p.box_i) && (img < p.img_n) && (oh < p.out_h) && (ow < p.out_w);
+            grow = ((long long)img * p.out_h + oh) * p.out_w + ow;
+        } else {
+            grow = m0 + r;
+            row_valid = grow < p.M;
+        }
+        const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+            tmem_ld_wait();
+            epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, bz);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    }
+    return fn;
+}
+
+int make_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint64_t* dims,
+              const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, const uint32_t* estr) {
+    EncodeTiledFn fn = get_encode_fn();
+    CB_REQUIRE(fn != nullptr, CB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+    CB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, CB_ERR_ALIGN, "tensor base %p not 16B aligned", ptr);
+    for (int i = 0; i < rank - 1; ++i)
+        CB_REQUIRE((strides_bytes[i] & 15u) == 0, CB_ERR_ALIGN, "tensor stride[%d]=%llu bytes not multiple of 16", i,
+                   (unsigned long long)strides_bytes[i]);
+    CUtensorMapDataType dt = dtype == CB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult rc = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CB_REQUIRE(rc == CUDA_SUCCESS, CB_ERR_DRIVER,
+               "cuTensorMapEncodeTiled failed rc=%d rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)rc,
+               rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+               box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = TileCfg<BN>;
+    static bool attr_done = false;
+    auto kern = cb_gemm_kernel<BN, A_MN, B_MN>;
+    if (!attr_done) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int pick_bn(const cb_gemm_desc& d) {
+    const int N = d.N;
+    if (d.b_major == CB_MAJOR_MN) return N <= 64 ? 64 : 128;
+    if (N % 160 == 0) return 160;
+    if (N <= 64) return 64;
+    if (N % 128 == 0 || N > 160) return 128;
+    return N <= 128 ? 128 : 160;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
+    CB_REQUIRE(dp != nullptr, CB_ERR_ARG, "cb_gemm: null desc");
+    const cb_gemm_desc& d = *dp;
+    CB_REQUIRE(d.ab_dtype == CB_F16 || d.ab_dtype == CB_BF16, CB_ERR_ARG, "cb_gemm: ab_dtype must be f16/bf16");
+    CB_REQUIRE(d.A && d.B && d.D, CB_ERR_ARG, "cb_gemm: null A/B/D");
+    CB_REQUIRE(d.N > 0 && d.K > 0 && d.batch > 0, CB_ERR_ARG, "cb_gemm: bad N/K/batch");
+    CB_REQUIRE(d.d_dtype >= CB_F16 && d.d_dtype <= CB_F32, CB_ERR_ARG, "cb_gemm: bad d_dtype");
+    const int es = 2;
+    const bool a_mn = d.a_major == CB_MAJOR_MN, b_mn = d.b_major == CB_MAJOR_MN;
+    CB_REQUIRE(!(d.conv && a_mn), CB_ERR_ARG, "cb_gemm: conv mode needs K-major A (NHWC)");
+    CB_REQUIRE(!(a_mn && !b_mn), CB_ERR_ARG, "cb_gemm: (A MN-major, B K-major) is not instantiated");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d.N;
+    p.K = d.K;
+    p.kchunks = ceil_div(d.K, BK);
+    p.ksteps_last = ceil_div(d.K - (p.kchunks - 1) * BK, 16);
+    p.conv = d.conv;
+    p.taps = 1;
+    p.kw = 1;
+    p.b_tap_rows = d.b_tap_rows;
+    p.flip_taps = d.flip_taps;
+
+    CUtensorMap tA, tB;
+    int m_tiles;
+    if (d.conv) {
+        CB_REQUIRE(d.img_n > 0 && d.img_h > 0 && d.img_w > 0 && d.out_h > 0 && d.out_w > 0 && d.kh > 0 && d.kw > 0,
+                   CB_ERR_ARG, "cb_gemm(conv): bad geometry");
+        CB_REQUIRE(d.stride == 1 || d.stride == 2, CB_ERR_ARG, "cb_gemm(conv): stride must be 1 or 2");
+        CB_REQUIRE(d.batch == 1, CB_ERR_ARG, "cb_gemm(conv): batch must be 1 (images are rows)");
+        p.taps = d.kh * d.kw;
+        p.kw = d.kw;
+        p.M = d.img_n * d.out_h * d.out_w;
+        p.out_h = d.out_h;
+        p.out_w = d.out_w;
+        p.img_n = d.img_n;
+        p.stride = d.stride;
+        p.pad_top = d.pad_top;
+        p.pad_left = d.pad_left;
+        // pixel box: <=128 output pixels as [box_i][box_h][box_w]
+        int bw = d.out_w < BM ? d.out_w : BM;
+        int bh = BM / bw;
+        if (bh > d.out_h) bh = d.out_h;
+        int bi = BM / (bw * bh);
+        if (bi > d.img_n) bi = d.img_n;
+        if (bi < 1) bi = 1;
+        p.box_w = bw;
+        p.box_h = bh;
+        p.box_i = bi;
+        p.tiles_w = ceil_div(d.out_w, bw);
+        p.tiles_h = ceil_div(d.out_h, bh);
+        m_tiles = p.tiles_w * p.tiles_h * ceil_div(d.img_n, bi);
+        p.a_bytes = (unsigned)(bw * bh * bi) * BK * es;
+        const uint64_t C = (uint64_t)d.K;
+        const uint64_t rowstride = (uint64_t)d.lda;  // elements between consecutive pixels (>= K)
+        uint64_t dims[4] = {C, (uint64_t)d.img_w, (uint64_t)d.img_h, (uint64_t)d.img_n};
+        uint64_t strides[3] = {rowstride * es, rowstride * es * d.img_w, rowstride * es * d.img_w * d.img_h};
+        uint32_t box[4] = {BK, (uint32_t)(bw * d.stride), (uint32_t)(bh * d.stride), (uint32_t)bi};
+        uint32_t estr[4] = {1, (uint32_t)d.stride, (uint32_t)d.stride, 1};
+        CB_REQUIRE(box[1] <= 256 && box[2] <= 256, CB_ERR_ARG, "cb_gemm(conv): box too large");
+        int rc = make_tmap(&tA, d.ab_dtype, 4, d.A, dims, strides, box, estr);
+        if (rc) return rc;
+    } else {
+        CB_REQUIRE(d.M > 0, CB_ERR_ARG, "cb_gemm: bad M");
+        p.M = d.M;
+        m_tiles = ceil_div(d.M, BM);
+        p.a_bytes = BM * BK * es;
+        const uint64_t bs = (uint64_t)(d.batch > 1 ? d.a_batch_stride : (a_mn ? d.lda * (int64_t)d.K : d.lda * (int64_t)d.M));
+        if (a_mn) {
+            uint64_t dims[4] = {(uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.batch, 1};
+            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs * es};
+            uint32_t box[4] = {64, BK, 1, 1};
+            uint32_t estr[4] = {1, 1, 1, 1};
+            int rc = make_tmap(&tA, d.ab_dtype, 4, d.A, dims, strides, box, estr);
+            if (rc) return rc;
+        } else {
+            uint64_t dims[4] = {(uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.batch, 1};
+            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs * es};
+            uint32_t box[4] = {BK, BM, 1, 1};
+            uint32_t estr[4] = {1, 1, 1, 1};
+            int rc = make_tmap(&tA, d.ab_dtype, 4, d.A, dims, strides, box, estr);
+            if (rc) return rc;
+        }
+    }
+
+    const int BN = pick_bn(d);
+    p.b_bytes = (unsigned)BN * BK * es;
+    {
+        const uint64_t brows_total = (uint64_t)(d.conv ? (int64_t)p.taps * d.b_tap_rows : (b_mn ? d.K : d.N));
+        const uint64_t bs = (uint64_t)(d.batch > 1 ? d.b_batch_stride : d.ldb * (int64_t)brows_total);
+        uint32_t estr[3] = {1, 1, 1};
+        if (b_mn) {
+            uint64_t dims[3] = {(uint64_t)d.N, brows_total, (uint64_t)d.batch};
+            uint64_t strides[2] = {(uint64_t)d.ldb * es, bs * es};
+            uint32_t box[3] = {64, BK, 1};
+            int rc = make_tmap(&tB, d.ab_dtype, 3, d.B, dims, strides, box, estr);
+            if (rc) return rc;
+        } else {
+            uint64_t dims[3] = {(uint64_t)d.K, brows_total, (uint64_t)d.batch};
+            uint64_t strides[2] = {(uint64_t)d.ldb * es, bs * es};
+            uint32_t box[3] = {BK, (uint32_t)BN, 1};
+            int rc = make_tmap(&tB, d.ab_dtype, 3, d.B, dims, strides, box, estr);
+            if (rc) return rc;
+        }
+    }
+
+    p.D = d.D;
+    p.d_dtype = d.d_dtype;
+    p.ldd = d.ldd;
+    p.d_bs = d.d_batch_stride;
+    p.d_transposed = d.d_transposed;
+    p.bias = d.bias;
+    p.bias_row_div = d.bias_row_div;
+    p.ldbias = d.ldbias;
+    p.R = d.R;
+    p.r_dtype = d.r_dtype;
+    p.ldr = d.ldr;
+    p.r_bs = d.r_batch_stride;
+    p.alpha = d.alpha;
+    p.act = d.act;
+    p.idesc = umma_idesc_f16(BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
+    {
+        const int des = d.d_dtype == CB_F32 ? 4 : 2;
+        bool ok = ((reinterpret_cast<uintptr_t>(d.D) & 15u) == 0) && ((d.ldd * des) % 16 == 0) &&
+                  ((d.d_batch_stride * des) % 16 == 0);
+        if (d.R) {
+            const int res = d.r_dtype == CB_F32 ? 4 : 2;
+            ok = ok && ((reinterpret_cast<uintptr_t>(d.R) & 15u) == 0) && ((d.ldr * res) % 16 == 0) &&
+                 ((d.r_batch_stride * res) % 16 == 0);
+        }
+        if (d.bias) ok = ok && ((reinterpret_cast<uintptr_t>(d.bias) & 15u) == 0) && ((d.ldbias * 4) % 16 == 0);
+        p.vec_ok = ok ? 1 : 0;
+    }
+
+    dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)d.batch);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!a_mn && !b_mn) {
+        if (BN == 64) return launch<64, false, false>(tA, tB, p, grid, st);
+        if (BN == 128) return launch<128, false, false>(tA, tB, p, grid, st);
+        return launch<160, false, false>(tA, tB, p, grid, st);
+    } else if (!a_mn && b_mn) {
+        if (BN == 64) return launch<64, false, true>(tA, tB, p, grid, st);
+        return launch<128, false, true>(tA, tB, p, grid, st);
+    } else {
+        if (BN == 64) return launch<64, true, true>(tA, tB, p, grid, st);
+        return launch<128, true, true>(tA, tB, p, grid, st);
+    }
+}
