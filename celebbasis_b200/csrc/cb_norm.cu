@@ -1,0 +1,425 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and activation-gradient backward, channels-last.
+//
+// Replaces ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32 / normalization),
+// ldm/modules/attention.py:76-77 + ldm/modules/diffusionmodules/model.py:38-39 (Normalize, eps 1e-6),
+// the nn.SiLU that follows them in ResBlock (openaimodel.py:201-241) and nn.LayerNorm in
+// BasicTransformerBlock (attention.py:196-215) / CLIP layers.  HBM-bound: every kernel reads its
+// input once (2-wide / 4-wide vector loads, channel index fastest => fully coalesced rows) and the
+// statistics pass keeps per-thread partials in registers, one shared atomic per channel pair and one
+// fp64 global atomic per (block, group).
+#include "cb_common.cuh"
+
+namespace cb {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> {
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+template <> struct Vec2<__half> {
+    static __device__ __forceinline__ float2 ld(const __half* p) {
+        return __half22float2(*reinterpret_cast<const __half2*>(p));
+    }
+    static __device__ __forceinline__ void st(__half* p, float2 v) {
+        *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y);
+    }
+};
+template <> struct Vec2<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) {
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 v) {
+        *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y);
+    }
+};
+
+__device__ __forceinline__ float silu_grad(float z) {
+    const float s = 1.0f / (1.0f + __expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+}
+
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxPairsPerThread = 8;  // C <= 2*256*8 = 4096
+
+// ---- GroupNorm statistics: ws[(n*G+g)*2 + {0,1}] += {sum, sumsq} (fp64) ---------------------------
+template <typename TX>
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C, int G, int rows_per_block) {
+    __shared__ float s_sum[64], s_sq[64];
+    const int n = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const int cpg = C / G;
+    const int npairs = C >> 1;
+    if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    float a1[kGnMaxPairsPerThread], a2[kGnMaxPairsPerThread];
+#pragma unroll
+    for (int i = 0; i < kGnMaxPairsPerThread; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
+    const TX* xb = x + ((size_t)n * HW) * C;
+    for (int r = r0; r < r1; ++r) {
+        const TX* xr = xb + (size_t)r * C;
+#pragma unroll
+        for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
+            const int pr = threadIdx.x + i * kGnThreads;
+            if (pr < npairs) {
+                const float2 v = Vec2<TX>::ld(xr + 2 * pr);
+                a1[i] += v.x + v.y;
+                a2[i] += v.x * v.x + v.y * v.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
+        const int pr = threadIdx.x + i * kGnThreads;
+        if (pr < npairs) {
+            const int g = (2 * pr) / cpg;
+            atomicAdd(&s_sum[g], a1[i]);
+            atomicAdd(&s_sq[g], a2[i]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    }
+}
+
+// ---- GroupNorm apply: y = act((x-mean)*rstd*gamma+beta) ---------------------------------------------
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const double* __restrict__ ws, float* __restrict__ mean_out,
+                float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act, int rows_per_block) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        const double m = ws[((size_t)n * G + threadIdx.x) * 2] / cnt;
+        double var = ws[((size_t)n * G + threadIdx.x) * 2 + 1] / cnt - m * m;
+        if (var < 0) var = 0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[threadIdx.x] = (float)m;
+        s_rstd[threadIdx.x] = rs;
+        if (blockIdx.x == 0) {
+            mean_out[n * G + threadIdx.x] = (float)m;
+            rstd_out[n * G + threadIdx.x] = rs;
+        }
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const int npairs = C >> 1;
+    const size_t base = ((size_t)n * HW) * C;
+    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
+        const int pr = threadIdx.x + i * kGnThreads;
+        if (pr >= npairs) break;
+        const int c = 2 * pr;
+        const int g = c / cpg;
+        const float m = s_mean[g], rs = s_rstd[g];
+        const float g0 = gamma[c] * rs, g1 = gamma[c + 1] * rs;
+        const float b0 = beta[c] - m * g0, b1 = beta[c + 1] - m * g1;
+        for (int r = r0; r < r1; ++r) {
+            const size_t off = base + (size_t)r * C + c;
+            float2 v = Vec2<TX>::ld(x + off);
+            v.x = v.x * g0 + b0;
+            v.y = v.y * g1 + b1;
+            if (act) { v.x = silu_f(v.x); v.y = silu_f(v.y); }
+            Vec2<TY>::st(y + off, v);
+        }
+    }
+}
+
+// ---- GroupNorm backward statistics: ws += {sum dz*gamma, sum dz*gamma*xhat} ---------------------------
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_stats_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    double* __restrict__ ws, int HW, int C, int G, int act, int rows_per_block) {
+    __shared__ float s_1[64], s_2[64];
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    const int npairs = C >> 1;
+    if (threadIdx.x < 64) { s_1[threadIdx.x] = 0.f; s_2[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const size_t base = ((size_t)n * HW) * C;
+    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
+        const int pr = threadIdx.x + i * kGnThreads;
+        if (pr >= npairs) break;
+        const int c = 2 * pr;
+        const int g = c / cpg;
+        const float m = mean[n * G + g], rs = rstd[n * G + g];
+        const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const size_t off = base + (size_t)r * C + c;
+            const float2 xv = Vec2<TX>::ld(x + off);
+            float2 d = Vec2<TG>::ld(dy + off);
+            const float xh0 = (xv.x - m) * rs, xh1 = (xv.y - m) * rs;
+            if (act) {
+                d.x *= silu_grad(xh0 * ga0 + be0);
+                d.y *= silu_grad(xh1 * ga1 + be1);
+            }
+            const float t0 = d.x * ga0, t1 = d.y * ga1;
+            a1 += t0 + t1;
+            a2 += t0 * xh0 + t1 * xh1;
+        }
+        atomicAdd(&s_1[g], a1);
+        atomicAdd(&s_2[g], a2);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_1[threadIdx.x]);
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_2[threadIdx.x]);
+    }
+}
+
+// ---- GroupNorm backward apply: dx (+)= rstd*(dz*gamma - s1/cnt - xhat*s2/cnt) ----------------------------
+template <typename TX, typename TG, typename TD>
+__global__ void __launch_bounds__(kGnThreads)
+gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const double* __restrict__ ws, TD* __restrict__ dx, int HW, int C, int G, int act,
+                    int accumulate, int rows_per_block) {
+    __shared__ float s_1[64], s_2[64];
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        s_1[threadIdx.x] = (float)(ws[((size_t)n * G + threadIdx.x) * 2] / cnt);
+        s_2[threadIdx.x] = (float)(ws[((size_t)n * G + threadIdx.x) * 2 + 1] / cnt);
+    }
+    __syncthreads();
+    const int npairs = C >> 1;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const size_t base = ((size_t)n * HW) * C;
+    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
+        const int pr = threadIdx.x + i * kGnThreads;
+        if (pr >= npairs) break;
+        const int c = 2 * pr;
+        const int g = c / cpg;
+        const float m = mean[n * G + g], rs = rstd[n * G + g];
+        const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
+        const float m1 = s_1[g], m2 = s_2[g];
+        for (int r = r0; r < r1; ++r) {
+            const size_t off = base + (size_t)r * C + c;
+            const float2 xv = Vec2<TX>::ld(x + off);
+            float2 d = Vec2<TG>::ld(dy + off);
+            const float xh0 = (xv.x - m) * rs, xh1 = (xv.y - m) * rs;
+            if (act) {
+                d.x *= silu_grad(xh0 * ga0 + be0);
+                d.y *= silu_grad(xh1 * ga1 + be1);
+            }
+            float2 o;
+            o.x = rs * (d.x * ga0 - m1 - xh0 * m2);
+            o.y = rs * (d.y * ga1 - m1 - xh1 * m2);
+            if (accumulate) {
+                const float2 p = Vec2<TD>::ld(dx + off);
+                o.x += p.x;
+                o.y += p.y;
+            }
+            Vec2<TD>::st(dx + off, o);
+        }
+    }
+}
+
+// ---- LayerNorm: one warp per row ------------------------------------------------------------------------
+constexpr int kLnMaxPairsPerLane = 32;  // C <= 2048
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(128)
+ln_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C,
+              float eps) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int npairs = C >> 1;
+    const TX* xr = x + (size_t)row * C;
+    float2 v[kLnMaxPairsPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairsPerLane; ++i) {
+        const int pr = lane + i * 32;
+        if (pr < npairs) {
+            v[i] = Vec2<TX>::ld(xr + 2 * pr);
+            s += v[i].x + v[i].y;
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairsPerLane; ++i) {
+        const int pr = lane + i * 32;
+        if (pr < npairs) {
+            const float a = v[i].x - mean, b = v[i].y - mean;
+            q += a * a + b * b;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+    TY* yr = y + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairsPerLane; ++i) {
+        const int pr = lane + i * 32;
+        if (pr < npairs) {
+            const int c = 2 * pr;
+            float2 o;
+            o.x = (v[i].x - mean) * rstd * gamma[c] + beta[c];
+            o.y = (v[i].y - mean) * rstd * gamma[c + 1] + beta[c + 1];
+            Vec2<TY>::st(yr + c, o);
+        }
+    }
+}
+
+template <typename TX, typename TG, typename TD>
+__global__ void __launch_bounds__(128)
+ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ mean, const float* __restrict__ rstd, TD* __restrict__ dx, int M, int C,
+              int accumulate) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int npairs = C >> 1;
+    const float m = mean[row], rs = rstd[row];
+    const TX* xr = x + (size_t)row * C;
+    const TG* dr = dy + (size_t)row * C;
+    float2 xh[kLnMaxPairsPerLane], t[kLnMaxPairsPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairsPerLane; ++i) {
+        const int pr = lane + i * 32;
+        if (pr < npairs) {
+            const int c = 2 * pr;
+            const float2 xv = Vec2<TX>::ld(xr + c);
+            const float2 d = Vec2<TG>::ld(dr + c);
+            xh[i].x = (xv.x - m) * rs;
+            xh[i].y = (xv.y - m) * rs;
+            t[i].x = d.x * gamma[c];
+            t[i].y = d.y * gamma[c + 1];
+            s1 += t[i].x + t[i].y;
+            s2 += t[i].x * xh[i].x + t[i].y * xh[i].y;
+        }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    TD* or_ = dx + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPairsPerLane; ++i) {
+        const int pr = lane + i * 32;
+        if (pr < npairs) {
+            const int c = 2 * pr;
+            float2 o;
+            o.x = rs * (t[i].x - s1 - xh[i].x * s2);
+            o.y = rs * (t[i].y - s1 - xh[i].y * s2);
+            if (accumulate) {
+                const float2 p = Vec2<TD>::ld(or_ + c);
+                o.x += p.x;
+                o.y += p.y;
+            }
+            Vec2<TD>::st(or_ + c, o);
+        }
+    }
+}
+
+static inline int gn_rows_per_block(int HW, int N) {
+    const int target_blocks = 2 * device_sm_count();
+    int per_img = ceil_div(target_blocks, N);
+    if (per_img < 1) per_img = 1;
+    int rpb = ceil_div(HW, per_img);
+    if (rpb < 1) rpb = 1;
+    return rpb;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+#define CB_DISPATCH_2(dtype, T, ...)                                             \
+    if ((dtype) == CB_F32) { using T = float; __VA_ARGS__; }                     \
+    else if ((dtype) == CB_F16) { using T = __half; __VA_ARGS__; }               \
+    else if ((dtype) == CB_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }       \
+    else { cb::set_error("unsupported dtype %d", (int)(dtype)); return CB_ERR_ARG; }
+
+static int gn_check(int N, int HW, int C, int G) {
+    CB_REQUIRE(N > 0 && HW > 0 && C > 0 && G > 0 && G <= 64 && C % G == 0, CB_ERR_ARG, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
+    CB_REQUIRE((C / G) % 2 == 0, CB_ERR_ARG, "groupnorm: channels per group must be even (C=%d G=%d)", C, G);
+    CB_REQUIRE(C <= 2 * kGnThreads * kGnMaxPairsPerThread, CB_ERR_ARG, "groupnorm: C=%d too large", C);
+    return 0;
+}
+
+extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                                int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
+                                double* ws, void* stream) {
+    int rc = gn_check(N, HW, C, G);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
+    const int rpb = gn_rows_per_block(HW, N);
+    dim3 grid(ceil_div(HW, rpb), N);
+    CB_DISPATCH_2(x_dtype, TX, gn_stats_kernel<TX><<<grid, kGnThreads, 0, st>>>((const TX*)x, ws, HW, C, G, rpb));
+    CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
+        gn_apply_kernel<TX, TY><<<grid, kGnThreads, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb)));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                                const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype,
+                                int N, int HW, int C, int G, int act_silu, int accumulate, double* ws, void* stream) {
+    int rc = gn_check(N, HW, C, G);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
+    const int rpb = gn_rows_per_block(HW, N);
+    dim3 grid(ceil_div(HW, rpb), N);
+    CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
+        gn_bwd_stats_kernel<TX, TG><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb)));
+    // dx dtype: f32 or the gradient dtype
+    if (dx_dtype == CB_F32) {
+        CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
+            gn_bwd_apply_kernel<TX, TG, float><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb)));
+    } else {
+        CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
+        CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
+            gn_bwd_apply_kernel<TX, TG, TG><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb)));
+    }
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                                int M, int C, float eps, float* mean_out, float* rstd_out, void* stream) {
+    CB_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && C <= 64 * kLnMaxPairsPerLane, CB_ERR_ARG, "layernorm: bad shape M=%d C=%d", M, C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid(ceil_div(M, 4));
+    CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
+        ln_fwd_kernel<TX, TY><<<grid, 128, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, mean_out, rstd_out, M, C, eps)));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                                const float* mean, const float* rstd, void* dx, int dx_dtype, int M, int C,
+                                int accumulate, void* stream) {
+    CB_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && C <= 64 * kLnMaxPairsPerLane, CB_ERR_ARG, "layernorm_bwd: bad shape M=%d C=%d", M, C);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid(ceil_div(M, 4));
+    if (dx_dtype == CB_F32) {
+        CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
+            ln_bwd_kernel<TX, TG, float><<<grid, 128, 0, st>>>((const TG*)dy, (const TX*)x, gamma, mean, rstd, (float*)dx, M, C, accumulate)));
+    } else {
+        CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "layernorm_bwd: dx dtype must be f32 or equal dy dtype");
+        CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
+            ln_bwd_kernel<TX, TG, TG><<<grid, 128, 0, st>>>((const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, M, C, accumulate)));
+    }
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
