@@ -34,7 +34,8 @@ struct GemmParams {
     int b_tap_rows, flip_taps;
     void* D;
     int d_dtype;
-    long long ldd, d_bs;
+    long long ldd, d_bs, d_bs2;
+    int batch_inner;
     int d_transposed;
     int vec_ok;
     const float* bias;
@@ -42,7 +43,7 @@ struct GemmParams {
     long long ldbias;
     const void* R;
     int r_dtype;
-    long long ldr, r_bs;
+    long long ldr, r_bs, r_bs2;
     float alpha;
     int act;
     unsigned idesc;
@@ -136,7 +137,7 @@ __device__ __forceinline__ void store_any(void* base, int dtype, long long idx, 
 
 // Epilogue for one 32-column chunk held by one thread (one output row).
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], bool row_valid,
-                                               long long grow, long long brow, int col0, int bz) {
+                                               long long grow, long long brow, int col0, long long d_off, long long r_off) {
     if (!row_valid) return;
     const int ncols = min(32, p.N - col0);
     if (ncols <= 0) return;
@@ -160,14 +161,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             }
             if (p.R) {
                 float r[8];
-                const long long ridx = (long long)bz * p.r_bs + grow * p.ldr + col;
+                const long long ridx = r_off + grow * p.ldr + col;
                 if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
                 else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, r);
                 else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += r[j];
             }
-            const long long didx = (long long)bz * p.d_bs + grow * p.ldd + col;
+            const long long didx = d_off + grow * p.ldd + col;
             if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
             else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
             else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
@@ -180,9 +181,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 float v = __uint_as_float(acc[j]) * p.alpha;
                 if (p.bias) v += p.bias[brow * p.ldbias + col];
                 v = apply_act(v, p.act);
-                if (p.R) v += load_any(p.R, p.r_dtype, (long long)bz * p.r_bs + grow * p.ldr + col);
-                const long long didx = p.d_transposed ? ((long long)bz * p.d_bs + (long long)col * p.ldd + grow)
-                                                      : ((long long)bz * p.d_bs + grow * p.ldd + col);
+                if (p.R) v += load_any(p.R, p.r_dtype, r_off + grow * p.ldr + col);
+                const long long didx = p.d_transposed ? (d_off + (long long)col * p.ldd + grow)
+                                                      : (d_off + grow * p.ldd + col);
                 store_any(p.D, p.d_dtype, didx, v);
             }
         }
@@ -208,6 +209,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.x * BN;
     const int m_tile = blockIdx.y;
     const int bz = blockIdx.z;
+    const int zi = bz % p.batch_inner;
+    const int zo = bz / p.batch_inner;
 
     // tile origin
     int m0 = 0, ow0 = 0, oh0 = 0, img0 = 0;
@@ -262,18 +265,18 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, ow0 * p.stride + sx - p.pad_left,
                                 oh0 * p.stride + r - p.pad_top, img0);
                 } else if (A_MN) {
-                    tma_load_4d(a_dst, &tmA, full_bar(s), m0, kc * BK, bz, 0);
-                    tma_load_4d(a_dst + 8192, &tmA, full_bar(s), m0 + 64, kc * BK, bz, 0);
+                    tma_load_4d(a_dst, &tmA, full_bar(s), m0, kc * BK, zi, zo);
+                    tma_load_4d(a_dst + 8192, &tmA, full_bar(s), m0 + 64, kc * BK, zi, zo);
                 } else {
-                    tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, m0, bz, 0);
+                    tma_load_4d(a_dst, &tmA, full_bar(s), kc * BK, m0, zi, zo);
                 }
                 if (B_MN) {
 #pragma unroll
                     for (int j = 0; j < BN / 64; ++j)
-                        tma_load_3d(b_dst + j * 8192, &tmB, full_bar(s), n0 + j * 64,
-                                    tap_b * p.b_tap_rows + kc * BK, bz);
+                        tma_load_4d(b_dst + j * 8192, &tmB, full_bar(s), n0 + j * 64,
+                                    tap_b * p.b_tap_rows + kc * BK, zi, zo);
                 } else {
-                    tma_load_3d(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + n0, bz);
+                    tma_load_4d(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + n0, zi, zo);
                 }
             }
         }
@@ -320,6 +323,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             row_valid = grow < p.M;
         }
         const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
+        const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
+        const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -327,7 +332,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t acc[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
             tmem_ld_wait();
-            epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, bz);
+            epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
         }
     }
 
@@ -420,8 +425,12 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     CB_REQUIRE(!(d.conv && a_mn), CB_ERR_ARG, "cb_gemm: conv mode needs K-major A (NHWC)");
     CB_REQUIRE(!(a_mn && !b_mn), CB_ERR_ARG, "cb_gemm: (A MN-major, B K-major) is not instantiated");
 
+    const int b_in = d.batch_inner > 0 ? d.batch_inner : d.batch;
+    CB_REQUIRE(d.batch % b_in == 0, CB_ERR_ARG, "cb_gemm: batch %d not a multiple of batch_inner %d", d.batch, b_in);
+    const int b_out = d.batch / b_in;
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    p.batch_inner = b_in;
     p.N = d.N;
     p.K = d.K;
     p.kchunks = ceil_div(d.K, BK);
@@ -476,17 +485,19 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         p.M = d.M;
         m_tiles = ceil_div(d.M, BM);
         p.a_bytes = BM * BK * es;
-        const uint64_t bs = (uint64_t)(d.batch > 1 ? d.a_batch_stride : (a_mn ? d.lda * (int64_t)d.K : d.lda * (int64_t)d.M));
+        const uint64_t dflt = (uint64_t)(a_mn ? d.lda * (int64_t)d.K : d.lda * (int64_t)d.M);
+        const uint64_t bs = (uint64_t)(b_in > 1 ? d.a_batch_stride : dflt);
+        const uint64_t bs2 = (uint64_t)(b_out > 1 ? d.a_batch_stride2 : dflt);
         if (a_mn) {
-            uint64_t dims[4] = {(uint64_t)d.M, (uint64_t)d.K, (uint64_t)d.batch, 1};
-            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs * es};
+            uint64_t dims[4] = {(uint64_t)d.M, (uint64_t)d.K, (uint64_t)b_in, (uint64_t)b_out};
+            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs2 * es};
             uint32_t box[4] = {64, BK, 1, 1};
             uint32_t estr[4] = {1, 1, 1, 1};
             int rc = make_tmap(&tA, d.ab_dtype, 4, d.A, dims, strides, box, estr);
             if (rc) return rc;
         } else {
-            uint64_t dims[4] = {(uint64_t)d.K, (uint64_t)d.M, (uint64_t)d.batch, 1};
-            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs * es};
+            uint64_t dims[4] = {(uint64_t)d.K, (uint64_t)d.M, (uint64_t)b_in, (uint64_t)b_out};
+            uint64_t strides[3] = {(uint64_t)d.lda * es, bs * es, bs2 * es};
             uint32_t box[4] = {BK, BM, 1, 1};
             uint32_t estr[4] = {1, 1, 1, 1};
             int rc = make_tmap(&tA, d.ab_dtype, 4, d.A, dims, strides, box, estr);
@@ -498,19 +509,21 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.b_bytes = (unsigned)BN * BK * es;
     {
         const uint64_t brows_total = (uint64_t)(d.conv ? (int64_t)p.taps * d.b_tap_rows : (b_mn ? d.K : d.N));
-        const uint64_t bs = (uint64_t)(d.batch > 1 ? d.b_batch_stride : d.ldb * (int64_t)brows_total);
-        uint32_t estr[3] = {1, 1, 1};
+        const uint64_t dflt = (uint64_t)(d.ldb * (int64_t)brows_total);
+        const uint64_t bs = (uint64_t)(b_in > 1 ? d.b_batch_stride : dflt);
+        const uint64_t bs2 = (uint64_t)(b_out > 1 ? d.b_batch_stride2 : dflt);
+        uint32_t estr[4] = {1, 1, 1, 1};
         if (b_mn) {
-            uint64_t dims[3] = {(uint64_t)d.N, brows_total, (uint64_t)d.batch};
-            uint64_t strides[2] = {(uint64_t)d.ldb * es, bs * es};
-            uint32_t box[3] = {64, BK, 1};
-            int rc = make_tmap(&tB, d.ab_dtype, 3, d.B, dims, strides, box, estr);
+            uint64_t dims[4] = {(uint64_t)d.N, brows_total, (uint64_t)b_in, (uint64_t)b_out};
+            uint64_t strides[3] = {(uint64_t)d.ldb * es, bs * es, bs2 * es};
+            uint32_t box[4] = {64, BK, 1, 1};
+            int rc = make_tmap(&tB, d.ab_dtype, 4, d.B, dims, strides, box, estr);
             if (rc) return rc;
         } else {
-            uint64_t dims[3] = {(uint64_t)d.K, brows_total, (uint64_t)d.batch};
-            uint64_t strides[2] = {(uint64_t)d.ldb * es, bs * es};
-            uint32_t box[3] = {BK, (uint32_t)BN, 1};
-            int rc = make_tmap(&tB, d.ab_dtype, 3, d.B, dims, strides, box, estr);
+            uint64_t dims[4] = {(uint64_t)d.K, brows_total, (uint64_t)b_in, (uint64_t)b_out};
+            uint64_t strides[3] = {(uint64_t)d.ldb * es, bs * es, bs2 * es};
+            uint32_t box[4] = {BK, (uint32_t)BN, 1, 1};
+            int rc = make_tmap(&tB, d.ab_dtype, 4, d.B, dims, strides, box, estr);
             if (rc) return rc;
         }
     }
@@ -519,6 +532,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.d_dtype = d.d_dtype;
     p.ldd = d.ldd;
     p.d_bs = d.d_batch_stride;
+    p.d_bs2 = d.d_batch_stride2;
     p.d_transposed = d.d_transposed;
     p.bias = d.bias;
     p.bias_row_div = d.bias_row_div;
@@ -527,17 +541,18 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.r_dtype = d.r_dtype;
     p.ldr = d.ldr;
     p.r_bs = d.r_batch_stride;
+    p.r_bs2 = d.r_batch_stride2;
     p.alpha = d.alpha;
     p.act = d.act;
     p.idesc = umma_idesc_f16(BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
     {
         const int des = d.d_dtype == CB_F32 ? 4 : 2;
         bool ok = ((reinterpret_cast<uintptr_t>(d.D) & 15u) == 0) && ((d.ldd * des) % 16 == 0) &&
-                  ((d.d_batch_stride * des) % 16 == 0);
+                  ((d.d_batch_stride * des) % 16 == 0) && ((d.d_batch_stride2 * des) % 16 == 0);
         if (d.R) {
             const int res = d.r_dtype == CB_F32 ? 4 : 2;
             ok = ok && ((reinterpret_cast<uintptr_t>(d.R) & 15u) == 0) && ((d.ldr * res) % 16 == 0) &&
-                 ((d.r_batch_stride * res) % 16 == 0);
+                 ((d.r_batch_stride * res) % 16 == 0) && ((d.r_batch_stride2 * res) % 16 == 0);
         }
         if (d.bias) ok = ok && ((reinterpret_cast<uintptr_t>(d.bias) & 15u) == 0) && ((d.ldbias * 4) % 16 == 0);
         p.vec_ok = ok ? 1 : 0;

@@ -34,6 +34,9 @@ class GemmDesc(ctypes.Structure):
         ("R", ctypes.c_void_p), ("r_dtype", ctypes.c_int32), ("ldr", ctypes.c_int64),
         ("r_batch_stride", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("act", ctypes.c_int32),
+        ("batch_inner", ctypes.c_int32),
+        ("a_batch_stride2", ctypes.c_int64), ("b_batch_stride2", ctypes.c_int64),
+        ("d_batch_stride2", ctypes.c_int64), ("r_batch_stride2", ctypes.c_int64),
     ]
 
 

@@ -1,0 +1,366 @@
+"""Typed launchers over the C-ABI: torch tensors are only storage + stream plumbing here.
+
+Layout conventions (see include/celebbasis_b200.h): activations are 2-D channels-last matrices
+[rows][C] (rows = N*H*W pixels in raster order, or tokens).  All math happens inside the .so.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+from .lib import (CB_ACT_GELU, CB_ACT_NONE, CB_ACT_QUICK_GELU, CB_ACT_SILU, CB_BF16, CB_F16, CB_F32,
+                  CB_MAJOR_K, CB_MAJOR_MN, GemmDesc)
+
+_DT = {torch.float16: CB_F16, torch.bfloat16: CB_BF16, torch.float32: CB_F32}
+
+
+def _dt(t):
+    return _DT[t.dtype]
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _L():
+    return _lib.load()
+
+
+class Geo:
+    """Image geometry of a channels-last activation matrix."""
+    __slots__ = ("n", "h", "w")
+
+    def __init__(self, n, h, w):
+        self.n, self.h, self.w = int(n), int(h), int(w)
+
+    @property
+    def rows(self):
+        return self.n * self.h * self.w
+
+    @property
+    def hw(self):
+        return self.h * self.w
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (host side, once per checkpoint load)
+# ------------------------------------------------------------------------------------------------
+def pack_conv_weight(w, dtype, cin_pad=None, cout_pad=None):
+    """[Cout][Cin][kh][kw] -> [kh*kw][Cout_pad][Cin_pad] (tap-major, Cin contiguous), as one 2-D matrix."""
+    cout, cin, kh, kw = w.shape
+    cin_pad = cin_pad or cin
+    cout_pad = cout_pad or cout
+    out = torch.zeros(kh * kw, cout_pad, cin_pad, dtype=dtype, device=w.device)
+    out[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(dtype)
+    return out.view(kh * kw * cout_pad, cin_pad).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM family
+# ------------------------------------------------------------------------------------------------
+def gemm_raw(A, B, D, **kw):
+    from . import raw
+    return raw.gemm(A, B, D, **kw)
+
+
+def linear(x, w, bias=None, *, out_dtype=None, out=None, act=CB_ACT_NONE, residual=None, alpha=1.0):
+    """y[M][N] = act(alpha * x[M][K] @ w[N][K]^T + bias) + residual."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype or x.dtype, device=x.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = M, N, K, 1, _dt(x)
+    d.A, d.lda, d.a_major = x.data_ptr(), K, CB_MAJOR_K
+    d.B, d.ldb, d.b_major = w.data_ptr(), K, CB_MAJOR_K
+    d.D, d.d_dtype, d.ldd = out.data_ptr(), _dt(out), out.stride(0)
+    if bias is not None:
+        d.bias, d.bias_row_div, d.ldbias = bias.data_ptr(), 0, N
+    if residual is not None:
+        d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
+    d.alpha, d.act = alpha, act
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(linear)")
+    return out
+
+
+def linear_dgrad(dy, w, *, out_dtype=None, out=None, residual=None, alpha=1.0):
+    """dx[M][K] = alpha * dy[M][N] @ w[N][K] (+ residual): the forward weight is read MN-major."""
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N and dy.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty(M, K, dtype=out_dtype or dy.dtype, device=dy.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = M, K, N, 1, _dt(dy)
+    d.A, d.lda, d.a_major = dy.data_ptr(), N, CB_MAJOR_K
+    d.B, d.ldb, d.b_major = w.data_ptr(), K, CB_MAJOR_MN
+    d.D, d.d_dtype, d.ldd = out.data_ptr(), _dt(out), out.stride(0)
+    if residual is not None:
+        d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
+    d.alpha = alpha
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(linear_dgrad)")
+    return out
+
+
+def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1), out_dtype=None, out=None,
+           residual=None, bias_per_image=False, ldbias=None, act=CB_ACT_NONE, cout_rows=None):
+    """Implicit-GEMM convolution on an NHWC activation matrix.
+
+    x: [geo.rows][Cin]; wpack: [k*k*cout_rows][Cin] from pack_conv_weight; pad=(top,bottom,left,right).
+    Returns (y [n*oh*ow][cout], Geo(n,oh,ow)).
+    """
+    cin = x.shape[1]
+    assert x.shape[0] == geo.rows and x.is_contiguous()
+    cout_rows = cout_rows or cout
+    oh = (geo.h + pad[0] + pad[1] - ksize) // stride + 1
+    ow = (geo.w + pad[2] + pad[3] - ksize) // stride + 1
+    ogeo = Geo(geo.n, oh, ow)
+    if out is None:
+        out = torch.empty(ogeo.rows, cout, dtype=out_dtype or x.dtype, device=x.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = ogeo.rows, cout, cin, 1, _dt(x)
+    d.A, d.lda, d.a_major = x.data_ptr(), cin, CB_MAJOR_K
+    d.B, d.ldb, d.b_major = wpack.data_ptr(), wpack.shape[1], CB_MAJOR_K
+    d.conv = 1
+    d.img_n, d.img_h, d.img_w, d.out_h, d.out_w = geo.n, geo.h, geo.w, oh, ow
+    d.kh = d.kw = ksize
+    d.stride, d.pad_top, d.pad_left = stride, pad[0], pad[2]
+    d.b_tap_rows, d.flip_taps = cout_rows, 0
+    d.D, d.d_dtype, d.ldd = out.data_ptr(), _dt(out), out.stride(0)
+    if bias is not None:
+        d.bias = bias.data_ptr()
+        d.bias_row_div = oh * ow if bias_per_image else 0
+        d.ldbias = ldbias if ldbias is not None else cout
+    if residual is not None:
+        d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
+    d.alpha, d.act = 1.0, act
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(conv2d)")
+    return out, ogeo
+
+
+def conv2d_dgrad(dy, ogeo, wpack, cin, *, ksize=3, pad=(1, 1, 1, 1), out_dtype=None, out=None, residual=None,
+                 cout_rows=None):
+    """dx of a stride-1 convolution: taps flipped, forward weight pack read MN-major (K = Cout)."""
+    cout = dy.shape[1]
+    assert dy.shape[0] == ogeo.rows and dy.is_contiguous()
+    cout_rows = cout_rows or cout
+    # forward: oh = h + pt + pb - k + 1  =>  input size
+    h = ogeo.h - pad[0] - pad[1] + ksize - 1
+    w = ogeo.w - pad[2] - pad[3] + ksize - 1
+    geo = Geo(ogeo.n, h, w)
+    if out is None:
+        out = torch.empty(geo.rows, cin, dtype=out_dtype or dy.dtype, device=dy.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = geo.rows, cin, cout, 1, _dt(dy)
+    d.A, d.lda, d.a_major = dy.data_ptr(), cout, CB_MAJOR_K
+    d.B, d.ldb, d.b_major = wpack.data_ptr(), wpack.shape[1], CB_MAJOR_MN
+    d.conv = 1
+    d.img_n, d.img_h, d.img_w, d.out_h, d.out_w = ogeo.n, ogeo.h, ogeo.w, h, w
+    d.kh = d.kw = ksize
+    d.stride, d.pad_top, d.pad_left = 1, ksize - 1 - pad[0], ksize - 1 - pad[2]
+    d.b_tap_rows, d.flip_taps = cout_rows, 1
+    d.D, d.d_dtype, d.ldd = out.data_ptr(), _dt(out), out.stride(0)
+    if residual is not None:
+        d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
+    d.alpha = 1.0
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(conv2d_dgrad)")
+    return out, geo
+
+
+def bmm(A, B, D, *, M, N, K, heads, images=1, lda, ldb, ldd, a_hs, b_hs, d_hs, a_is=0, b_is=0, d_is=0,
+        a_major=CB_MAJOR_K, b_major=CB_MAJOR_K, alpha=1.0):
+    """Two-level batched GEMM over (image, head); *_hs = head stride, *_is = image stride (elements)."""
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = M, N, K, heads * images, _dt(A)
+    d.batch_inner = heads
+    d.A, d.lda, d.a_batch_stride, d.a_batch_stride2, d.a_major = A.data_ptr(), lda, a_hs, a_is, a_major
+    d.B, d.ldb, d.b_batch_stride, d.b_batch_stride2, d.b_major = B.data_ptr(), ldb, b_hs, b_is, b_major
+    d.D, d.d_dtype, d.ldd, d.d_batch_stride, d.d_batch_stride2 = D.data_ptr(), _dt(D), ldd, d_hs, d_is
+    d.alpha = alpha
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(bmm)")
+    return D
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+class NormStats:
+    __slots__ = ("mean", "rstd")
+
+    def __init__(self, mean, rstd):
+        self.mean, self.rstd = mean, rstd
+
+
+_ws_cache = {}
+
+
+def _gn_ws(device, n):
+    key = (device, n)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(n, dtype=torch.float64, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=torch.float16, want_stats=True):
+    C = x.shape[1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    mean = torch.empty(geo.n * groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty(2 * geo.n * groups, dtype=torch.float64, device=x.device)
+    _lib.check(_L().cb_groupnorm_fwd(_p(x), _dt(x), _p(y), _dt(y), _p(gamma), _p(beta), geo.n, geo.hw, C, groups,
+                                     eps, 1 if silu else 0, _p(mean), _p(rstd), _p(ws), _st()), "cb_groupnorm_fwd")
+    return y, NormStats(mean, rstd)
+
+
+def groupnorm_bwd(dy, x, geo, gamma, beta, stats, *, groups=32, silu=False, dx=None, accumulate=False,
+                  dx_dtype=torch.float32):
+    C = x.shape[1]
+    if dx is None:
+        dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+        accumulate = False
+    ws = torch.empty(2 * geo.n * groups, dtype=torch.float64, device=x.device)
+    _lib.check(_L().cb_groupnorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(beta), _p(stats.mean),
+                                     _p(stats.rstd), _p(dx), _dt(dx), geo.n, geo.hw, C, groups, 1 if silu else 0,
+                                     1 if accumulate else 0, _p(ws), _st()), "cb_groupnorm_bwd")
+    return dx
+
+
+def layernorm(x, gamma, beta, *, eps=1e-5, out_dtype=torch.float16):
+    M, C = x.shape
+    y = torch.empty(M, C, dtype=out_dtype, device=x.device)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    _lib.check(_L().cb_layernorm_fwd(_p(x), _dt(x), _p(y), _dt(y), _p(gamma), _p(beta), M, C, eps, _p(mean),
+                                     _p(rstd), _st()), "cb_layernorm_fwd")
+    return y, NormStats(mean, rstd)
+
+
+def layernorm_bwd(dy, x, gamma, stats, *, dx=None, accumulate=False, dx_dtype=torch.float32):
+    M, C = x.shape
+    if dx is None:
+        dx = torch.empty(M, C, dtype=dx_dtype, device=x.device)
+        accumulate = False
+    _lib.check(_L().cb_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(stats.mean), _p(stats.rstd),
+                                     _p(dx), _dt(dx), M, C, 1 if accumulate else 0, _st()), "cb_layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# pointwise
+# ------------------------------------------------------------------------------------------------
+def axpby(x, a=1.0, y=None, b=0.0, *, out=None, out_dtype=None):
+    """out = a*x + b*y on 2-D (possibly row-strided) views; also the cast / strided-copy kernel."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=out_dtype or x.dtype, device=x.device)
+    assert out.stride(1) == 1 and (y is None or y.stride(1) == 1)
+    _lib.check(_L().cb_axpby2d(_p(x), _dt(x), x.stride(0), a, _p(y), _dt(y) if y is not None else 0,
+                               y.stride(0) if y is not None else 0, b, _p(out), _dt(out), out.stride(0), rows, cols,
+                               _st()), "cb_axpby2d")
+    return out
+
+
+def cast(x, dtype, scale=1.0):
+    return axpby(x, scale, out_dtype=dtype)
+
+
+def act_fwd(x, act, out_dtype=None):
+    y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    _lib.check(_L().cb_act_fwd(_p(x), _dt(x), _p(y), _dt(y), x.numel(), act, _st()), "cb_act_fwd")
+    return y
+
+
+def act_bwd(dy, x, act, out_dtype=None):
+    dx = torch.empty(x.shape, dtype=out_dtype or dy.dtype, device=x.device)
+    _lib.check(_L().cb_act_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(dx), _dt(dx), x.numel(), act, _st()), "cb_act_bwd")
+    return dx
+
+
+def geglu(x):
+    M, F2 = x.shape
+    y = torch.empty(M, F2 // 2, dtype=x.dtype, device=x.device)
+    _lib.check(_L().cb_geglu_fwd(_p(x), _p(y), _dt(x), M, F2 // 2, _st()), "cb_geglu_fwd")
+    return y
+
+
+def geglu_bwd(dy, x):
+    M, F2 = x.shape
+    dx = torch.empty(M, F2, dtype=dy.dtype, device=x.device)
+    _lib.check(_L().cb_geglu_bwd(_p(dy), _p(x), _p(dx), _dt(x), _dt(dy), M, F2 // 2, _st()), "cb_geglu_bwd")
+    return dx
+
+
+def softmax_(s, rows, ncols, ld, causal_period=0):
+    """In-place row softmax over the first ncols of each ld-wide row; pad columns are zeroed."""
+    _lib.check(_L().cb_softmax_fwd(_p(s), _p(s), _dt(s), rows, ncols, ld, causal_period, _st()), "cb_softmax_fwd")
+    return s
+
+
+def softmax_bwd_(dp, p, rows, ncols, ld):
+    """In-place: dp <- p * (dp - sum(dp*p))."""
+    _lib.check(_L().cb_softmax_bwd(_p(dp), _p(p), _p(dp), _dt(p), _dt(dp), rows, ncols, ld, _st()), "cb_softmax_bwd")
+    return dp
+
+
+def upsample2x(x, geo):
+    C = x.shape[1]
+    y = torch.empty(4 * geo.rows, C, dtype=x.dtype, device=x.device)
+    _lib.check(_L().cb_upsample2x_fwd(_p(x), _p(y), _dt(x), geo.n, geo.h, geo.w, C, _st()), "cb_upsample2x_fwd")
+    return y, Geo(geo.n, 2 * geo.h, 2 * geo.w)
+
+
+def upsample2x_bwd(dy, geo, *, dx=None, accumulate=False, dx_dtype=None):
+    """geo = geometry of the (smaller) forward input."""
+    C = dy.shape[1]
+    if dx is None:
+        dx = torch.empty(geo.rows, C, dtype=dx_dtype or dy.dtype, device=dy.device)
+        accumulate = False
+    _lib.check(_L().cb_upsample2x_bwd(_p(dy), _dt(dy), _p(dx), _dt(dx), geo.n, geo.h, geo.w, C,
+                                      1 if accumulate else 0, _st()), "cb_upsample2x_bwd")
+    return dx
+
+
+def zero_insert2x(dy, geo):
+    C = dy.shape[1]
+    z = torch.empty(4 * geo.rows, C, dtype=dy.dtype, device=dy.device)
+    _lib.check(_L().cb_zero_insert2x(_p(dy), _p(z), _dt(dy), geo.n, geo.h, geo.w, C, _st()), "cb_zero_insert2x")
+    return z, Geo(geo.n, 2 * geo.h, 2 * geo.w)
+
+
+def nchw_to_nhwc(x, cpad, dtype):
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(n * h * w, cpad, dtype=dtype, device=x.device)
+    _lib.check(_L().cb_nchw_to_nhwc(_p(x), _p(y), _dt(y), n, c, h * w, cpad, _st()), "cb_nchw_to_nhwc")
+    return y, Geo(n, h, w)
+
+
+def nhwc_to_nchw(x, geo, c):
+    y = torch.empty(geo.n, c, geo.h, geo.w, dtype=torch.float32, device=x.device)
+    _lib.check(_L().cb_nhwc_to_nchw(_p(x), _dt(x), _p(y), geo.n, c, geo.hw, x.shape[1], _st()), "cb_nhwc_to_nchw")
+    return y
+
+
+def mse_fwd_bwd(pred, target, gscale=1.0, want_grad=True):
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    _lib.check(_L().cb_mse_fwd_bwd(_p(pred), _p(target), _p(loss), _p(grad), pred.numel(), gscale, _st()),
+               "cb_mse_fwd_bwd")
+    return loss, grad
+
+
+def timestep_embedding(t, dim, dtype=torch.float16, max_period=10000.0):
+    assert t.dtype == torch.int64
+    out = torch.empty(t.shape[0], dim, dtype=dtype, device=t.device)
+    _lib.check(_L().cb_timestep_embedding(_p(t), _p(out), _dt(out), t.shape[0], dim, max_period, _st()),
+               "cb_timestep_embedding")
+    return out

@@ -1,0 +1,404 @@
+"""SD-v1 UNet forward + activation-gradient backward on the sm_100a kernels.
+
+This is the executor behind ldm.modules.diffusionmodules.openaimodel.UNetModel in the host mirror.
+It follows the reference's module graph exactly (openaimodel.py:413-742 UNetModel, :163-275 ResBlock,
+:91-160 Up/Downsample; attention.py:152-261 CrossAttention/BasicTransformerBlock/SpatialTransformer)
+but runs it as an explicit tape of kernel launches:
+
+  * activations are channels-last matrices [N*H*W][C]; the residual stream, norm inputs and block
+    outputs stay fp32, every tensor-core operand is fp16 (or bf16), accumulation is fp32 in TMEM;
+  * all 22 ResBlock `emb_layers` linears are one GEMM per step whose output slice is the per-image
+    bias of that block's first conv (fused in the conv epilogue together with the conv bias);
+  * q/k/v (self) and k/v (cross) projections are single GEMMs over concatenated weights;
+  * backward computes only what the reference's autograd needs with frozen weights
+    (SURVEY.md §8 a29): activation gradients down to d(context); no weight gradients, no d(emb).
+    Gradients are carried fp16 with a static loss scale; residual-stream gradients are fp32.
+"""
+import math
+
+import torch
+
+from . import ops
+from .lib import CB_ACT_NONE, CB_ACT_SILU, CB_MAJOR_K, CB_MAJOR_MN
+from .ops import Geo
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class _Attn:
+    """softmax(q k^T * scale) v for (image, head) batches; probabilities are kept for backward."""
+
+    @staticmethod
+    def fwd(q, k, v, *, images, heads, dh, nq, nk, scale, out, causal=False):
+        ldp = _round_up(nk, 8)
+        P = torch.empty(images * heads * nq, ldp, dtype=q.dtype, device=q.device)
+        ops.bmm(q, k, P, M=nq, N=nk, K=dh, heads=heads, images=images, lda=q.stride(0), ldb=k.stride(0), ldd=ldp,
+                a_hs=dh, b_hs=dh, d_hs=nq * ldp, a_is=nq * q.stride(0), b_is=nk * k.stride(0),
+                d_is=heads * nq * ldp, alpha=scale)
+        ops.softmax_(P, images * heads * nq, nk, ldp, nq if causal else 0)
+        ops.bmm(P, v, out, M=nq, N=dh, K=nk, heads=heads, images=images, lda=ldp, ldb=v.stride(0),
+                ldd=out.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nk * v.stride(0),
+                d_is=nq * out.stride(0), b_major=CB_MAJOR_MN)
+        return P
+
+    @staticmethod
+    def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv):
+        ldp = P.shape[1]
+        dP = torch.empty_like(P)
+        # dP = dO V^T
+        ops.bmm(dO, v, dP, M=nq, N=nk, K=dh, heads=heads, images=images, lda=dO.stride(0), ldb=v.stride(0), ldd=ldp,
+                a_hs=dh, b_hs=dh, d_hs=nq * ldp, a_is=nq * dO.stride(0), b_is=nk * v.stride(0),
+                d_is=heads * nq * ldp)
+        # dV = P^T dO   (both operands read MN-major straight from their forward layouts)
+        ops.bmm(P, dO, dv, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=dO.stride(0),
+                ldd=dv.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * dO.stride(0),
+                d_is=nk * dv.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+        ops.softmax_bwd_(dP, P, images * heads * nq, nk, ldp)  # dP <- dS
+        # dQ = scale * dS K
+        ops.bmm(dP, k, dq, M=nq, N=dh, K=nk, heads=heads, images=images, lda=ldp, ldb=k.stride(0),
+                ldd=dq.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nk * k.stride(0),
+                d_is=nq * dq.stride(0), b_major=CB_MAJOR_MN, alpha=scale)
+        # dK = scale * dS^T Q
+        ops.bmm(dP, q, dk, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=q.stride(0),
+                ldd=dk.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * q.stride(0),
+                d_is=nk * dk.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN, alpha=scale)
+
+
+class UNetEngine:
+    def __init__(self, cfg, state_dict, device, dtype=torch.float16, loss_scale=1024.0):
+        self.cfg = dict(cfg)
+        self.dev = torch.device(device)
+        self.dt = dtype
+        self.loss_scale = float(loss_scale)
+        self.mc = cfg["model_channels"]
+        self.heads = cfg["num_heads"]
+        self.ctx_dim = cfg["context_dim"]
+        self.in_ch = cfg["in_channels"]
+        self.out_ch = cfg["out_channels"]
+        self.in_pad = _round_up(self.in_ch, 8)
+        self.out_pad = 16
+        self._build(state_dict)
+        self.tape = None
+
+    # ------------------------------------------------------------------------------------------
+    # weight preparation
+    # ------------------------------------------------------------------------------------------
+    def _w16(self, t):
+        return t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+
+    def _f32(self, t):
+        return t.detach().to(self.dev, torch.float32).contiguous()
+
+    def _build(self, sd):
+        cfg = self.cfg
+        mc, mult = self.mc, cfg["channel_mult"]
+        nres = cfg["num_res_blocks"]
+        attn_res = set(cfg["attention_resolutions"])
+        g = lambda k: sd[k]
+
+        self.te0_w, self.te0_b = self._w16(g("time_embed.0.weight")), self._f32(g("time_embed.0.bias"))
+        self.te2_w, self.te2_b = self._w16(g("time_embed.2.weight")), self._f32(g("time_embed.2.bias"))
+
+        emb_ws, emb_bs = [], []
+        self._emb_off = 0
+
+        def res(prefix, cin, cout):
+            w = {"kind": "res", "cin": cin, "cout": cout}
+            w["g1"], w["b1"] = self._f32(g(prefix + "in_layers.0.weight")), self._f32(g(prefix + "in_layers.0.bias"))
+            w["w1"] = ops.pack_conv_weight(g(prefix + "in_layers.2.weight").to(self.dev), self.dt)
+            emb_ws.append(g(prefix + "emb_layers.1.weight"))
+            emb_bs.append(g(prefix + "emb_layers.1.bias") + g(prefix + "in_layers.2.bias"))
+            w["emb_off"] = self._emb_off
+            self._emb_off += cout
+            w["g2"], w["b2"] = self._f32(g(prefix + "out_layers.0.weight")), self._f32(g(prefix + "out_layers.0.bias"))
+            w["w2"] = ops.pack_conv_weight(g(prefix + "out_layers.3.weight").to(self.dev), self.dt)
+            w["bias2"] = self._f32(g(prefix + "out_layers.3.bias"))
+            if cin != cout:
+                w["ws"] = self._w16(g(prefix + "skip_connection.weight").reshape(cout, cin))
+                w["bs"] = self._f32(g(prefix + "skip_connection.bias"))
+            else:
+                w["ws"] = None
+            return w
+
+        def xf(prefix, c):
+            w = {"kind": "xf", "c": c, "dh": c // self.heads}
+            w["gn"], w["bn"] = self._f32(g(prefix + "norm.weight")), self._f32(g(prefix + "norm.bias"))
+            w["wpi"], w["bpi"] = self._w16(g(prefix + "proj_in.weight").reshape(c, c)), self._f32(g(prefix + "proj_in.bias"))
+            tb = prefix + "transformer_blocks.0."
+            for i in (1, 2, 3):
+                w[f"ln{i}g"], w[f"ln{i}b"] = self._f32(g(tb + f"norm{i}.weight")), self._f32(g(tb + f"norm{i}.bias"))
+            w["wqkv"] = self._w16(torch.cat([g(tb + "attn1.to_q.weight"), g(tb + "attn1.to_k.weight"),
+                                             g(tb + "attn1.to_v.weight")], 0))
+            w["wo1"], w["bo1"] = self._w16(g(tb + "attn1.to_out.0.weight")), self._f32(g(tb + "attn1.to_out.0.bias"))
+            w["wq2"] = self._w16(g(tb + "attn2.to_q.weight"))
+            w["wkv2"] = self._w16(torch.cat([g(tb + "attn2.to_k.weight"), g(tb + "attn2.to_v.weight")], 0))
+            w["wo2"], w["bo2"] = self._w16(g(tb + "attn2.to_out.0.weight")), self._f32(g(tb + "attn2.to_out.0.bias"))
+            w["wff1"], w["bff1"] = self._w16(g(tb + "ff.net.0.proj.weight")), self._f32(g(tb + "ff.net.0.proj.bias"))
+            w["wff2"], w["bff2"] = self._w16(g(tb + "ff.net.2.weight")), self._f32(g(tb + "ff.net.2.bias"))
+            w["wpo"], w["bpo"] = self._w16(g(prefix + "proj_out.weight").reshape(c, c)), self._f32(g(prefix + "proj_out.bias"))
+            return w
+
+        def resample(kind, prefix, c):
+            key = prefix + ("op." if kind == "down" else "conv.")
+            return {"kind": kind, "c": c, "w": ops.pack_conv_weight(g(key + "weight").to(self.dev), self.dt),
+                    "b": self._f32(g(key + "bias"))}
+
+        # stem
+        self.stem_w = ops.pack_conv_weight(g("input_blocks.0.0.weight").to(self.dev), self.dt, cin_pad=self.in_pad)
+        self.stem_b = self._f32(g("input_blocks.0.0.bias"))
+
+        self.input_blocks = []   # list of layer lists (block 0 = stem handled separately)
+        chans = [mc]
+        ch, ds, idx = mc, 1, 1
+        for level, m in enumerate(mult):
+            for _ in range(nres):
+                layers = [res(f"input_blocks.{idx}.0.", ch, m * mc)]
+                ch = m * mc
+                if ds in attn_res:
+                    layers.append(xf(f"input_blocks.{idx}.1.", ch))
+                self.input_blocks.append(layers)
+                chans.append(ch)
+                idx += 1
+            if level != len(mult) - 1:
+                self.input_blocks.append([resample("down", f"input_blocks.{idx}.0.", ch)])
+                chans.append(ch)
+                idx += 1
+                ds *= 2
+        self.middle = [res("middle_block.0.", ch, ch), xf("middle_block.1.", ch), res("middle_block.2.", ch, ch)]
+        self.output_blocks = []
+        idx = 0
+        for level, m in list(enumerate(mult))[::-1]:
+            for i in range(nres + 1):
+                ich = chans.pop()
+                layers = [res(f"output_blocks.{idx}.0.", ch + ich, mc * m)]
+                ch = mc * m
+                if ds in attn_res:
+                    layers.append(xf(f"output_blocks.{idx}.1.", ch))
+                if level and i == nres:
+                    layers.append(resample("up", f"output_blocks.{idx}.{len(layers)}.", ch))
+                    ds //= 2
+                self.output_blocks.append(layers)
+                idx += 1
+        # head
+        self.out_g, self.out_b = self._f32(g("out.0.weight")), self._f32(g("out.0.bias"))
+        self.out_w = ops.pack_conv_weight(g("out.2.weight").to(self.dev), self.dt, cout_pad=self.out_pad)
+        ob = torch.zeros(self.out_pad, dtype=torch.float32, device=self.dev)
+        ob[: self.out_ch] = self._f32(g("out.2.bias"))
+        self.out_bias = ob
+        # all ResBlock timestep projections as one GEMM
+        self.emb_w = self._w16(torch.cat(emb_ws, 0))
+        self.emb_b = self._f32(torch.cat(emb_bs, 0))
+        self.emb_total = self._emb_off
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _res_fwd(self, w, x, geo, emb_all, tape):
+        cout = w["cout"]
+        a16, st1 = ops.groupnorm(x, geo, w["g1"], w["b1"], eps=1e-5, silu=True, out_dtype=self.dt)
+        bias1 = emb_all[:, w["emb_off"]: w["emb_off"] + cout]
+        h16, _ = ops.conv2d(a16, geo, w["w1"], cout, bias=bias1, bias_per_image=True, ldbias=emb_all.stride(0),
+                            out_dtype=self.dt)
+        b16, st2 = ops.groupnorm(h16, geo, w["g2"], w["b2"], eps=1e-5, silu=True, out_dtype=self.dt)
+        if w["ws"] is None:
+            resid = x
+        else:
+            resid = ops.linear(ops.cast(x, self.dt), w["ws"], w["bs"], out_dtype=torch.float32)
+        out, _ = ops.conv2d(b16, geo, w["w2"], cout, bias=w["bias2"], out_dtype=torch.float32, residual=resid)
+        if tape is not None:
+            tape.append(("res", w, geo, x, st1, h16, st2))
+        return out
+
+    def _res_bwd(self, rec, dout):
+        _, w, geo, x, st1, h16, st2 = rec
+        dout16 = ops.cast(dout, self.dt)
+        db16, _ = ops.conv2d_dgrad(dout16, geo, w["w2"], w["cout"])
+        dh16 = ops.groupnorm_bwd(db16, h16, geo, w["g2"], w["b2"], st2, silu=True, dx_dtype=self.dt)
+        da16, _ = ops.conv2d_dgrad(dh16, geo, w["w1"], w["cin"])
+        if w["ws"] is None:
+            dx = dout
+        else:
+            dx = ops.linear_dgrad(dout16, w["ws"], out_dtype=torch.float32)
+        ops.groupnorm_bwd(da16, x, geo, w["g1"], w["b1"], st1, silu=True, dx=dx, accumulate=True)
+        return dx
+
+    def _xf_fwd(self, w, x, geo, ctx16, tape):
+        c, dh, H = w["c"], w["dh"], self.heads
+        B, nq, nk = geo.n, geo.hw, ctx16.shape[0] // geo.n
+        scale = dh ** -0.5
+        n16, stn = ops.groupnorm(x, geo, w["gn"], w["bn"], eps=1e-6, silu=False, out_dtype=self.dt)
+        h0 = ops.linear(n16, w["wpi"], w["bpi"], out_dtype=torch.float32)
+        # self attention
+        l1, s1 = ops.layernorm(h0, w["ln1g"], w["ln1b"], out_dtype=self.dt)
+        qkv = ops.linear(l1, w["wqkv"])
+        o1 = torch.empty(geo.rows, c, dtype=self.dt, device=self.dev)
+        P1 = _Attn.fwd(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], images=B, heads=H, dh=dh, nq=nq, nk=nq,
+                       scale=scale, out=o1)
+        h1 = ops.linear(o1, w["wo1"], w["bo1"], out_dtype=torch.float32, residual=h0)
+        # cross attention
+        l2, s2 = ops.layernorm(h1, w["ln2g"], w["ln2b"], out_dtype=self.dt)
+        q2 = ops.linear(l2, w["wq2"])
+        kv2 = ops.linear(ctx16, w["wkv2"])
+        o2 = torch.empty(geo.rows, c, dtype=self.dt, device=self.dev)
+        P2 = _Attn.fwd(q2, kv2[:, :c], kv2[:, c:], images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale, out=o2)
+        h2 = ops.linear(o2, w["wo2"], w["bo2"], out_dtype=torch.float32, residual=h1)
+        # GEGLU feed-forward
+        l3, s3 = ops.layernorm(h2, w["ln3g"], w["ln3b"], out_dtype=self.dt)
+        g16 = ops.linear(l3, w["wff1"], w["bff1"])
+        u16 = ops.geglu(g16)
+        h3 = ops.linear(u16, w["wff2"], w["bff2"], out_dtype=self.dt, residual=h2)
+        out = ops.linear(h3, w["wpo"], w["bpo"], out_dtype=torch.float32, residual=x)
+        if tape is not None:
+            tape.append(("xf", w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk))
+        return out
+
+    def _xf_bwd(self, rec, dout, dctx):
+        _, w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk = rec
+        c, dh, H = w["c"], w["dh"], self.heads
+        B, nq = geo.n, geo.hw
+        scale = dh ** -0.5
+        dx = dout
+        dr = ops.linear_dgrad(ops.cast(dout, self.dt), w["wpo"], out_dtype=torch.float32)  # d h3 (fp32 running)
+        # feed-forward
+        du = ops.linear_dgrad(ops.cast(dr, self.dt), w["wff2"])
+        dg = ops.geglu_bwd(du, g16)
+        dl3 = ops.linear_dgrad(dg, w["wff1"])
+        ops.layernorm_bwd(dl3, h2, w["ln3g"], s3, dx=dr, accumulate=True)
+        # cross attention
+        dO = ops.linear_dgrad(ops.cast(dr, self.dt), w["wo2"])
+        dq2 = torch.empty_like(q2)
+        dkv2 = torch.empty_like(kv2)
+        _Attn.bwd(dO, q2, kv2[:, :c], kv2[:, c:], P2, images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale,
+                  dq=dq2, dk=dkv2[:, :c], dv=dkv2[:, c:])
+        ops.linear_dgrad(dkv2, w["wkv2"], out=dctx, residual=dctx)
+        dl2 = ops.linear_dgrad(dq2, w["wq2"])
+        ops.layernorm_bwd(dl2, h1, w["ln2g"], s2, dx=dr, accumulate=True)
+        # self attention
+        dO = ops.linear_dgrad(ops.cast(dr, self.dt), w["wo1"])
+        dqkv = torch.empty_like(qkv)
+        _Attn.bwd(dO, qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], P1, images=B, heads=H, dh=dh, nq=nq, nk=nq,
+                  scale=scale, dq=dqkv[:, :c], dk=dqkv[:, c:2 * c], dv=dqkv[:, 2 * c:])
+        dl1 = ops.linear_dgrad(dqkv, w["wqkv"])
+        ops.layernorm_bwd(dl1, h0, w["ln1g"], s1, dx=dr, accumulate=True)
+        # proj_in + group norm
+        dn = ops.linear_dgrad(ops.cast(dr, self.dt), w["wpi"])
+        ops.groupnorm_bwd(dn, x, geo, w["gn"], w["bn"], stn, silu=False, dx=dx, accumulate=True)
+        return dx
+
+    def _down_fwd(self, w, x, geo, tape):
+        out, ogeo = ops.conv2d(ops.cast(x, self.dt), geo, w["w"], w["c"], bias=w["b"], stride=2,
+                               out_dtype=torch.float32)
+        if tape is not None:
+            tape.append(("down", w, geo, ogeo))
+        return out, ogeo
+
+    def _down_bwd(self, rec, dout):
+        _, w, geo, ogeo = rec
+        z, zgeo = ops.zero_insert2x(ops.cast(dout, self.dt), ogeo)
+        dx, _ = ops.conv2d_dgrad(z, zgeo, w["w"], w["c"], out_dtype=torch.float32)
+        return dx
+
+    def _up_fwd(self, w, x, geo, tape):
+        u, ugeo = ops.upsample2x(ops.cast(x, self.dt), geo)
+        out, _ = ops.conv2d(u, ugeo, w["w"], w["c"], bias=w["b"], out_dtype=torch.float32)
+        if tape is not None:
+            tape.append(("up", w, geo, ugeo))
+        return out, ugeo
+
+    def _up_bwd(self, rec, dout):
+        _, w, geo, ugeo = rec
+        du, _ = ops.conv2d_dgrad(ops.cast(dout, self.dt), ugeo, w["w"], w["c"])
+        return ops.upsample2x_bwd(du, geo, dx_dtype=torch.float32)
+
+    def _run_layers(self, layers, h, geo, emb_all, ctx16, tape):
+        for w in layers:
+            k = w["kind"]
+            if k == "res":
+                h = self._res_fwd(w, h, geo, emb_all, tape)
+            elif k == "xf":
+                h = self._xf_fwd(w, h, geo, ctx16, tape)
+            elif k == "down":
+                h, geo = self._down_fwd(w, h, geo, tape)
+            else:
+                h, geo = self._up_fwd(w, h, geo, tape)
+        return h, geo
+
+    def forward(self, x, t, context, need_grad=True):
+        """x: (B,in_ch,H,W) fp32 NCHW; t: (B,) int64; context: (B,T,ctx_dim) fp32.  Returns eps (B,out_ch,H,W) fp32."""
+        assert x.dtype == torch.float32 and context.dtype == torch.float32
+        B = x.shape[0]
+        tape = [] if need_grad else None
+        # timestep embedding MLP + all ResBlock projections
+        temb = ops.timestep_embedding(t, self.mc, dtype=self.dt)
+        e1 = ops.linear(temb, self.te0_w, self.te0_b, act=CB_ACT_SILU)
+        # SiLU(emb) is what every ResBlock consumes (openaimodel.py:222-226): fuse it into the 2nd linear
+        e2 = ops.linear(e1, self.te2_w, self.te2_b, act=CB_ACT_SILU)
+        emb_all = ops.linear(e2, self.emb_w, self.emb_b, out_dtype=torch.float32)
+        ctx16 = ops.cast(context.reshape(-1, self.ctx_dim), self.dt)
+        x16, geo = ops.nchw_to_nhwc(x.contiguous(), self.in_pad, self.dt)
+        h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32)
+        hs = [(h, geo)]
+        for layers in self.input_blocks:
+            h, geo = self._run_layers(layers, h, geo, emb_all, ctx16, tape)
+            if tape is not None:
+                tape.append(("push",))
+            hs.append((h, geo))
+        h, geo = self._run_layers(self.middle, h, geo, emb_all, ctx16, tape)
+        for layers in self.output_blocks:
+            skip, _ = hs.pop()
+            c1, c2 = h.shape[1], skip.shape[1]
+            cat = torch.empty(geo.rows, c1 + c2, dtype=torch.float32, device=self.dev)
+            ops.axpby(h, 1.0, out=cat[:, :c1])
+            ops.axpby(skip, 1.0, out=cat[:, c1:])
+            if tape is not None:
+                tape.append(("cat", c1, c2))
+            h, geo = self._run_layers(layers, cat, geo, emb_all, ctx16, tape)
+        a16, sto = ops.groupnorm(h, geo, self.out_g, self.out_b, eps=1e-5, silu=True, out_dtype=self.dt)
+        y, _ = ops.conv2d(a16, geo, self.out_w, self.out_ch, bias=self.out_bias, out_dtype=torch.float32,
+                          cout_rows=self.out_pad)
+        eps = ops.nhwc_to_nchw(y, geo, self.out_ch)
+        if tape is not None:
+            tape.append(("head", geo, h, sto))
+            self.tape = (tape, context.shape)
+        return eps
+
+    # ------------------------------------------------------------------------------------------
+    # backward: d(eps) -> d(context)
+    # ------------------------------------------------------------------------------------------
+    def backward(self, d_eps):
+        """d_eps: (B,out_ch,H,W) fp32 (unscaled).  Returns d_context (B,T,ctx_dim) fp32 (unscaled)."""
+        assert self.tape is not None, "UNetEngine.backward without a recorded forward"
+        tape, ctx_shape = self.tape
+        self.tape = None
+        S = self.loss_scale
+        dctx = torch.zeros(ctx_shape[0] * ctx_shape[1], ctx_shape[2], dtype=torch.float32, device=self.dev)
+        rec = tape.pop()
+        _, geo, h_head, sto = rec
+        d32, _ = ops.nchw_to_nhwc(d_eps.contiguous(), self.out_pad, torch.float32)
+        dy16 = ops.cast(d32, self.dt, scale=S)
+        da16, _ = ops.conv2d_dgrad(dy16, geo, self.out_w, self.mc, cout_rows=self.out_pad)
+        dh = ops.groupnorm_bwd(da16, h_head, geo, self.out_g, self.out_b, sto, silu=True, dx_dtype=torch.float32)
+        dskips = []
+        while tape:
+            rec = tape.pop()
+            k = rec[0]
+            if k == "res":
+                dh = self._res_bwd(rec, dh)
+            elif k == "xf":
+                dh = self._xf_bwd(rec, dh, dctx)
+            elif k == "down":
+                dh = self._down_bwd(rec, dh)
+            elif k == "up":
+                dh = self._up_bwd(rec, dh)
+            elif k == "cat":
+                _, c1, c2 = rec
+                dskips.append(dh[:, c1:])
+                dh = ops.axpby(dh[:, :c1], 1.0)
+            elif k == "push":
+                # this activation also fed a skip connection: add that branch's gradient
+                dsk = dskips.pop()
+                ops.axpby(dh, 1.0, dsk, 1.0, out=dh)
+        out = ops.axpby(dctx, 1.0 / S)
+        return out.view(ctx_shape)

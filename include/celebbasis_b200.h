@@ -117,9 +117,106 @@ typedef struct cb_gemm_desc {
 
     float alpha;
     int32_t act;
+
+    /* two-level batch: batch index z = zo*batch_inner + zi uses offset zi*stride + zo*stride2
+     * (e.g. zi = attention head, zo = image).  batch_inner == 0 means a single level. */
+    int32_t batch_inner;
+    int64_t a_batch_stride2, b_batch_stride2, d_batch_stride2, r_batch_stride2;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Normalisation (channels-last).  ws = caller workspace of 2*N*G doubles.
+ * cb_groupnorm_*: ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32, eps 1e-5),
+ *   ldm/modules/attention.py:76-77 and ldm/modules/diffusionmodules/model.py:38-39 (Normalize, eps 1e-6),
+ *   optionally fused with the nn.SiLU that follows (openaimodel.py:201-241, model.py:33-35 nonlinearity).
+ * cb_layernorm_*: nn.LayerNorm in BasicTransformerBlock (attention.py:196-215) and the CLIP layers.
+ * The *_bwd entry points are the activation gradients torch.autograd computes in the reference
+ * (SURVEY.md §8 a29); accumulate != 0 adds into dx (residual-branch join).
+ * ------------------------------------------------------------------------------------------- */
+int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                     int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
+                     double* ws, void* stream);
+int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                     const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int N, int HW,
+                     int C, int G, int act_silu, int accumulate, double* ws, void* stream);
+int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, int M,
+                     int C, float eps, float* mean_out, float* rstd_out, void* stream);
+int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                     const float* rstd, void* dx, int dx_dtype, int M, int C, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pointwise / row-wise kernels.
+ * cb_axpby2d: out = a*x + b*y over a [rows][cols] view with independent row strides (elements) and
+ *   dtypes; y may be NULL.  Serves residual adds, casts, torch.cat / chunk along channels
+ *   (openaimodel.py:736-739 skip concat), q_sample (ddpm.py:289-292) and the EMA update
+ *   (embedding_manager.py:484-489).
+ * cb_act_fwd/bwd: SiLU (openaimodel.py:208,222 emb_layers), quick-GELU (CLIP MLP), GELU.
+ * cb_geglu_*: ldm/modules/attention.py:37-45.      cb_softmax_*: attention.py:185 (+ CLIP causal mask,
+ *   modules.py:24-31: row r may attend columns <= r % causal_period).
+ * cb_upsample2x_*: openaimodel.py:112-117 nearest x2.   cb_zero_insert2x: input of the stride-2 conv dgrad.
+ * cb_nchw_to_nhwc / cb_nhwc_to_nchw: ddpm.py:344-350 layout glue (+ channel padding to a multiple of 8).
+ * cb_mse_fwd_bwd: ddpm.py:294-307 + :1084-1096 (l2 loss, mean over all elements) and dL/dpred * gscale.
+ * cb_timestep_embedding: diffusionmodules/util.py:151-171.
+ * ------------------------------------------------------------------------------------------- */
+int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, const void* y, int y_dtype, long long ldy, float b,
+               void* out, int o_dtype, long long ldo, long long rows, int cols, void* stream);
+int cb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long n, int act, void* stream);
+int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype, long long n, int act,
+               void* stream);
+int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, void* stream);
+int cb_geglu_bwd(const void* dout, const void* in, void* din, int dtype, int g_dtype, long long M, int F,
+                 void* stream);
+int cb_softmax_fwd(const void* s, void* p, int dtype, long long rows, int ncols, int ld, int causal_period,
+                   void* stream);
+int cb_softmax_bwd(const void* dp, const void* p, void* ds, int p_dtype, int g_dtype, long long rows, int ncols,
+                   int ld, void* stream);
+int cb_upsample2x_fwd(const void* x, void* y, int dtype, int N, int H, int W, int C, void* stream);
+int cb_upsample2x_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int N, int H, int W, int C,
+                      int accumulate, void* stream);
+int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H, int W, int C, void* stream);
+int cb_nchw_to_nhwc(const float* x, void* y, int y_dtype, int N, int C, int HW, int Cpad, void* stream);
+int cb_nhwc_to_nchw(const void* x, int x_dtype, float* y, int N, int C, int HW, int Cpad, void* stream);
+int cb_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, long long n, float gscale,
+                   void* stream);
+int cb_timestep_embedding(const long long* t, void* out, int o_dtype, int B, int dim, float max_period,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Celeb-basis embedding path (fp32): the only trainable tensors of the method live here.
+ * cb_embedding_gather: token_embedding(input_ids), ldm/modules/encoders/modules.py:237.
+ * cb_celeb_mlp_fwd: EqualLinear(512->es*K, lr_mul=1)+LeakyReLU(0.2) -> 'b (e h d) -> b e h d' -> L2 normalise,
+ *   ldm/modules/id_embedding/meta_net.py:27-48,61-87,266-273.  pre/coef/nrm are saved for backward.
+ * cb_celeb_basis_fwd/bwd: einsum('b e h k, e k c -> b e h c', x, basis[:,1:]) + basis[:,0], meta_net.py:275-289
+ *   (also embedding_manager.py:464-475 at inference and scripts/extract_pt.py:113-118).
+ * cb_celeb_mlp_bwd: gradient of W (es*K x in_dim) and b; gscale un-does the fp16 loss scale.
+ * cb_embed_inject_fwd/bwd: the row rewrite of EmbeddingManagerId.forward (embedding_manager.py:322-360) as one
+ *   gather: map[b][i] >= 0 takes token row map[b][i] of the same prompt, map < 0 takes z row -(map+1);
+ *   then + position_embedding (modules.py:295-296).  The integer map is produced on the host by the
+ *   bit-exact mirror of ldm/modules/id_embedding/helpers.py:6-41.
+ * cb_adamw_step: torch.optim.AdamW step on the flat trainable buffer (ddpm.py:1442-1454); if step_dev is
+ *   not NULL the 1-based step counter is read from (and bumped on) the device so the launch is graph-replayable.
+ * cb_posterior_sample: DiagonalGaussianDistribution.sample * scale_factor (distributions.py:25-37, ddpm.py:590-597)
+ *   with the normal draw eps supplied by the caller (the reference draws it on the CPU).
+ * ------------------------------------------------------------------------------------------- */
+int cb_embedding_gather(const long long* ids, const float* table, float* out, int n, int D, int V, void* stream);
+int cb_celeb_mlp_fwd(const float* v, const float* W, const float* b, float* pre, float* coef, float* nrm, int F,
+                     int in_dim, int K, int es, float slope, void* stream);
+int cb_celeb_basis_fwd(const float* coef, const float* basis, float* z, int F, int es, int K, int D, void* stream);
+int cb_celeb_basis_bwd(const float* dz, const float* basis, float* dcoef, int F, int es, int K, int D, void* stream);
+int cb_celeb_mlp_bwd(const float* dcoef, const float* coef, const float* nrm, const float* pre, const float* v,
+                     float* dpre_ws, float* dW, float* db, int F, int in_dim, int K, int es, float slope,
+                     float gscale, void* stream);
+int cb_embed_inject_fwd(const float* tok, const float* z, const int* map, const float* pos, float* out, int B, int T,
+                        int D, void* stream);
+int cb_embed_inject_bwd(const float* dout, const int* map, float* dz, int n_z_rows, int B, int T, int D,
+                        void* stream);
+int cb_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, int* step_dev, void* stream);
+int cb_posterior_sample(const float* moments, const float* eps, float* z, int N, int Cz, int HW, float scale,
+                        void* stream);
 
 #ifdef __cplusplus
 }

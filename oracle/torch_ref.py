@@ -1,0 +1,398 @@
+"""ORACLE (test infrastructure, not product): plain-PyTorch fp32 restatement of the CelebBasis hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
+It restates, module by module and with the reference's state-dict key names, what the reference computes so
+that it can travel to the GPU box (where /root/reference does not exist).  It is pinned against the
+UNMODIFIED reference imported from /root/reference by oracle/make_golden.py (fixtures in tests/golden/);
+tests/test_oracle_golden.py re-checks this file against those fixtures on every run.
+
+Reference lines followed:
+  UNet          ldm/modules/diffusionmodules/openaimodel.py:74-160,163-275,413-742
+  attention     ldm/modules/attention.py:37-64,76-77,152-261
+  util          ldm/modules/diffusionmodules/util.py:21-25,96-99,151-171,199-216
+  VAE           ldm/modules/diffusionmodules/model.py:33-202,368-568 ; ldm/models/autoencoder.py:285-333
+  posterior     ldm/modules/distributions/distributions.py:24-37
+  CLIP text     ldm/modules/encoders/modules.py:24-31,176-298,345-406 (+ transformers CLIPEncoderLayer maths)
+  embedding     ldm/modules/embedding_manager.py:279-394,452-490 ; ldm/modules/id_embedding/meta_net.py:27-87,250-346
+  helpers       ldm/modules/id_embedding/helpers.py:6-41
+  iresnet       ldm/modules/id_embedding/iresnet.py:26-181
+  diffusion     ldm/models/diffusion/ddpm.py:126-178,289-307,590-597,926-936,1069-1116 ; ddim.py:25-204
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# =================================================================================================
+# UNet
+# =================================================================================================
+def timestep_embedding(timesteps, dim, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        inner = dim * mult
+        self.net = nn.Sequential(GEGLU(dim, inner), nn.Dropout(0.0), nn.Linear(inner, dim))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64):
+        super().__init__()
+        inner = dim_head * heads
+        context_dim = context_dim if context_dim is not None else query_dim
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(0.0))
+
+    def forward(self, x, context=None):
+        h = self.heads
+        q = self.to_q(x)
+        context = context if context is not None else x
+        k, v = self.to_k(context), self.to_v(context)
+        b, n, _ = q.shape
+
+        def split(t):
+            return t.reshape(b, t.shape[1], h, -1).permute(0, 2, 1, 3).reshape(b * h, t.shape[1], -1)
+
+        q, k, v = split(q), split(k), split(v)
+        sim = torch.einsum("bid,bjd->bij", q, k) * self.scale
+        attn = sim.softmax(dim=-1)
+        out = torch.einsum("bij,bjd->bid", attn, v)
+        out = out.reshape(b, h, n, -1).permute(0, 2, 1, 3).reshape(b, n, -1)
+        return self.to_out(out)
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, n_heads, d_head, context_dim=None):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, heads=n_heads, dim_head=d_head)
+        self.ff = FeedForward(dim)
+        self.attn2 = CrossAttention(dim, context_dim=context_dim, heads=n_heads, dim_head=d_head)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+    def forward(self, x, context=None):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context=context) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class SpatialTransformer(nn.Module):
+    def __init__(self, in_channels, n_heads, d_head, depth=1, context_dim=None):
+        super().__init__()
+        inner = n_heads * d_head
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, n_heads, d_head, context_dim=context_dim) for _ in range(depth)])
+        self.proj_out = nn.Conv2d(inner, in_channels, 1)
+
+    def forward(self, x, context=None):
+        b, c, h, w = x.shape
+        x_in = x
+        x = self.proj_in(self.norm(x))
+        x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)
+        for blk in self.transformer_blocks:
+            x = blk(x, context=context)
+        x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
+        return self.proj_out(x) + x_in
+
+
+class ResBlock(nn.Module):
+    def __init__(self, channels, emb_channels, out_channels):
+        super().__init__()
+        self.in_layers = nn.Sequential(GroupNorm32(32, channels), nn.SiLU(), nn.Conv2d(channels, out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, out_channels))
+        self.out_layers = nn.Sequential(GroupNorm32(32, out_channels), nn.SiLU(), nn.Dropout(0.0),
+                                        nn.Conv2d(out_channels, out_channels, 3, padding=1))
+        self.skip_connection = nn.Identity() if out_channels == channels else nn.Conv2d(channels, out_channels, 1)
+
+    def forward(self, x, emb):
+        h = self.in_layers(x)
+        h = h + self.emb_layers(emb).type(h.dtype)[..., None, None]
+        h = self.out_layers(h)
+        return self.skip_connection(x) + h
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.op = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2, mode="nearest"))
+
+
+class TimestepEmbedSequential(nn.Sequential):
+    def forward(self, x, emb, context=None):
+        for layer in self:
+            if isinstance(layer, ResBlock):
+                x = layer(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            else:
+                x = layer(x)
+        return x
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=(4, 2, 1),
+                 num_res_blocks=2, channel_mult=(1, 2, 4, 4), num_heads=8, context_dim=768, **_):
+        super().__init__()
+        self.model_channels = model_channels
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, ted, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(SpatialTransformer(ch, num_heads, ch // num_heads, context_dim=context_dim))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, ted, ch), SpatialTransformer(ch, num_heads, ch // num_heads, context_dim=context_dim),
+            ResBlock(ch, ted, ch))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = chans.pop()
+                layers = [ResBlock(ch + ich, ted, model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(SpatialTransformer(ch, num_heads, ch // num_heads, context_dim=context_dim))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(GroupNorm32(32, ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+
+    def forward(self, x, timesteps=None, context=None):
+        hs = []
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        h = x
+        for m in self.input_blocks:
+            h = m(h, emb, context)
+            hs.append(h)
+        h = self.middle_block(h, emb, context)
+        for m in self.output_blocks:
+            h = torch.cat([h, hs.pop()], dim=1)
+            h = m(h, emb, context)
+        return self.out(h)
+
+
+# =================================================================================================
+# CLIP text transformer (maths of transformers CLIPTextModel as driven by modules.py:302-406)
+# =================================================================================================
+class CLIPAttention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.heads, self.dh = heads, dim // heads
+        self.q_proj, self.k_proj = nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.v_proj, self.out_proj = nn.Linear(dim, dim), nn.Linear(dim, dim)
+
+    def forward(self, x, mask):
+        b, t, c = x.shape
+        sh = lambda y: y.view(b, t, self.heads, self.dh).transpose(1, 2)
+        q, k, v = sh(self.q_proj(x) * self.dh ** -0.5), sh(self.k_proj(x)), sh(self.v_proj(x))
+        w = torch.matmul(q, k.transpose(-1, -2)) + mask
+        w = w.softmax(dim=-1)
+        o = torch.matmul(w, v).transpose(1, 2).reshape(b, t, c)
+        return self.out_proj(o)
+
+
+class CLIPMLP(nn.Module):
+    def __init__(self, dim, inter):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, inter), nn.Linear(inter, dim)
+
+    def forward(self, x):
+        x = self.fc1(x)
+        return self.fc2(x * torch.sigmoid(1.702 * x))
+
+
+class CLIPEncoderLayer(nn.Module):
+    def __init__(self, dim, heads, inter, eps):
+        super().__init__()
+        self.self_attn = CLIPAttention(dim, heads)
+        self.layer_norm1 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = CLIPMLP(dim, inter)
+        self.layer_norm2 = nn.LayerNorm(dim, eps=eps)
+
+    def forward(self, x, mask):
+        x = x + self.self_attn(self.layer_norm1(x), mask)
+        return x + self.mlp(self.layer_norm2(x))
+
+
+class _Embeddings(nn.Module):
+    def __init__(self, vocab, dim, max_pos):
+        super().__init__()
+        self.token_embedding = nn.Embedding(vocab, dim)
+        self.position_embedding = nn.Embedding(max_pos, dim)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, n, dim, heads, inter, eps):
+        super().__init__()
+        self.layers = nn.ModuleList([CLIPEncoderLayer(dim, heads, inter, eps) for _ in range(n)])
+
+
+class CLIPTextTransformer(nn.Module):
+    """state-dict keys match HF `CLIPTextModel().text_model` (embeddings.*, encoder.layers.N.*, final_layer_norm.*)."""
+
+    def __init__(self, vocab=49408, dim=768, layers=12, heads=12, inter=3072, max_pos=77, eps=1e-5):
+        super().__init__()
+        self.embeddings = _Embeddings(vocab, dim, max_pos)
+        self.encoder = _Encoder(layers, dim, heads, inter, eps)
+        self.final_layer_norm = nn.LayerNorm(dim, eps=eps)
+
+    def embed_tokens(self, ids):
+        return self.embeddings.token_embedding(ids)
+
+    def forward_embeds(self, inputs_embeds):
+        """inputs_embeds: (B,T,D) token embeddings AFTER the embedding-manager rewrite, before position add."""
+        b, t, _ = inputs_embeds.shape
+        pos = self.embeddings.position_embedding.weight[:t]
+        h = inputs_embeds + pos[None]
+        mask = torch.full((t, t), torch.finfo(h.dtype).min, device=h.device, dtype=h.dtype).triu_(1)[None, None]
+        for layer in self.encoder.layers:
+            h = layer(h, mask)
+        return self.final_layer_norm(h)
+
+
+# =================================================================================================
+# placeholder index arithmetic (integer path, must be bit-exact)
+# =================================================================================================
+def get_rep_pos(tokenized, rep_tokens):
+    tok = np.asarray(tokenized)
+    return [np.where(tok == t)[0] for t in rep_tokens]
+
+
+def shift_index_map(d, r_pos, reps):
+    """Restates helpers.py:13-41 on an index vector: returns (src, rep_final_pos_list) where src[i] is the original
+    row that ends up in row i after the shift/duplicate, and the final placeholder positions per token."""
+    offset = np.zeros(d, dtype=np.int64)
+    r_cat = np.concatenate(r_pos) if len(r_pos) else np.zeros(0, dtype=np.int64)
+    for p in r_cat:
+        offset[p + 1:] += (reps - 1)
+    r_cnt = r_cat.shape[0]
+    target_pos = (np.arange(d) + offset)[: d - r_cnt * (reps - 1)]
+    src = np.arange(d)
+    src[target_pos] = np.arange(target_pos.shape[0])
+    rep_final = target_pos[r_cat].repeat(reps) + np.tile(np.arange(reps), r_cnt)
+    snapshot = src.copy()
+    src[rep_final] = snapshot[target_pos[r_cat].repeat(reps)]
+    out, lo = [], 0
+    for i in range(len(r_pos)):
+        times = r_pos[i].shape[0]
+        out.append(rep_final[lo: lo + times * reps].reshape(times, reps))
+        lo += times * reps
+    return src, out
+
+
+# =================================================================================================
+# celeb-basis MLP + embedding rewrite
+# =================================================================================================
+def celeb_mlp(v, W, b, es=2):
+    """meta_net.py:27-48 (lr_mul=1) + :266-273: returns normalised coefficients (F, es, 1, K)."""
+    x = F.leaky_relu(F.linear(v, W, b), 0.2)
+    x = x.view(v.shape[0], es, 1, -1)
+    return F.normalize(x, dim=-1, p=2)
+
+
+def celeb_basis(coef, basis):
+    """meta_net.py:275-289: (F,es,1,K) x (es,1+K,D) -> (F, es, D)."""
+    c_mean, pca = basis[:, 0], basis[:, 1:]
+    z = torch.einsum("behk,ekc->behc", coef, pca) + c_mean[None, :, None, :]
+    return z.reshape(coef.shape[0], -1, basis.shape[-1])
+
+
+def inject_embeddings(ids, tok_emb, z, placeholder_token, reps):
+    """embedding_manager.py:347-360 for num_ids == 1.  ids (B,T) int64 cpu/np, tok_emb (B,T,D), z (B, reps, D)."""
+    out = []
+    all_pos = []
+    for b in range(tok_emb.shape[0]):
+        pos = get_rep_pos(np.asarray(ids[b].cpu()), [placeholder_token])
+        src, fin = shift_index_map(tok_emb.shape[1], pos, reps)
+        e = tok_emb[b][torch.as_tensor(src, device=tok_emb.device)]
+        rows = [e[i] for i in range(e.shape[0])]
+        for one_pos in fin[0]:
+            for j, p in enumerate(one_pos):
+                rows[int(p)] = z[b][j]
+        out.append(torch.stack(rows, 0))
+        all_pos.append(fin)
+    return torch.stack(out, 0), all_pos
+
+
+# =================================================================================================
+# diffusion schedule / loss
+# =================================================================================================
+def make_schedule(timesteps=1000, linear_start=0.00085, linear_end=0.0120):
+    betas = torch.linspace(linear_start ** 0.5, linear_end ** 0.5, timesteps, dtype=torch.float64) ** 2
+    betas = betas.numpy()
+    alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+    return {
+        "betas": torch.tensor(betas, dtype=torch.float32),
+        "alphas_cumprod": torch.tensor(alphas_cumprod, dtype=torch.float32),
+        "sqrt_alphas_cumprod": torch.tensor(np.sqrt(alphas_cumprod), dtype=torch.float32),
+        "sqrt_one_minus_alphas_cumprod": torch.tensor(np.sqrt(1.0 - alphas_cumprod), dtype=torch.float32),
+    }
+
+
+def q_sample(sched, x0, t, noise):
+    a = sched["sqrt_alphas_cumprod"].to(x0.device)[t].view(-1, 1, 1, 1)
+    s = sched["sqrt_one_minus_alphas_cumprod"].to(x0.device)[t].view(-1, 1, 1, 1)
+    return a * x0 + s * noise
+
+
+def eps_loss(pred, noise):
+    """ddpm.py:1084-1096 with logvar == 0, l_simple_weight 1, original_elbo_weight 0."""
+    return ((pred - noise) ** 2).mean(dim=[1, 2, 3]).mean()
