@@ -1,0 +1,130 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (through oracle/ref_shim.py) on CPU.
+
+    python oracle/make_golden.py tiny        # seconds
+    python oracle/make_golden.py full        # ~1-2 min, needs ~12 GB host RAM
+
+Fixtures hold the inputs' seeds (the inputs themselves are re-derivable from celebbasis_b200.workload +
+celebbasis_b200.synth) and the reference's outputs: latent z, context, eps prediction, loss, and the gradient
+of the two trainable tensors (full tensor for 'tiny'; norm + a fixed strided sample for 'full').
+Also the integer known-answer of ldm/modules/id_embedding/helpers.py:44-54.
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from celebbasis_b200 import synth, workload
+from oracle import ref_shim
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def run(kind):
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    basis = synth.synth_celeb_basis(seed=0)
+    t0 = time.time()
+    model = ref_shim.build_reference(workload.model_params(kind), seed=0, clip_layers=workload.clip_layers(kind),
+                                     celeb_basis=basis)
+    print(f"[{kind}] reference built in {time.time() - t0:.1f}s")
+    batch, draws = workload.synth_batch(kind, B=1, seed=1234)
+    cap = {}
+    # capture intermediate tensors without touching the arithmetic
+    orig_apply = model.apply_model
+
+    def apply_model(x_noisy, t, cond, *a, **k):
+        out = orig_apply(x_noisy, t, cond, *a, **k)
+        cap["x_noisy"], cap["context"], cap["eps"] = x_noisy.detach().clone(), cond.detach().clone(), out.detach().clone()
+        return out
+    model.apply_model = apply_model
+    orig_fse = model.get_first_stage_encoding
+
+    def fse(post):
+        z = orig_fse(post)
+        cap["z"] = z.detach().clone()
+        cap["moments"] = post.parameters.detach().clone()
+        return z
+    model.get_first_stage_encoding = fse
+    mlp = model.embedding_manager.meta_id_net
+    orig_celebs = mlp._celebs_forward
+
+    def celebs_forward(img, id_idx, celebs_embeds):
+        z, cls, x = orig_celebs(img, id_idx, celebs_embeds)
+        cap["celeb_z"], cap["celeb_coef"] = z.detach().clone(), x.detach().clone()
+        return z, cls, x
+    mlp._celebs_forward = celebs_forward
+    orig_idm = mlp.id_model.forward
+
+    def idm(x):
+        y = orig_idm(x)
+        cap["face_in"], cap["face_feat"] = x.detach().clone(), y.detach().clone()
+        return y
+    mlp.id_model.forward = idm
+
+    t0 = time.time()
+    with ref_shim.replay_randomness(draws["t"], draws["noise"], draws["posterior_eps"]):
+        loss, loss_dict = model.shared_step(batch)
+    print(f"[{kind}] forward {time.time() - t0:.1f}s loss={loss.item():.6f}")
+    t0 = time.time()
+    loss.backward()
+    print(f"[{kind}] backward {time.time() - t0:.1f}s")
+    W = mlp.stylegan_mlp.net[0].weight
+    b = mlp.stylegan_mlp.net[0].bias
+    graded = [n for n, p in model.named_parameters() if p.grad is not None]
+    out = {
+        "kind": kind, "loss": loss.detach().clone(), "z": cap["z"], "moments": cap["moments"],
+        "context": cap["context"], "eps": cap["eps"], "x_noisy": cap["x_noisy"], "celeb_z": cap["celeb_z"],
+        "celeb_coef": cap["celeb_coef"], "face_feat": cap["face_feat"],
+        "graded": graded, "gW_norm": W.grad.norm().clone(), "gb": b.grad.detach().clone(),
+        "ema_coef_id0": model.embedding_manager.id_coefficients[0].detach().clone(),
+    }
+    if kind == "tiny":
+        out["gW"] = W.grad.detach().clone()
+        out["face_in"] = cap["face_in"]
+    else:
+        out["gW_sample"] = W.grad.detach().flatten()[::131].clone()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.save(out, os.path.join(GOLD, f"step_{kind}.pt"))
+    print(f"[{kind}] graded params: {graded}; |gW|={W.grad.norm().item():.6e}")
+
+
+def helpers_kat():
+    """helpers.py:44-54 toy case, computed by the reference's own functions."""
+    ref_shim.install_stubs()
+    from ldm.modules.id_embedding.helpers import get_rep_pos, shift_tensor_dim0
+    tok = torch.LongTensor([0, 1, 2, 2, 3, 4, 5, 6, 7, 99] + [99] * 20)
+    pos = get_rep_pos(tok, [2, 6])
+    res, fin = shift_tensor_dim0(tok.clone(), pos, 2)
+    cases = [{"tokens": tok, "rep_tokens": [2, 6], "reps": 2, "rep_pos": [p.tolist() for p in pos],
+              "result": res, "final_pos": [f.tolist() for f in fin]}]
+    rng = np.random.RandomState(0)
+    for _ in range(40):
+        n = 77
+        t = torch.from_numpy(rng.randint(1000, 2000, size=n)).long()
+        toks = list(range(5, 5 + int(rng.randint(1, 4))))
+        reps = int(rng.randint(1, 4))
+        for tk in toks:  # each placeholder occurs 1-2 times, early in the prompt (as in real captions)
+            for p_ in rng.choice(np.arange(1, 30), size=int(rng.randint(1, 3)), replace=False):
+                if int(t[p_]) >= 1000:
+                    t[p_] = tk
+        pos = get_rep_pos(t, toks)
+        emb = torch.arange(n).float()[:, None].repeat(1, 3)
+        res, fin = shift_tensor_dim0(emb.clone(), pos, reps)
+        cases.append({"tokens": t, "rep_tokens": toks, "reps": reps, "rep_pos": [p.tolist() for p in pos],
+                      "result": res[:, 0].long(), "final_pos": [f.tolist() for f in fin]})
+    torch.save(cases, os.path.join(GOLD, "helpers_kat.pt"))
+    print(f"[helpers] {len(cases)} known-answer cases")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["helpers", "tiny"]
+    for w in which:
+        if w == "helpers":
+            helpers_kat()
+        else:
+            run(w)

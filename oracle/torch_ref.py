@@ -396,3 +396,258 @@ def q_sample(sched, x0, t, noise):
 def eps_loss(pred, noise):
     """ddpm.py:1084-1096 with logvar == 0, l_simple_weight 1, original_elbo_weight 0."""
     return ((pred - noise) ** 2).mean(dim=[1, 2, 3]).mean()
+
+
+# =================================================================================================
+# VAE encoder (AutoencoderKL.encode)
+# =================================================================================================
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def _vae_norm(c):
+    return nn.GroupNorm(32, c, eps=1e-6, affine=True)
+
+
+class VaeResnetBlock(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1, self.conv1 = _vae_norm(cin), nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2, self.conv2 = _vae_norm(cout), nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x):
+        h = self.conv1(_swish(self.norm1(x)))
+        h = self.conv2(_swish(self.norm2(h)))
+        if hasattr(self, "nin_shortcut"):
+            x = self.nin_shortcut(x)
+        return x + h
+
+
+class VaeAttnBlock(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.norm = _vae_norm(c)
+        self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
+
+    def forward(self, x):
+        h = self.norm(x)
+        q, k, v = self.q(h), self.k(h), self.v(h)
+        b, c, hh, ww = q.shape
+        q = q.reshape(b, c, hh * ww).permute(0, 2, 1)
+        k = k.reshape(b, c, hh * ww)
+        w_ = torch.softmax(torch.bmm(q, k) * (int(c) ** -0.5), dim=2)
+        v = v.reshape(b, c, hh * ww)
+        h = torch.bmm(v, w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+        return x + self.proj_out(h)
+
+
+class VaeDownsample(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class VaeEncoder(nn.Module):
+    def __init__(self, *, ch, ch_mult, num_res_blocks, in_channels, z_channels, double_z=True, **_):
+        super().__init__()
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, padding=1)
+        in_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        bin_ = ch
+        for i in range(self.num_resolutions):
+            lvl = nn.Module()
+            lvl.block = nn.ModuleList()
+            lvl.attn = nn.ModuleList()
+            bin_, bout = ch * in_mult[i], ch * ch_mult[i]
+            for _ in range(num_res_blocks):
+                lvl.block.append(VaeResnetBlock(bin_, bout))
+                bin_ = bout
+            if i != self.num_resolutions - 1:
+                lvl.downsample = VaeDownsample(bin_)
+            self.down.append(lvl)
+        self.mid = nn.Module()
+        self.mid.block_1, self.mid.attn_1, self.mid.block_2 = VaeResnetBlock(bin_, bin_), VaeAttnBlock(bin_), VaeResnetBlock(bin_, bin_)
+        self.norm_out = _vae_norm(bin_)
+        self.conv_out = nn.Conv2d(bin_, 2 * z_channels if double_z else z_channels, 3, padding=1)
+
+    def forward(self, x):
+        h = self.conv_in(x)
+        for i in range(self.num_resolutions):
+            for j in range(self.num_res_blocks):
+                h = self.down[i].block[j](h)
+            if i != self.num_resolutions - 1:
+                h = self.down[i].downsample(h)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        return self.conv_out(_swish(self.norm_out(h)))
+
+
+class AutoencoderKLEncode(nn.Module):
+    """encoder + quant_conv of AutoencoderKL (keys: encoder.*, quant_conv.*)."""
+
+    def __init__(self, ddconfig, embed_dim):
+        super().__init__()
+        self.encoder = VaeEncoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
+
+    def forward(self, x):
+        return self.quant_conv(self.encoder(x))
+
+
+def posterior_sample(moments, eps, scale_factor):
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return scale_factor * (mean + torch.exp(0.5 * logvar) * eps)
+
+
+# =================================================================================================
+# CosFace iresnet100 + face preprocessing
+# =================================================================================================
+class IBasicBlock(nn.Module):
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.bn1 = nn.BatchNorm2d(inplanes, eps=1e-5)
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes, eps=1e-5)
+        self.prelu = nn.PReLU(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes, eps=1e-5)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.bn3(self.conv2(self.prelu(self.bn2(self.conv1(self.bn1(x))))))
+        return out + (x if self.downsample is None else self.downsample(x))
+
+
+class IResNet(nn.Module):
+    def __init__(self, layers=(3, 13, 30, 3), num_features=512):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(64, eps=1e-5)
+        self.prelu = nn.PReLU(64)
+        self.layer1 = self._make(64, layers[0])
+        self.layer2 = self._make(128, layers[1])
+        self.layer3 = self._make(256, layers[2])
+        self.layer4 = self._make(512, layers[3])
+        self.bn2 = nn.BatchNorm2d(512, eps=1e-5)
+        self.fc = nn.Linear(512 * 49, num_features)
+        self.features = nn.BatchNorm1d(num_features, eps=1e-5)
+
+    def _make(self, planes, blocks):
+        ds = nn.Sequential(nn.Conv2d(self.inplanes, planes, 1, stride=2, bias=False), nn.BatchNorm2d(planes, eps=1e-5))
+        layers = [IBasicBlock(self.inplanes, planes, 2, ds)]
+        self.inplanes = planes
+        layers += [IBasicBlock(planes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.prelu(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = torch.flatten(self.bn2(x), 1)
+        return self.features(self.fc(x))
+
+
+TRANS_MATRIX = [[1.07695457, -0.03625215, -1.56352194 / 512], [0.03625215, 1.07695457, -5.32134629 / 512]]
+
+
+def face_preprocess(faces_nhwc):
+    """meta_net.py:253-262: NHWC -> NCHW, fixed affine warp (grid_sample), bilinear resize to 112."""
+    img = faces_nhwc.permute(0, 3, 1, 2)
+    M = torch.tensor([TRANS_MATRIX], dtype=torch.float32, device=img.device).repeat(img.shape[0], 1, 1)
+    grid = F.affine_grid(M, size=img.size(), align_corners=True)
+    img = F.grid_sample(img, grid, align_corners=True, mode="bilinear", padding_mode="zeros")
+    return F.interpolate(img, size=112, mode="bilinear", align_corners=True)
+
+
+# =================================================================================================
+# one full training-step forward (rows a1-a28 of SURVEY.md §8) on explicit weights
+# =================================================================================================
+class OracleModel(nn.Module):
+    """Same submodule names / state-dict keys as the reference LatentDiffusion for every tensor on the path."""
+
+    def __init__(self, params, clip_layers=12):
+        super().__init__()
+        self.params = params
+
+        class _Wrap(nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.diffusion_model = m
+        self.model = _Wrap(UNetModel(**params["unet_config"]["params"]))
+        fs = params["first_stage_config"]["params"]
+        self.first_stage_model = AutoencoderKLEncode(fs["ddconfig"], fs["embed_dim"])
+
+        class _T(nn.Module):
+            def __init__(self, n):
+                super().__init__()
+                self.text_model = CLIPTextTransformer(layers=n)
+
+        class _C(nn.Module):
+            def __init__(self, n):
+                super().__init__()
+                self.transformer = _T(n)
+        self.cond_stage_model = _C(clip_layers)
+
+        class _Lin(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.weight = nn.Parameter(torch.zeros(1024, 512))
+                self.bias = nn.Parameter(torch.zeros(1024))
+
+        class _SV(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.net = nn.Sequential(_Lin())
+
+        class _Meta(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.id_model = IResNet()
+                self.stylegan_mlp = _SV()
+
+        class _EM(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.meta_id_net = _Meta()
+        self.embedding_manager = _EM()
+        self.sched = make_schedule(params["timesteps"], params["linear_start"], params["linear_end"])
+        self.scale_factor = params["scale_factor"]
+
+    def trainable(self):
+        lin = self.embedding_manager.meta_id_net.stylegan_mlp.net[0]
+        return lin.weight, lin.bias
+
+    def step(self, batch, draws, token_ids, basis, placeholder_token):
+        """Returns dict(loss, z, context, eps, x_noisy, coef, celeb_z, face_feat)."""
+        out = {}
+        x = batch["image"].permute(0, 3, 1, 2).contiguous().float()
+        with torch.no_grad():
+            moments = self.first_stage_model(x)
+            z = posterior_sample(moments, draws["posterior_eps"].to(x.device), self.scale_factor)
+            faces = batch["image_ori"]["faces"]
+            n_id = batch["image_ori"]["ids"].shape[1]
+            cat = torch.cat(faces.chunk(n_id, -1), 0)
+            self.embedding_manager.meta_id_net.id_model.eval()
+            v = F.normalize(self.embedding_manager.meta_id_net.id_model(face_preprocess(cat)), dim=-1, p=2)
+        W, b = self.trainable()
+        coef = celeb_mlp(v, W, b)
+        zc = celeb_basis(coef, basis.to(x.device))
+        B = x.shape[0]
+        tm = self.cond_stage_model.transformer.text_model
+        tok_emb = tm.embed_tokens(token_ids.to(x.device))
+        emb, pos = inject_embeddings(token_ids, tok_emb, zc[:B], placeholder_token, zc.shape[1])
+        context = tm.forward_embeds(emb)
+        t = draws["t"].to(x.device)
+        noise = draws["noise"].to(x.device)
+        x_noisy = q_sample(self.sched, z, t, noise)
+        eps = self.model.diffusion_model(x_noisy, t, context)
+        loss = eps_loss(eps, noise)
+        out.update(loss=loss, z=z, moments=moments, context=context, eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
+                   face_feat=v, positions=pos)
+        return out

@@ -1,0 +1,67 @@
+"""CPU: pin the oracle restatement (oracle/torch_ref.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py ran /root/reference's LatentDiffusion.shared_step + backward through oracle/ref_shim.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from celebbasis_b200 import synth, workload
+from celebbasis_b200.tokenizer import SyntheticCLIPTokenizer
+from oracle import torch_ref
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+def test_helpers_known_answers(golden_dir):
+    """ldm/modules/id_embedding/helpers.py: integer path, bit-exact (incl. the reference's own __main__ toy case)."""
+    cases = torch.load(os.path.join(golden_dir, "helpers_kat.pt"))
+    assert len(cases) >= 20
+    for c in cases:
+        tok = c["tokens"].numpy()
+        pos = torch_ref.get_rep_pos(tok, c["rep_tokens"])
+        assert [p.tolist() for p in pos] == c["rep_pos"]
+        src, fin = torch_ref.shift_index_map(tok.shape[0], pos, c["reps"])
+        assert [f.tolist() for f in fin] == c["final_pos"]
+        if c is cases[0]:
+            got = tok[src]            # the toy case shifts the token vector itself
+        else:
+            got = src                 # the others shift arange(n)
+        assert got.tolist() == c["result"].tolist()
+    first = cases[0]
+    assert first["rep_pos"] == [[2, 3], [7]] and first["final_pos"] == [[[2, 3], [4, 5]], [[9, 10]]]
+
+
+def test_tiny_step_matches_reference(golden_dir):
+    """Whole training-step forward + backward of the restatement == the reference's, fp32, same weights/inputs."""
+    gold = torch.load(os.path.join(golden_dir, "step_tiny.pt"))
+    torch.manual_seed(0)
+    params = workload.model_params("tiny")
+    model = torch_ref.OracleModel(params, clip_layers=workload.clip_layers("tiny"))
+    sd = synth.synth_state_dict(model, seed=0)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    batch, draws = workload.synth_batch("tiny", B=1, seed=1234)
+    ids = SyntheticCLIPTokenizer()(batch["caption"])["input_ids"]
+    basis = synth.synth_celeb_basis(seed=0)
+    W, b = model.trainable()
+    W.requires_grad_(True)
+    b.requires_grad_(True)
+    out = model.step(batch, draws, ids, basis, placeholder_token=SyntheticCLIPTokenizer.word_id("sks"))
+    out["loss"].backward()
+    assert _rel(out["face_feat"], torch.nn.functional.normalize(gold["face_feat"], dim=-1)) < 1e-5
+    assert _rel(out["z"], gold["z"]) < 1e-5
+    assert _rel(out["coef"], gold["celeb_coef"]) < 1e-5
+    assert _rel(out["celeb_z"], gold["celeb_z"]) < 1e-5
+    assert _rel(out["context"], gold["context"]) < 1e-5
+    assert _rel(out["x_noisy"], gold["x_noisy"]) < 1e-5
+    assert _rel(out["eps"], gold["eps"]) < 1e-4
+    assert abs(out["loss"].item() - gold["loss"].item()) / abs(gold["loss"].item()) < 1e-5
+    assert _rel(W.grad, gold["gW"]) < 1e-3
+    assert _rel(b.grad, gold["gb"]) < 1e-3
+    assert gold["graded"] == ["embedding_manager.meta_id_net.stylegan_mlp.net.0.weight",
+                              "embedding_manager.meta_id_net.stylegan_mlp.net.0.bias"]
+    # placeholder lands at positions 7,8 of "a photo of a face of sks person"
+    assert [f.tolist() for f in out["positions"][0]] == [[[7, 8]]]
