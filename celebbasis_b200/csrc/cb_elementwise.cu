@@ -332,6 +332,101 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, void*
     if ((dim & 1) && k == 0) st_any(out, odt, (size_t)b * dim + dim - 1, 0.f);
 }
 
+// ---- per-channel affine (+ optional PReLU): eval-mode BatchNorm2d / nn.PReLU of iresnet.py:26-64 -------------
+template <typename T>
+__global__ void channel_affine_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, const float* __restrict__ slope,
+                                          long long rows, int C4) {
+    const long long total = rows * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        float f[4];
+        V4<T>::ld(x + i * 4, f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = f[k];
+            if (scale) v = v * scale[c + k] + shift[c + k];
+            if (slope) v = v > 0.f ? v : v * slope[c + k];
+            f[k] = v;
+        }
+        V4<T>::st(y + i * 4, f);
+    }
+}
+
+// ---- face crop for the CosFace backbone: affine_grid + grid_sample(bilinear, zeros, align_corners) then
+//      bilinear resize to out_hw x out_hw (align_corners) -- meta_net.py:253-262.  faces is [B][H][W][6]
+//      (two stacked RGB crops, face_id.py:598-644); output image f = chunk*B + b, NHWC with Cpad channels.
+__device__ __forceinline__ float warp_src(const float* __restrict__ img, int H, int W, int cstride, float gy, float gx) {
+    // grid_sample with align_corners=True: normalised (gx,gy) -> pixel coordinates, zero padding
+    const float ix = (gx + 1.f) * 0.5f * (W - 1), iy = (gy + 1.f) * 0.5f * (H - 1);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - x0f, wy1 = iy - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    float acc = 0.f;
+    if (y0 >= 0 && y0 < H) {
+        if (x0 >= 0 && x0 < W) acc += img[((size_t)y0 * W + x0) * cstride] * wy0 * wx0;
+        if (x1 >= 0 && x1 < W) acc += img[((size_t)y0 * W + x1) * cstride] * wy0 * wx1;
+    }
+    if (y1 >= 0 && y1 < H) {
+        if (x0 >= 0 && x0 < W) acc += img[((size_t)y1 * W + x0) * cstride] * wy1 * wx0;
+        if (x1 >= 0 && x1 < W) acc += img[((size_t)y1 * W + x1) * cstride] * wy1 * wx1;
+    }
+    return acc;
+}
+__global__ void face_warp_resize_kernel(const float* __restrict__ faces, void* __restrict__ out, int odt, int B, int H,
+                                        int W, int n_chunks, int out_hw, int Cpad, float m00, float m01, float m02,
+                                        float m10, float m11, float m12) {
+    const int total = n_chunks * B * out_hw * out_hw * Cpad;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = idx % Cpad;
+    int t = idx / Cpad;
+    const int j = t % out_hw; t /= out_hw;
+    const int i = t % out_hw;
+    const int f = t / out_hw;
+    float v = 0.f;
+    if (c < 3) {
+        const int chunk = f / B, b = f - chunk * B;
+        const int cs = 3 * n_chunks;
+        const float* img = faces + (size_t)b * H * W * cs + chunk * 3 + c;
+        const float sy = (float)i * (float)(H - 1) / (float)(out_hw - 1);
+        const float sx = (float)j * (float)(W - 1) / (float)(out_hw - 1);
+        const int y0 = (int)floorf(sy), x0 = (int)floorf(sx);
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+        const float wy[2] = {1.f - ly, ly}, wx[2] = {1.f - lx, lx};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                // warped pixel (ys[a], xs[bb]) = grid_sample(img, affine_grid)
+                const float gx0 = -1.f + 2.f * xs[bb] / (float)(W - 1);
+                const float gy0 = -1.f + 2.f * ys[a] / (float)(H - 1);
+                const float gx = m00 * gx0 + m01 * gy0 + m02;
+                const float gy = m10 * gx0 + m11 * gy0 + m12;
+                v += wy[a] * wx[bb] * warp_src(img, H, W, cs, gy, gx);
+            }
+    }
+    st_any(out, odt, (size_t)idx, v);
+}
+
+// ---- row L2 normalise: F.normalize(x, dim=-1, p=2) (meta_net.py:264) ------------------------------------------
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int D) {
+    __shared__ float red[8];
+    const float* xr = x + (size_t)blockIdx.x * D;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) q += xr[i] * xr[i];
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) y[(size_t)blockIdx.x * D + i] = xr[i] * inv;
+}
+
 static inline int grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
     const long long cap = 32LL * device_sm_count();
@@ -475,6 +570,33 @@ extern "C" int cb_timestep_embedding(const long long* t, void* out, int o_dtype,
     CB_REQUIRE(B > 0 && dim >= 2, CB_ERR_ARG, "timestep_embedding: bad shape");
     const int n = B * (dim / 2);
     timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, out, o_dtype, B, dim, max_period);
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_channel_affine_act(const void* x, void* y, int dtype, const float* scale, const float* shift,
+                                     const float* slope, long long rows, int C, void* stream) {
+    CB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, CB_ERR_ARG, "channel_affine_act: bad shape");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CB_DISPATCH(dtype, T, channel_affine_act_kernel<T><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, slope, rows, C / 4));
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_face_warp_resize(const float* faces, void* out, int o_dtype, int B, int H, int W, int n_chunks,
+                                   int out_hw, int Cpad, const float* host_affine6, void* stream) {
+    CB_REQUIRE(B > 0 && H > 1 && W > 1 && n_chunks > 0 && out_hw > 1 && Cpad >= 3 && host_affine6, CB_ERR_ARG, "face_warp_resize: bad args");
+    const int total = n_chunks * B * out_hw * out_hw * Cpad;
+    face_warp_resize_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        faces, out, o_dtype, B, H, W, n_chunks, out_hw, Cpad, host_affine6[0], host_affine6[1], host_affine6[2],
+        host_affine6[3], host_affine6[4], host_affine6[5]);
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* stream) {
+    CB_REQUIRE(rows > 0 && D > 0, CB_ERR_ARG, "l2norm_rows: bad shape");
+    l2norm_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, D);
     CB_CUDA(cudaGetLastError());
     return 0;
 }

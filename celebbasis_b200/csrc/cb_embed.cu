@@ -191,9 +191,30 @@ __global__ void posterior_sample_kernel(const float* __restrict__ moments, const
     }
 }
 
+// x_t = sqrt(acp[t]) * x0 + sqrt(1-acp[t]) * noise, t read on the device (ddpm.py:289-292, util.py:96-99)
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
+                                const float* __restrict__ sqrt_1mac, float* __restrict__ out, int per_sample) {
+    const int b = blockIdx.y;
+    const float a = sqrt_ac[t[b]], s = sqrt_1mac[t[b]];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+        const size_t k = (size_t)b * per_sample + i;
+        out[k] = a * x0[k] + s * noise[k];
+    }
+}
+
 }  // namespace cb
 
 using namespace cb;
+
+extern "C" int cb_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
+                           const float* sqrt_1mac, float* out, int B, int per_sample, void* stream) {
+    CB_REQUIRE(B > 0 && per_sample > 0, CB_ERR_ARG, "q_sample: bad shape");
+    dim3 grid((unsigned)((per_sample + 255) / 256 > 64 ? 64 : (per_sample + 255) / 256), (unsigned)B);
+    q_sample_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
+    CB_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int cb_embedding_gather(const long long* ids, const float* table, float* out, int n, int D, int V,
                                    void* stream) {

@@ -364,3 +364,110 @@ def timestep_embedding(t, dim, dtype=torch.float16, max_period=10000.0):
     _lib.check(_L().cb_timestep_embedding(_p(t), _p(out), _dt(out), t.shape[0], dim, max_period, _st()),
                "cb_timestep_embedding")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CosFace front end / celeb-basis embedding path / optimiser (fp32 side kernels)
+# ------------------------------------------------------------------------------------------------
+def channel_affine_act(x, scale=None, shift=None, slope=None, out=None):
+    rows, C = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    _lib.check(_L().cb_channel_affine_act(_p(x), _p(y), _dt(x), _p(scale), _p(shift), _p(slope), rows, C, _st()),
+               "cb_channel_affine_act")
+    return y
+
+
+def face_warp_resize(faces, n_chunks, affine6, out_hw=112, cpad=8, dtype=torch.float16):
+    """faces: [B][H][W][3*n_chunks] fp32 -> ([n_chunks*B*out_hw*out_hw][cpad], Geo)."""
+    B, H, W, C = faces.shape
+    assert C == 3 * n_chunks and faces.dtype == torch.float32 and faces.is_contiguous()
+    out = torch.empty(n_chunks * B * out_hw * out_hw, cpad, dtype=dtype, device=faces.device)
+    arr = (ctypes.c_float * 6)(*[float(v) for v in affine6])
+    _lib.check(_L().cb_face_warp_resize(_p(faces), _p(out), _dt(out), B, H, W, n_chunks, out_hw, cpad, arr, _st()),
+               "cb_face_warp_resize")
+    return out, Geo(n_chunks * B, out_hw, out_hw)
+
+
+def l2norm_rows(x):
+    y = torch.empty_like(x)
+    _lib.check(_L().cb_l2norm_rows(_p(x), _p(y), x.shape[0], x.shape[1], _st()), "cb_l2norm_rows")
+    return y
+
+
+def embedding_gather(ids, table):
+    n = ids.numel()
+    out = torch.empty(n, table.shape[1], dtype=torch.float32, device=table.device)
+    _lib.check(_L().cb_embedding_gather(_p(ids), _p(table), _p(out), n, table.shape[1], table.shape[0], _st()),
+               "cb_embedding_gather")
+    return out
+
+
+def celeb_mlp_fwd(v, W, b, es, slope=0.2):
+    F_, in_dim = v.shape
+    K = W.shape[0] // es
+    pre = torch.empty(F_, es * K, dtype=torch.float32, device=v.device)
+    coef = torch.empty(F_, es, K, dtype=torch.float32, device=v.device)
+    nrm = torch.empty(F_ * es, dtype=torch.float32, device=v.device)
+    _lib.check(_L().cb_celeb_mlp_fwd(_p(v), _p(W), _p(b), _p(pre), _p(coef), _p(nrm), F_, in_dim, K, es, slope, _st()),
+               "cb_celeb_mlp_fwd")
+    return pre, coef, nrm
+
+
+def celeb_basis_fwd(coef, basis):
+    F_, es, K = coef.shape
+    D = basis.shape[2]
+    z = torch.empty(F_, es, D, dtype=torch.float32, device=coef.device)
+    _lib.check(_L().cb_celeb_basis_fwd(_p(coef), _p(basis), _p(z), F_, es, K, D, _st()), "cb_celeb_basis_fwd")
+    return z
+
+
+def celeb_basis_bwd(dz, basis):
+    F_, es, D = dz.shape
+    K = basis.shape[1] - 1
+    dcoef = torch.empty(F_, es, K, dtype=torch.float32, device=dz.device)
+    _lib.check(_L().cb_celeb_basis_bwd(_p(dz), _p(basis), _p(dcoef), F_, es, K, D, _st()), "cb_celeb_basis_bwd")
+    return dcoef
+
+
+def celeb_mlp_bwd(dcoef, coef, nrm, pre, v, dW, db, slope=0.2, gscale=1.0):
+    F_, es, K = coef.shape
+    ws = torch.empty(F_, es * K, dtype=torch.float32, device=v.device)
+    _lib.check(_L().cb_celeb_mlp_bwd(_p(dcoef), _p(coef), _p(nrm), _p(pre), _p(v), _p(ws), _p(dW), _p(db), F_,
+                                     v.shape[1], K, es, slope, gscale, _st()), "cb_celeb_mlp_bwd")
+    return dW, db
+
+
+def embed_inject_fwd(tok, z_rows, map_, pos, B, T):
+    D = tok.shape[1]
+    out = torch.empty(B * T, D, dtype=torch.float32, device=tok.device)
+    _lib.check(_L().cb_embed_inject_fwd(_p(tok), _p(z_rows), _p(map_), _p(pos), _p(out), B, T, D, _st()),
+               "cb_embed_inject_fwd")
+    return out
+
+
+def embed_inject_bwd(dout, map_, n_z_rows, B, T):
+    D = dout.shape[1]
+    dz = torch.empty(n_z_rows, D, dtype=torch.float32, device=dout.device)
+    _lib.check(_L().cb_embed_inject_bwd(_p(dout), _p(map_), _p(dz), n_z_rows, B, T, D, _st()), "cb_embed_inject_bwd")
+    return dz
+
+
+def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=0, step_dev=None):
+    _lib.check(_L().cb_adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                  _p(step_dev), _st()), "cb_adamw_step")
+
+
+def posterior_sample(moments_nchw, eps, scale):
+    N, C2, H, W = moments_nchw.shape
+    z = torch.empty(N, C2 // 2, H, W, dtype=torch.float32, device=moments_nchw.device)
+    _lib.check(_L().cb_posterior_sample(_p(moments_nchw), _p(eps), _p(z), N, C2 // 2, H * W, scale, _st()),
+               "cb_posterior_sample")
+    return z
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
+    out = torch.empty_like(x0)
+    B = x0.shape[0]
+    _lib.check(_L().cb_q_sample(_p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), B, x0.numel() // B,
+                                _st()), "cb_q_sample")
+    return out

@@ -1,0 +1,195 @@
+"""One CelebBasis training step on the sm_100a kernels.
+
+    image --VAE encode--> z --q_sample(t, noise)--> x_t --\
+    faces --warp/resize--> CosFace R100 --> v -- MLP(W,b) --> coef --basis--> 2 token embeddings      UNet --> eps
+    caption --tokenise--> ids --gather--> token rows --inject @placeholder--> +pos --> CLIP text --> context --/
+    loss = MSE(eps, noise);  backward: UNet -> d(context) -> CLIP -> d(embeddings) -> d(W), d(b);  AdamW.
+
+This is the function LatentDiffusion.shared_step + loss.backward() + optimizer.step() of the reference performs
+(ldm/models/diffusion/ddpm.py:921-936,1069-1116,1442-1454).  Forward and backward are launched back to back so the
+whole step can be captured in one CUDA graph; torch is used for buffers, streams and the graph only.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .clip_engine import CLIPTextEngine
+from .iresnet_engine import IResNetEngine
+from .unet_engine import UNetEngine
+from .vae_engine import VAEEncoderEngine
+
+TRANS_MATRIX = (1.07695457, -0.03625215, -1.56352194 / 512, 0.03625215, 1.07695457, -5.32134629 / 512)
+
+
+def get_rep_pos(tokenized, rep_tokens):
+    """ldm/modules/id_embedding/helpers.py:6-10 on a host int array."""
+    tok = np.asarray(tokenized)
+    return [np.where(tok == int(t))[0] for t in rep_tokens]
+
+
+def placeholder_row_map(n_rows, r_pos, reps):
+    """Host mirror of shift_tensor_dim0 (helpers.py:13-41) expressed as a gather map.
+
+    Returns (src, final_pos): src[i] = index of the ORIGINAL row that sits in row i after the reference's two
+    in-place advanced-index writes; final_pos[k] = (occurrences, reps) array of rows that then receive the learned
+    embeddings for placeholder k.  Pure integer arithmetic, bit-exact with the reference."""
+    offset = np.zeros(n_rows, dtype=np.int64)
+    cat = np.concatenate(r_pos) if len(r_pos) else np.zeros(0, dtype=np.int64)
+    for p in cat:
+        offset[p + 1:] += reps - 1
+    n_occ = cat.shape[0]
+    target = (np.arange(n_rows) + offset)[: n_rows - n_occ * (reps - 1)]
+    src = np.arange(n_rows)
+    src[target] = np.arange(target.shape[0])                     # "shift words"
+    final = target[cat].repeat(reps) + np.tile(np.arange(reps), n_occ)
+    before = src.copy()
+    src[final] = before[target[cat].repeat(reps)]                # "fill blanks with repeat words"
+    out, lo = [], 0
+    for p in r_pos:
+        k = p.shape[0]
+        out.append(final[lo: lo + k * reps].reshape(k, reps))
+        lo += k * reps
+    return src, out
+
+
+def build_inject_map(ids, placeholder_token, reps, z_row_of_sample):
+    """ids: (B,T) host int64.  map[b][i] >= 0: take token row map of prompt b; < 0: take z row -(map+1).
+    (EmbeddingManagerId.forward, num_ids == 1 branch, embedding_manager.py:347-360.)"""
+    ids = np.asarray(ids)
+    B, T = ids.shape
+    m = np.zeros((B, T), dtype=np.int32)
+    positions = []
+    for b in range(B):
+        pos = get_rep_pos(ids[b], [placeholder_token])
+        src, fin = placeholder_row_map(T, pos, reps)
+        row = src.astype(np.int32)
+        for one_pos in fin[0]:
+            for j, p in enumerate(one_pos):
+                row[int(p)] = -(z_row_of_sample(b) * reps + j + 1)
+        m[b] = row
+        positions.append(fin)
+    return m, positions
+
+
+class CelebBasisStep:
+    def __init__(self, params, state_dict, basis, device, *, tokenizer, placeholder="sks", clip_layers=None,
+                 dtype=torch.float16, loss_scale=1024.0, vae_res_dtype=torch.float32, lr=5e-3):
+        self.dev = torch.device(device)
+        self.dt = dtype
+        sd = state_dict
+        sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        self.unet = UNetEngine(params["unet_config"]["params"], sub("model.diffusion_model."), self.dev, dtype=dtype,
+                               loss_scale=loss_scale)
+        self.clip = CLIPTextEngine(sub("cond_stage_model.transformer."), self.dev, dtype=dtype, loss_scale=loss_scale)
+        fs = params["first_stage_config"]["params"]
+        self.vae = VAEEncoderEngine(fs["ddconfig"], fs["embed_dim"], sub("first_stage_model."), self.dev, dtype=dtype,
+                                    res_dtype=vae_res_dtype)
+        self.face = IResNetEngine(sub("embedding_manager.meta_id_net.id_model."), self.dev, dtype=dtype)
+        pc = params["personalization_config"]["params"]
+        self.es = pc["num_embeds_per_token"]
+        self.K = pc["meta_inner_dim"]
+        self.momentum = pc.get("momentum", 0.9)
+        self.max_ids = pc.get("max_ids", 10)
+        self.W = sd["embedding_manager.meta_id_net.stylegan_mlp.net.0.weight"].detach().to(self.dev, torch.float32).contiguous()
+        self.b = sd["embedding_manager.meta_id_net.stylegan_mlp.net.0.bias"].detach().to(self.dev, torch.float32).contiguous()
+        # trainable tensors live in ONE flat fp32 buffer (what the data-parallel all-reduce and AdamW operate on)
+        self.flat = torch.cat([self.W.flatten(), self.b.flatten()]).contiguous()
+        self.W = self.flat[: self.W.numel()].view_as(self.W)
+        self.b = self.flat[self.W.numel():]
+        self.grad = torch.zeros_like(self.flat)
+        self.gW = self.grad[: self.W.numel()].view_as(self.W)
+        self.gb = self.grad[self.W.numel():]
+        self.adam_m = torch.zeros_like(self.flat)
+        self.adam_v = torch.zeros_like(self.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.lr = lr
+        self.basis = basis.detach().to(self.dev, torch.float32).contiguous()
+        self.tokenizer = tokenizer
+        self.placeholder_token = int(tokenizer(placeholder)["input_ids"][0, 1])
+        self.scale_factor = float(params["scale_factor"])
+        # schedule (ddpm.py:126-178; util.py:21-25: float64 linspace of sqrt(beta), squared)
+        T = params["timesteps"]
+        betas = torch.linspace(params["linear_start"] ** 0.5, params["linear_end"] ** 0.5, T, dtype=torch.float64) ** 2
+        ac = np.cumprod(1.0 - betas.numpy(), axis=0)
+        self.sqrt_ac = torch.tensor(np.sqrt(ac), dtype=torch.float32, device=self.dev)
+        self.sqrt_1mac = torch.tensor(np.sqrt(1.0 - ac), dtype=torch.float32, device=self.dev)
+        self.num_timesteps = T
+        # per-identity EMA side state (embedding_manager.py:229-231,484-489)
+        self.id_coefficients = torch.zeros(self.max_ids, self.es, 1, self.K, dtype=torch.float32, device=self.dev)
+        self.id_embeddings = torch.zeros(self.max_ids, self.es, self.clip.hidden, dtype=torch.float32, device=self.dev)
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------
+    def tokenize(self, captions):
+        return self.tokenizer(captions, truncation=True, max_length=77, return_length=True,
+                              return_overflowing_tokens=False, padding="max_length", return_tensors="pt")["input_ids"]
+
+    def encode_first_stage(self, image_nhwc, posterior_eps):
+        """get_input (ddpm.py:344-350,702-759): HWC->CHW, VAE encode, posterior sample * scale_factor."""
+        x = image_nhwc.permute(0, 3, 1, 2).contiguous().float()   # layout glue exactly as ddpm.py:348-349
+        moments = self.vae.encode_moments(x)
+        z = ops.posterior_sample(moments, posterior_eps.contiguous(), self.scale_factor)
+        return z, moments
+
+    def face_features(self, faces, n_chunks):
+        x, geo = ops.face_warp_resize(faces.contiguous(), n_chunks, TRANS_MATRIX, out_hw=112, cpad=8, dtype=self.dt)
+        feat = self.face.forward(x, geo)
+        return ops.l2norm_rows(feat)
+
+    def q_sample(self, z, t, noise):
+        """ddpm.py:289-292 per sample (the two coefficients are device scalars gathered by t)."""
+        return ops.q_sample(z.contiguous(), noise.contiguous(), t.contiguous(), self.sqrt_ac, self.sqrt_1mac)
+
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self, batch, draws, need_grad=True, ema_update=True):
+        """batch: dict as face_id.py:598-644 yields (tensors on self.dev); draws: t (B,), noise, posterior_eps.
+        Returns the loss (1-element device tensor).  Gradients of (W,b) land in self.grad."""
+        image = batch["image"]
+        B = image.shape[0]
+        io = batch["image_ori"]
+        faces, ids_person = io["faces"], io["ids"]
+        n_chunks = ids_person.shape[1]
+        z, _ = self.encode_first_stage(image, draws["posterior_eps"])
+        v = self.face_features(faces, n_chunks)                                  # (n_chunks*B, 512)
+        pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
+        zc = ops.celeb_basis_fwd(coef, self.basis)                               # (F, es, 768)
+        ids = self.tokenize(batch["caption"])
+        map_np, positions = build_inject_map(ids.numpy(), self.placeholder_token, self.es, lambda b: b)
+        ids_dev = ids.to(self.dev)
+        map_dev = torch.from_numpy(map_np).to(self.dev)
+        T = ids.shape[1]
+        tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
+        emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
+        context = self.clip.forward(emb, B, need_grad=need_grad)                 # (B*T, 768) fp32
+        t = draws["t"]
+        noise = draws["noise"].contiguous()
+        x_noisy = self.q_sample(z, t, noise)
+        eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
+        loss, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)
+        self.last = dict(z=z, context=context.view(B, T, -1), eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
+                         face_feat=v, positions=positions, ids=ids)
+        if ema_update:
+            self._ema_update(zc, coef, ids_person, B)
+        if need_grad:
+            dctx = self.unet.backward(d_eps)
+            demb = self.clip.backward(dctx.view(B * T, -1))
+            dz = ops.embed_inject_bwd(demb, map_dev.view(-1), zc.shape[0] * self.es, B, T)
+            dcoef = ops.celeb_basis_bwd(dz.view(zc.shape), self.basis)
+            ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, self.gW, self.gb)
+        return loss
+
+    def _ema_update(self, zc, coef, ids_person, B):
+        """_momentum_update, training branch (embedding_manager.py:484-489) for the main identity of each sample."""
+        m = self.momentum
+        idl = ids_person[:, 0].tolist()   # identity indices are host data (face_id.py:598-644)
+        for b in range(B):
+            i = int(idl[b])
+            if i < self.max_ids:
+                ops.axpby(self.id_embeddings[i], m, zc[b], 1.0 - m, out=self.id_embeddings[i])
+                ops.axpby(self.id_coefficients[i].view(self.es, self.K), m, coef[b], 1.0 - m,
+                          out=self.id_coefficients[i].view(self.es, self.K))
+
+    def optimizer_step(self, lr=None):
+        """torch.optim.AdamW defaults (ddpm.py:1442-1454): betas (.9,.999), eps 1e-8, weight_decay 1e-2."""
+        ops.adamw_step(self.flat, self.grad, self.adam_m, self.adam_v, lr=self.lr if lr is None else lr,
+                       step_dev=self.step_dev)

@@ -1,0 +1,125 @@
+"""AutoencoderKL.encode (first-stage encoder + quant_conv) on the sm_100a kernels, forward only / no grad.
+
+Mirrors ldm/models/autoencoder.py:324-328 -> ldm/modules/diffusionmodules/model.py:434-459 (Encoder.forward),
+:82-141 (ResnetBlock), :150-202 (AttnBlock: 1 head over all pixels), :60-79 (Downsample: pad (0,1,0,1) + stride 2).
+The largest single item of a training step (1.1 TFLOP at 512x512): every conv is the same TMA-shifted implicit
+GEMM as the UNet's, GroupNorm(eps 1e-6)+swish is the fused norm kernel, the 4096-token attention reuses the
+batched GEMM + softmax path with head_dim = 512.
+"""
+import torch
+
+from . import ops
+from .ops import Geo
+from .unet_engine import _Attn, _round_up
+
+
+class VAEEncoderEngine:
+    def __init__(self, ddconfig, embed_dim, state_dict, device, *, prefix="", dtype=torch.float16,
+                 res_dtype=torch.float32):
+        self.dev = torch.device(device)
+        self.dt = dtype
+        self.rt = res_dtype
+        sd, p = state_dict, prefix
+        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
+        w16 = lambda t: t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+        pack = lambda k, **kw: ops.pack_conv_weight(sd[p + k].to(self.dev), self.dt, **kw)
+        ch, mult, nres = ddconfig["ch"], ddconfig["ch_mult"], ddconfig["num_res_blocks"]
+        self.in_ch = ddconfig["in_channels"]
+        self.in_pad = _round_up(self.in_ch, 8)
+        self.zc2 = 2 * ddconfig["z_channels"] if ddconfig.get("double_z", True) else ddconfig["z_channels"]
+        self.conv_in_w, self.conv_in_b = pack("encoder.conv_in.weight", cin_pad=self.in_pad), f32(sd[p + "encoder.conv_in.bias"])
+        self.ch0 = ch
+
+        def res(pre, cin, cout):
+            w = {"cin": cin, "cout": cout,
+                 "g1": f32(sd[pre + "norm1.weight"]), "b1": f32(sd[pre + "norm1.bias"]),
+                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"].to(self.dev), self.dt), "c1b": f32(sd[pre + "conv1.bias"]),
+                 "g2": f32(sd[pre + "norm2.weight"]), "b2": f32(sd[pre + "norm2.bias"]),
+                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"].to(self.dev), self.dt), "c2b": f32(sd[pre + "conv2.bias"])}
+            if cin != cout:
+                w["ws"] = w16(sd[pre + "nin_shortcut.weight"].reshape(cout, cin))
+                w["bs"] = f32(sd[pre + "nin_shortcut.bias"])
+            else:
+                w["ws"] = None
+            return w
+
+        in_mult = (1,) + tuple(mult)
+        self.levels = []
+        bin_ = ch
+        for i in range(len(mult)):
+            bin_, bout = ch * in_mult[i], ch * mult[i]
+            blocks = []
+            for j in range(nres):
+                blocks.append(res(p + f"encoder.down.{i}.block.{j}.", bin_, bout))
+                bin_ = bout
+            down = None
+            if i != len(mult) - 1:
+                dk = p + f"encoder.down.{i}.downsample.conv."
+                down = {"w": ops.pack_conv_weight(sd[dk + "weight"].to(self.dev), self.dt), "b": f32(sd[dk + "bias"]), "c": bin_}
+            self.levels.append((blocks, down))
+        self.mid1 = res(p + "encoder.mid.block_1.", bin_, bin_)
+        self.mid2 = res(p + "encoder.mid.block_2.", bin_, bin_)
+        ak = p + "encoder.mid.attn_1."
+        c = bin_
+        self.attn = {"c": c, "gn": f32(sd[ak + "norm.weight"]), "bn": f32(sd[ak + "norm.bias"]),
+                     "wqkv": w16(torch.cat([sd[ak + "q.weight"].reshape(c, c), sd[ak + "k.weight"].reshape(c, c),
+                                            sd[ak + "v.weight"].reshape(c, c)], 0)),
+                     "bqkv": f32(torch.cat([sd[ak + "q.bias"], sd[ak + "k.bias"], sd[ak + "v.bias"]], 0)),
+                     "wo": w16(sd[ak + "proj_out.weight"].reshape(c, c)), "bo": f32(sd[ak + "proj_out.bias"])}
+        self.no_g, self.no_b = f32(sd[p + "encoder.norm_out.weight"]), f32(sd[p + "encoder.norm_out.bias"])
+        self.c_last = bin_
+        self.out_rows = _round_up(self.zc2, 16)
+        self.conv_out_w = pack("encoder.conv_out.weight", cout_pad=self.out_rows)
+        cb = torch.zeros(self.out_rows, dtype=torch.float32, device=self.dev)
+        cb[: self.zc2] = f32(sd[p + "encoder.conv_out.bias"])
+        self.conv_out_b = cb
+        qw = sd[p + "quant_conv.weight"]
+        self.q_out = qw.shape[0]
+        qpad = torch.zeros(self.q_out, _round_up(self.zc2, 8), dtype=torch.float32)
+        qpad[:, : self.zc2] = qw.reshape(self.q_out, self.zc2)
+        self.quant_w, self.quant_b = w16(qpad), f32(sd[p + "quant_conv.bias"])
+        self.mid_pad = _round_up(self.zc2, 8)
+
+    def _res(self, w, x, geo):
+        a, _ = ops.groupnorm(x, geo, w["g1"], w["b1"], eps=1e-6, silu=True, out_dtype=self.dt)
+        h, _ = ops.conv2d(a, geo, w["w1"], w["cout"], bias=w["c1b"], out_dtype=self.dt)
+        b, _ = ops.groupnorm(h, geo, w["g2"], w["b2"], eps=1e-6, silu=True, out_dtype=self.dt)
+        if w["ws"] is None:
+            resid = x
+        else:
+            x16 = x if x.dtype == self.dt else ops.cast(x, self.dt)
+            resid = ops.linear(x16, w["ws"], w["bs"], out_dtype=self.rt)
+        out, _ = ops.conv2d(b, geo, w["w2"], w["cout"], bias=w["c2b"], out_dtype=self.rt, residual=resid)
+        return out
+
+    def _attn(self, x, geo):
+        w = self.attn
+        c = w["c"]
+        n, _ = ops.groupnorm(x, geo, w["gn"], w["bn"], eps=1e-6, silu=False, out_dtype=self.dt)
+        qkv = ops.linear(n, w["wqkv"], w["bqkv"])
+        o = torch.empty(geo.rows, c, dtype=self.dt, device=self.dev)
+        _Attn.fwd(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], images=geo.n, heads=1, dh=c, nq=geo.hw, nk=geo.hw,
+                  scale=float(c) ** -0.5, out=o)
+        return ops.linear(o, w["wo"], w["bo"], out_dtype=self.rt, residual=x)
+
+    @torch.no_grad()
+    def encode_moments(self, x):
+        """x: (B,3,H,W) fp32 NCHW in [-1,1] -> moments (B, 2*z, H/8, W/8) fp32 NCHW (the posterior parameters)."""
+        x16, geo = ops.nchw_to_nhwc(x.contiguous().float(), self.in_pad, self.dt)
+        h, _ = ops.conv2d(x16, geo, self.conv_in_w, self.ch0, bias=self.conv_in_b, out_dtype=self.rt)
+        for blocks, down in self.levels:
+            for w in blocks:
+                h = self._res(w, h, geo)
+            if down is not None:
+                h16 = h if h.dtype == self.dt else ops.cast(h, self.dt)
+                h, geo = ops.conv2d(h16, geo, down["w"], down["c"], bias=down["b"], stride=2, pad=(0, 1, 0, 1),
+                                    out_dtype=self.rt)
+        h = self._res(self.mid1, h, geo)
+        h = self._attn(h, geo)
+        h = self._res(self.mid2, h, geo)
+        a, _ = ops.groupnorm(h, geo, self.no_g, self.no_b, eps=1e-6, silu=True, out_dtype=self.dt)
+        m = torch.zeros(geo.rows, self.mid_pad, dtype=self.dt, device=self.dev) if self.mid_pad != self.zc2 else \
+            torch.empty(geo.rows, self.mid_pad, dtype=self.dt, device=self.dev)
+        ops.conv2d(a, geo, self.conv_out_w, self.zc2, bias=self.conv_out_b, out=m, cout_rows=self.out_rows)
+        q = ops.linear(m, self.quant_w, self.quant_b, out_dtype=torch.float32)
+        return ops.nhwc_to_nchw(q, geo, self.q_out)

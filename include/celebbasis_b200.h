@@ -217,6 +217,24 @@ int cb_adamw_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float eps, float weight_decay, int step, int* step_dev, void* stream);
 int cb_posterior_sample(const float* moments, const float* eps, float* z, int N, int Cz, int HW, float scale,
                         void* stream);
+/* cb_q_sample: DDPM.q_sample (ddpm.py:289-292) with the timestep read on the device: out = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise */
+int cb_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
+                float* out, int B, int per_sample, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CosFace-R100 front end (no-grad): meta_net.py:253-264, iresnet.py:26-64.
+ * cb_face_warp_resize: fixed 2x3 affine warp (affine_grid + grid_sample bilinear/zeros/align_corners) of the
+ *   [B][H][W][3*n_chunks] face stack followed by bilinear resize to out_hw (align_corners), NHWC output with
+ *   Cpad channels, image f = chunk*B + b (torch.cat(chunk(...), 0) order, meta_net.py:336-337).
+ *   host_affine6 is a HOST pointer to the 6 matrix entries (trans_matrix, meta_net.py:131-142).
+ * cb_channel_affine_act: eval BatchNorm2d as y = x*scale[c]+shift[c] and/or PReLU slope[c] (either may be NULL).
+ * cb_l2norm_rows: F.normalize(v, dim=-1).
+ * ------------------------------------------------------------------------------------------- */
+int cb_channel_affine_act(const void* x, void* y, int dtype, const float* scale, const float* shift,
+                          const float* slope, long long rows, int C, void* stream);
+int cb_face_warp_resize(const float* faces, void* out, int o_dtype, int B, int H, int W, int n_chunks, int out_hw,
+                        int Cpad, const float* host_affine6, void* stream);
+int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* stream);
 
 #ifdef __cplusplus
 }
