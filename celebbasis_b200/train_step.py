@@ -176,6 +176,7 @@ class CelebBasisStep:
             dz = ops.embed_inject_bwd(demb, map_dev.view(-1), zc.shape[0] * self.es, B, T)
             dcoef = ops.celeb_basis_bwd(dz.view(zc.shape), self.basis)
             ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, self.gW, self.gb)
+            self.last.update(d_eps=d_eps, dctx=dctx, demb=demb, dz=dz, dcoef=dcoef)
         return loss
 
     def _ema_update(self, zc, coef, ids_person, B):

@@ -18,7 +18,7 @@ def model_params(kind="full"):
                 num_heads=8, use_spatial_transformer=True, transformer_depth=1, context_dim=768,
                 use_checkpoint=True, legacy=False)
     dd = dict(double_z=True, z_channels=4, resolution=512 if full else 64, in_channels=3, out_ch=3,
-              ch=128 if full else 32, ch_mult=[1, 2, 4, 4], num_res_blocks=2 if full else 1, attn_resolutions=[],
+              ch=128 if full else 64, ch_mult=[1, 2, 4, 4], num_res_blocks=2 if full else 1, attn_resolutions=[],
               dropout=0.0)
     return dict(
         linear_start=0.00085, linear_end=0.0120, num_timesteps_cond=1, log_every_t=200, timesteps=1000,

@@ -648,6 +648,9 @@ class OracleModel(nn.Module):
         x_noisy = q_sample(self.sched, z, t, noise)
         eps = self.model.diffusion_model(x_noisy, t, context)
         loss = eps_loss(eps, noise)
+        for tns in (emb, context, zc, coef, eps):
+            if tns.requires_grad:
+                tns.retain_grad()
         out.update(loss=loss, z=z, moments=moments, context=context, eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
-                   face_feat=v, positions=pos)
+                   face_feat=v, positions=pos, emb=emb)
         return out
