@@ -20,7 +20,7 @@ SIGS = {
     "cb_zero_insert2x": [_p, _p, _i, _i, _i, _i, _i, _p],
     "cb_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
     "cb_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _p],
-    "cb_mse_fwd_bwd": [_p, _p, _p, _p, _l, _f, _p],
+    "cb_mse_fwd_bwd": [_p, _p, _p, _p, _i, _i, _f, _p],
     "cb_timestep_embedding": [_p, _p, _i, _i, _i, _f, _p],
     "cb_embedding_gather": [_p, _p, _p, _i, _i, _i, _p],
     "cb_celeb_mlp_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
@@ -31,8 +31,9 @@ SIGS = {
     "cb_embed_inject_bwd": [_p, _p, _p, _i, _i, _i, _i, _p],
     "cb_adamw_step": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _p],
     "cb_posterior_sample": [_p, _p, _p, _i, _i, _i, _f, _p],
+    "cb_ddim_step": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _p],
     "cb_q_sample": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "cb_channel_affine_act": [_p, _p, _i, _p, _p, _p, _l, _i, _p],
+    "cb_channel_affine_act": [_p, _i, _p, _i, _p, _p, _p, _l, _i, _p],
     "cb_face_warp_resize": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "cb_l2norm_rows": [_p, _p, _i, _i, _p],
 }

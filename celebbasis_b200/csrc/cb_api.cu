@@ -31,7 +31,13 @@ int device_sm_count() {
     return n;
 }
 
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long get_launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 }  // namespace cb
+
+extern "C" unsigned long long cb_launch_count(void) { return cb::get_launches(); }
 
 extern "C" int cb_abi_version(void) { return CB_ABI_VERSION; }
 

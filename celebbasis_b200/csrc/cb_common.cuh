@@ -40,6 +40,7 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int device_sm_count();
+void count_launches(int n);  // bookkeeping for cb_launch_count()
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

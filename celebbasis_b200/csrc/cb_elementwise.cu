@@ -297,16 +297,19 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, float* 
 }
 
 // ---- eps-MSE loss + its gradient (ddpm.py:294-307 get_loss 'l2', :1084-1096) -------------------------------
-// loss = mean((pred-target)^2) per batch item averaged over the batch; grad = 2*(pred-target)/n * gscale.
+// loss[b] = mean_i (pred[b,i]-target[b,i])^2  (loss_simple, one value per sample);
+// grad = d(mean_b loss[b]) / d pred * gscale = 2*(pred-target)/(B*per_sample) * gscale.
 __global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                                   float* __restrict__ loss, float* __restrict__ grad, long long n, float gscale) {
+                                   float* __restrict__ loss, float* __restrict__ grad, int per_sample, float ginv,
+                                   float gscale) {
     __shared__ float red[8];
+    const int b = blockIdx.y;
+    const size_t base = (size_t)b * per_sample;
     float acc = 0.f;
-    const float inv = 1.f / (float)n;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float d = pred[i] - target[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+        const float d = pred[base + i] - target[base + i];
         acc += d * d;
-        if (grad) grad[i] = 2.f * d * inv * gscale;
+        if (grad) grad[base + i] = 2.f * d * ginv * gscale;
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -314,7 +317,7 @@ __global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* 
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-        atomicAdd(loss, s * inv);
+        atomicAdd(loss + b, s / (float)per_sample);
     }
 }
 
@@ -333,8 +336,8 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, void*
 }
 
 // ---- per-channel affine (+ optional PReLU): eval-mode BatchNorm2d / nn.PReLU of iresnet.py:26-64 -------------
-template <typename T>
-__global__ void channel_affine_act_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ scale,
+template <typename T, typename TY>
+__global__ void channel_affine_act_kernel(const T* __restrict__ x, TY* __restrict__ y, const float* __restrict__ scale,
                                           const float* __restrict__ shift, const float* __restrict__ slope,
                                           long long rows, int C4) {
     const long long total = rows * C4;
@@ -350,7 +353,7 @@ __global__ void channel_affine_act_kernel(const T* __restrict__ x, T* __restrict
             if (slope) v = v > 0.f ? v : v * slope[c + k];
             f[k] = v;
         }
-        V4<T>::st(y + i * 4, f);
+        V4<TY>::st(y + i * 4, f);
     }
 }
 
@@ -461,6 +464,7 @@ extern "C" int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, co
     CB_DISPATCH(x_dtype, TX, CB_DISPATCH(y_dtype, TY, CB_DISPATCH(o_dtype, TO,
         axpby2d_kernel<TX, TY, TO><<<grid, 256, 0, st>>>((const TX*)x, ldx, a, (const TY*)y, ldy, b, (TO*)out, ldo, rows, c4))));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -468,6 +472,7 @@ extern "C" int cb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, long
     CB_REQUIRE(n > 0, CB_ERR_ARG, "act_fwd: n<=0");
     act_fwd_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, y, y_dtype, (size_t)n, act);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
@@ -475,6 +480,7 @@ extern "C" int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dty
     CB_REQUIRE(n > 0, CB_ERR_ARG, "act_bwd: n<=0");
     act_bwd_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, (size_t)n, act);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -483,6 +489,7 @@ extern "C" int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, i
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH16(dtype, T, geglu_fwd_kernel<T><<<grid_for(M * (F / 4), 256), 256, 0, st>>>((const T*)in, (T*)out, M, F));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_geglu_bwd(const void* dout, const void* in, void* din, int dtype, int g_dtype, long long M, int F,
@@ -492,6 +499,7 @@ extern "C" int cb_geglu_bwd(const void* dout, const void* in, void* din, int dty
     CB_DISPATCH16(dtype, T, CB_DISPATCH16(g_dtype, TG,
         geglu_bwd_kernel<T, TG><<<grid_for(M * (F / 4), 256), 256, 0, st>>>((const TG*)dout, (const T*)in, (TG*)din, M, F)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -501,6 +509,7 @@ extern "C" int cb_softmax_fwd(const void* s, void* p, int dtype, long long rows,
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH16(dtype, T, softmax_fwd_kernel<T><<<(unsigned)rows, 128, 0, st>>>((const T*)s, (T*)p, ncols, ld, causal_period));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_softmax_bwd(const void* dp, const void* p, void* ds, int p_dtype, int g_dtype, long long rows,
@@ -510,6 +519,7 @@ extern "C" int cb_softmax_bwd(const void* dp, const void* p, void* ds, int p_dty
     CB_DISPATCH16(p_dtype, T, CB_DISPATCH16(g_dtype, TG,
         softmax_bwd_kernel<T, TG><<<(unsigned)rows, 128, 0, st>>>((const TG*)dp, (const T*)p, (TG*)ds, ncols, ld)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -519,6 +529,7 @@ extern "C" int cb_upsample2x_fwd(const void* x, void* y, int dtype, int N, int H
     const long long total = (long long)N * 4 * H * W * (C / 4);
     CB_DISPATCH(dtype, T, upsample2x_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C / 4));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_upsample2x_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int N, int H, int W, int C,
@@ -529,6 +540,7 @@ extern "C" int cb_upsample2x_bwd(const void* dy, int dy_dtype, void* dx, int dx_
     CB_DISPATCH(dy_dtype, TG, CB_DISPATCH(dx_dtype, TD,
         upsample2x_bwd_kernel<TG, TD><<<grid_for(total, 256), 256, 0, st>>>((const TG*)dy, (TD*)dx, N, H, W, C / 4, accumulate)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H, int W, int C, void* stream) {
@@ -537,6 +549,7 @@ extern "C" int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H
     const long long total = (long long)N * 4 * H * W * (C / 4);
     CB_DISPATCH(dtype, T, zero_insert2x_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)dy, (T*)z, N, H, W, C / 4));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -544,24 +557,28 @@ extern "C" int cb_nchw_to_nhwc(const float* x, void* y, int y_dtype, int N, int 
     CB_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C, CB_ERR_ARG, "nchw_to_nhwc: bad shape");
     nchw_to_nhwc_kernel<<<grid_for((long long)N * HW * Cpad, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, y_dtype, N, C, HW, Cpad);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_nhwc_to_nchw(const void* x, int x_dtype, float* y, int N, int C, int HW, int Cpad, void* stream) {
     CB_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C, CB_ERR_ARG, "nhwc_to_nchw: bad shape");
     nhwc_to_nchw_kernel<<<grid_for((long long)N * HW * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, y, N, C, HW, Cpad);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
-extern "C" int cb_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, long long n,
-                              float gscale, void* stream) {
-    CB_REQUIRE(n > 0 && pred && target && loss, CB_ERR_ARG, "mse: bad args");
+extern "C" int cb_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, int B,
+                              int per_sample, float gscale, void* stream) {
+    CB_REQUIRE(B > 0 && per_sample > 0 && pred && target && loss, CB_ERR_ARG, "mse: bad args");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-    int grid = grid_for(n, 256);
-    if (grid > 64) grid = 64;
-    mse_fwd_bwd_kernel<<<grid, 256, 0, st>>>(pred, target, loss, grad, n, gscale);
+    CB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, st));
+    int gx = ceil_div(per_sample, 256);
+    if (gx > 64) gx = 64;
+    mse_fwd_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(pred, target, loss, grad, per_sample,
+                                                    1.f / ((float)B * (float)per_sample), gscale);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -571,15 +588,18 @@ extern "C" int cb_timestep_embedding(const long long* t, void* out, int o_dtype,
     const int n = B * (dim / 2);
     timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, out, o_dtype, B, dim, max_period);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
-extern "C" int cb_channel_affine_act(const void* x, void* y, int dtype, const float* scale, const float* shift,
-                                     const float* slope, long long rows, int C, void* stream) {
+extern "C" int cb_channel_affine_act(const void* x, int x_dtype, void* y, int y_dtype, const float* scale,
+                                     const float* shift, const float* slope, long long rows, int C, void* stream) {
     CB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, CB_ERR_ARG, "channel_affine_act: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_DISPATCH(dtype, T, channel_affine_act_kernel<T><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>((const T*)x, (T*)y, scale, shift, slope, rows, C / 4));
+    CB_DISPATCH(x_dtype, T, CB_DISPATCH(y_dtype, TY,
+        channel_affine_act_kernel<T, TY><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>((const T*)x, (TY*)y, scale, shift, slope, rows, C / 4)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -591,6 +611,7 @@ extern "C" int cb_face_warp_resize(const float* faces, void* out, int o_dtype, i
         faces, out, o_dtype, B, H, W, n_chunks, out_hw, Cpad, host_affine6[0], host_affine6[1], host_affine6[2],
         host_affine6[3], host_affine6[4], host_affine6[5]);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -598,5 +619,6 @@ extern "C" int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* s
     CB_REQUIRE(rows > 0 && D > 0, CB_ERR_ARG, "l2norm_rows: bad shape");
     l2norm_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, D);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }

@@ -203,9 +203,40 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
     }
 }
 
+// DDIM update with classifier-free guidance (ldm/models/diffusion/ddim.py:166-204)
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ e_u, const float* __restrict__ e_c,
+                                 const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                 long long n, float scale, float sqrt_at, float sqrt_aprev, float sigma, float sqrt_1m_at,
+                                 float dir_coef) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float e = e_u[i];
+        if (e_c) e = e + scale * (e_c[i] - e);
+        const float p0 = (x[i] - sqrt_1m_at * e) / sqrt_at;
+        float xp = sqrt_aprev * p0 + dir_coef * e;
+        if (noise) xp += sigma * noise[i];
+        x_prev[i] = xp;
+        if (pred_x0) pred_x0[i] = p0;
+    }
+}
+
 }  // namespace cb
 
 using namespace cb;
+
+extern "C" int cb_ddim_step(const float* x, const float* e_uncond, const float* e_cond, const float* noise,
+                            float* x_prev, float* pred_x0, long long n, float guidance_scale, float a_t, float a_prev,
+                            float sigma_t, float sqrt_one_minus_at, void* stream) {
+    CB_REQUIRE(n > 0 && x && e_uncond && x_prev, CB_ERR_ARG, "ddim_step: bad args");
+    const float dir = sqrtf(fmaxf(1.f - a_prev - sigma_t * sigma_t, 0.f));
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    ddim_step_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, e_uncond, e_cond, noise, x_prev, pred_x0, n, guidance_scale, sqrtf(a_t), sqrtf(a_prev), sigma_t,
+        sqrt_one_minus_at, dir);
+    CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
+    return 0;
+}
 
 extern "C" int cb_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac,
                            const float* sqrt_1mac, float* out, int B, int per_sample, void* stream) {
@@ -213,6 +244,7 @@ extern "C" int cb_q_sample(const float* x0, const float* noise, const long long*
     dim3 grid((unsigned)((per_sample + 255) / 256 > 64 ? 64 : (per_sample + 255) / 256), (unsigned)B);
     q_sample_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -221,6 +253,7 @@ extern "C" int cb_embedding_gather(const long long* ids, const float* table, flo
     CB_REQUIRE(n > 0 && D > 0 && D % 4 == 0 && V > 0, CB_ERR_ARG, "embedding_gather: bad shape");
     embedding_gather_kernel<<<n, 192, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, table, out, n, D, V);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -230,6 +263,7 @@ extern "C" int cb_celeb_mlp_fwd(const float* v, const float* W, const float* b, 
     celeb_mlp_fwd_kernel<<<F * es, 256, (in_dim + K) * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
         v, W, b, pre, coef, nrm, in_dim, K, es, slope);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -238,6 +272,7 @@ extern "C" int cb_celeb_basis_fwd(const float* coef, const float* basis, float* 
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && K * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_fwd: bad shape");
     celeb_basis_fwd_kernel<<<F * es, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(coef, basis, z, K, D, es);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -246,6 +281,7 @@ extern "C" int cb_celeb_basis_bwd(const float* dz, const float* basis, float* dc
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && D * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_bwd: bad shape");
     celeb_basis_bwd_kernel<<<F * es, 256, D * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(dz, basis, dcoef, K, D, es);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -258,6 +294,7 @@ extern "C" int cb_celeb_mlp_bwd(const float* dcoef, const float* coef, const flo
     const int out_dim = es * K;
     celeb_mlp_bwd_w_kernel<<<ceil_div(out_dim * in_dim, 256), 256, 0, st>>>(dpre_ws, v, dW, db, F, out_dim, in_dim);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(2);
     return 0;
 }
 
@@ -266,6 +303,7 @@ extern "C" int cb_embed_inject_fwd(const float* tok, const float* z, const int* 
     CB_REQUIRE(B > 0 && T > 0 && D > 0, CB_ERR_ARG, "embed_inject_fwd: bad shape");
     embed_inject_fwd_kernel<<<B * T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tok, z, map, pos, out, T, D);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -276,6 +314,7 @@ extern "C" int cb_embed_inject_bwd(const float* dout, const int* map, float* dz,
     CB_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n_z_rows * D, st));
     embed_inject_bwd_kernel<<<B * T, 256, 0, st>>>(dout, map, dz, D);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -290,6 +329,7 @@ extern "C" int cb_adamw_step(float* p, const float* g, float* m, float* v, long 
     adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, step_dev);
     if (step_dev) bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(2);
     return 0;
 }
 
@@ -299,5 +339,6 @@ extern "C" int cb_posterior_sample(const float* moments, const float* eps, float
     const long long total = (long long)N * Cz * HW;
     posterior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(moments, eps, z, N, Cz, HW, scale);
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }

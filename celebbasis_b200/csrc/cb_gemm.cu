@@ -397,6 +397,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
     }
     kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(tA, tB, p);
     CB_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }
 

@@ -368,6 +368,7 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
         gn_apply_kernel<TX, TY><<<grid, kGnThreads, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(2);
     return 0;
 }
 
@@ -392,6 +393,7 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
             gn_bwd_apply_kernel<TX, TG, TG><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb)));
     }
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(2);
     return 0;
 }
 
@@ -403,6 +405,7 @@ extern "C" int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
         ln_fwd_kernel<TX, TY><<<grid, 128, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, mean_out, rstd_out, M, C, eps)));
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }
 
@@ -421,5 +424,6 @@ extern "C" int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int
             ln_bwd_kernel<TX, TG, TG><<<grid, 128, 0, st>>>((const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, M, C, accumulate)));
     }
     CB_CUDA(cudaGetLastError());
+    cb::count_launches(1);
     return 0;
 }

@@ -64,19 +64,20 @@ class IResNetEngine:
     @torch.no_grad()
     def forward(self, x, geo):
         """x: [F*112*112][8] channels-last (RGB + zero pad), geo=(F,112,112) -> features [F][512] fp32."""
-        h, _ = ops.conv2d(x, geo, self.stem_w, 64, bias=self.stem_b, out_dtype=self.dt)
+        # the residual stream is fp32 (100 blocks deep); tensor-core operands are fp16
+        h, _ = ops.conv2d(x, geo, self.stem_w, 64, bias=self.stem_b, out_dtype=torch.float32)
         ops.channel_affine_act(h, slope=self.stem_slope, out=h)
         for b in self.blocks:
-            t = ops.channel_affine_act(h, scale=b["s1"], shift=b["sh1"])
+            t = ops.channel_affine_act(h, scale=b["s1"], shift=b["sh1"], out_dtype=self.dt)
             u, _ = ops.conv2d(t, geo, b["w1"], b["cout"], bias=b["b1"], out_dtype=self.dt)
             ops.channel_affine_act(u, slope=b["slope"], out=u)
             if "wd" in b:
-                idn, ogeo = ops.conv2d(h, geo, b["wd"], b["cout"], bias=b["bd"], ksize=1, stride=2, pad=(0, 0, 0, 0),
-                                       out_dtype=self.dt)
+                idn, ogeo = ops.conv2d(ops.cast(h, self.dt), geo, b["wd"], b["cout"], bias=b["bd"], ksize=1, stride=2,
+                                       pad=(0, 0, 0, 0), out_dtype=torch.float32)
             else:
                 idn, ogeo = h, geo
-            h, geo = ops.conv2d(u, geo, b["w2"], b["cout"], bias=b["b2"], stride=b["stride"], out_dtype=self.dt,
-                                residual=idn)
+            h, geo = ops.conv2d(u, geo, b["w2"], b["cout"], bias=b["b2"], stride=b["stride"],
+                                out_dtype=torch.float32, residual=idn)
             assert (geo.h, geo.w) == (ogeo.h, ogeo.w)
-        flat = h.view(geo.n, geo.hw * h.shape[1])
+        flat = ops.cast(h, self.dt).view(geo.n, geo.hw * h.shape[1])
         return ops.linear(flat, self.fc_w, self.fc_b, out_dtype=torch.float32)

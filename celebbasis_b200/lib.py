@@ -59,6 +59,7 @@ def load():
     lib.cb_last_error.restype = ctypes.c_char_p
     lib.cb_abi_version.restype = ctypes.c_int
     lib.cb_device_ok.restype = ctypes.c_int
+    lib.cb_launch_count.restype = ctypes.c_ulonglong
     lib.cb_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
     lib.cb_gemm.restype = ctypes.c_int
     _declare_rest(lib)
@@ -80,3 +81,7 @@ def check(rc, what=""):
 
 def last_error():
     return load().cb_last_error().decode(errors="replace")
+
+
+def launch_count():
+    return int(load().cb_launch_count())

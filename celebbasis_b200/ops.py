@@ -350,10 +350,12 @@ def nhwc_to_nchw(x, geo, c):
 
 
 def mse_fwd_bwd(pred, target, gscale=1.0, want_grad=True):
+    """Returns (loss_simple [B], grad of mean_b(loss_simple) w.r.t. pred (scaled by gscale) or None)."""
     assert pred.dtype == torch.float32 and target.dtype == torch.float32
-    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    B = pred.shape[0]
+    loss = torch.empty(B, dtype=torch.float32, device=pred.device)
     grad = torch.empty_like(pred) if want_grad else None
-    _lib.check(_L().cb_mse_fwd_bwd(_p(pred), _p(target), _p(loss), _p(grad), pred.numel(), gscale, _st()),
+    _lib.check(_L().cb_mse_fwd_bwd(_p(pred), _p(target), _p(loss), _p(grad), B, pred.numel() // B, gscale, _st()),
                "cb_mse_fwd_bwd")
     return loss, grad
 
@@ -369,11 +371,11 @@ def timestep_embedding(t, dim, dtype=torch.float16, max_period=10000.0):
 # ------------------------------------------------------------------------------------------------
 # CosFace front end / celeb-basis embedding path / optimiser (fp32 side kernels)
 # ------------------------------------------------------------------------------------------------
-def channel_affine_act(x, scale=None, shift=None, slope=None, out=None):
+def channel_affine_act(x, scale=None, shift=None, slope=None, out=None, out_dtype=None):
     rows, C = x.shape
-    y = out if out is not None else torch.empty_like(x)
-    _lib.check(_L().cb_channel_affine_act(_p(x), _p(y), _dt(x), _p(scale), _p(shift), _p(slope), rows, C, _st()),
-               "cb_channel_affine_act")
+    y = out if out is not None else torch.empty(rows, C, dtype=out_dtype or x.dtype, device=x.device)
+    _lib.check(_L().cb_channel_affine_act(_p(x), _dt(x), _p(y), _dt(y), _p(scale), _p(shift), _p(slope), rows, C,
+                                          _st()), "cb_channel_affine_act")
     return y
 
 
@@ -471,3 +473,11 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     _lib.check(_L().cb_q_sample(_p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), B, x0.numel() // B,
                                 _st()), "cb_q_sample")
     return out
+
+
+def ddim_step(x, e_uncond, e_cond, noise, *, scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, want_x0=True):
+    x_prev = torch.empty_like(x)
+    pred_x0 = torch.empty_like(x) if want_x0 else None
+    _lib.check(_L().cb_ddim_step(_p(x), _p(e_uncond), _p(e_cond), _p(noise), _p(x_prev), _p(pred_x0), x.numel(),
+                                 scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, _st()), "cb_ddim_step")
+    return x_prev, pred_x0

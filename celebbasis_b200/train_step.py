@@ -52,23 +52,32 @@ def placeholder_row_map(n_rows, r_pos, reps):
     return src, out
 
 
-def build_inject_map(ids, placeholder_token, reps, z_row_of_sample):
-    """ids: (B,T) host int64.  map[b][i] >= 0: take token row map of prompt b; < 0: take z row -(map+1).
-    (EmbeddingManagerId.forward, num_ids == 1 branch, embedding_manager.py:347-360.)"""
+def build_inject_map_multi(ids, per_sample, reps):
+    """ids: (B,T) host int64.  per_sample[b] = (placeholder_tokens, z_row_bases): the k-th placeholder of prompt b is
+    replaced by z rows z_row_bases[k] .. +reps-1.  map[b][i] >= 0: take token row map[b][i] of prompt b; < 0: take
+    z row -(map+1).  (EmbeddingManagerId.forward, embedding_manager.py:322-392: one/two/three persons.)"""
     ids = np.asarray(ids)
     B, T = ids.shape
     m = np.zeros((B, T), dtype=np.int32)
     positions = []
     for b in range(B):
-        pos = get_rep_pos(ids[b], [placeholder_token])
+        toks, bases = per_sample[b]
+        pos = get_rep_pos(ids[b], toks)
         src, fin = placeholder_row_map(T, pos, reps)
         row = src.astype(np.int32)
-        for one_pos in fin[0]:
-            for j, p in enumerate(one_pos):
-                row[int(p)] = -(z_row_of_sample(b) * reps + j + 1)
+        for k, base in enumerate(bases):
+            for one_pos in fin[k]:
+                for j, p in enumerate(one_pos):
+                    row[int(p)] = -(int(base) + j + 1)
         m[b] = row
         positions.append(fin)
     return m, positions
+
+
+def build_inject_map(ids, placeholder_token, reps, z_row_of_sample):
+    """Single-person prompts (num_ids == 1 branch, embedding_manager.py:347-360)."""
+    B = np.asarray(ids).shape[0]
+    return build_inject_map_multi(ids, [([placeholder_token], [z_row_of_sample(b) * reps]) for b in range(B)], reps)
 
 
 class CelebBasisStep:
@@ -165,7 +174,8 @@ class CelebBasisStep:
         noise = draws["noise"].contiguous()
         x_noisy = self.q_sample(z, t, noise)
         eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
-        loss, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)
+        loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)   # (B,) per-sample losses
+        loss = loss_simple if B == 1 else loss_simple.mean(0, keepdim=True)
         self.last = dict(z=z, context=context.view(B, T, -1), eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
                          face_feat=v, positions=positions, ids=ids)
         if ema_update:

@@ -123,3 +123,98 @@ class VAEEncoderEngine:
         ops.conv2d(a, geo, self.conv_out_w, self.zc2, bias=self.conv_out_b, out=m, cout_rows=self.out_rows)
         q = ops.linear(m, self.quant_w, self.quant_b, out_dtype=torch.float32)
         return ops.nhwc_to_nchw(q, geo, self.q_out)
+
+
+class VAEDecoderEngine:
+    """AutoencoderKL.decode: post_quant_conv + Decoder (ldm/models/autoencoder.py:330-333, model.py:462-568), no grad.
+
+    The decoder's 512x512x128 activations are the largest tensors of the txt2img path, so its residual stream is
+    fp16 (the reference runs it under fp16 autocast as well, scripts/stable_txt2img.py:320-322)."""
+
+    def __init__(self, ddconfig, embed_dim, state_dict, device, *, prefix="", dtype=torch.float16, res_dtype=None):
+        self.dev = torch.device(device)
+        self.dt = dtype
+        self.rt = res_dtype or dtype
+        sd, p = state_dict, prefix
+        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
+        w16 = lambda t: t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+        ch, mult, nres = ddconfig["ch"], ddconfig["ch_mult"], ddconfig["num_res_blocks"]
+        zc = ddconfig["z_channels"]
+        self.zc, self.zpad = zc, _round_up(zc, 8)
+        self.out_ch = ddconfig["out_ch"]
+        pq = torch.zeros(self.zpad, self.zpad, dtype=torch.float32)
+        pq[:zc, :embed_dim] = sd[p + "post_quant_conv.weight"].reshape(zc, embed_dim)
+        self.pq_w = w16(pq)
+        pqb = torch.zeros(self.zpad, dtype=torch.float32)
+        pqb[:zc] = sd[p + "post_quant_conv.bias"]
+        self.pq_b = f32(pqb)
+        self.embed_dim = embed_dim
+
+        def res(pre, cin, cout):
+            w = {"cin": cin, "cout": cout,
+                 "g1": f32(sd[pre + "norm1.weight"]), "b1": f32(sd[pre + "norm1.bias"]),
+                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"].to(self.dev), self.dt), "c1b": f32(sd[pre + "conv1.bias"]),
+                 "g2": f32(sd[pre + "norm2.weight"]), "b2": f32(sd[pre + "norm2.bias"]),
+                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"].to(self.dev), self.dt), "c2b": f32(sd[pre + "conv2.bias"])}
+            if cin != cout:
+                w["ws"] = w16(sd[pre + "nin_shortcut.weight"].reshape(cout, cin))
+                w["bs"] = f32(sd[pre + "nin_shortcut.bias"])
+            else:
+                w["ws"] = None
+            return w
+
+        bin_ = ch * mult[-1]
+        self.c_in = bin_
+        self.conv_in_w = ops.pack_conv_weight(sd[p + "decoder.conv_in.weight"].to(self.dev), self.dt, cin_pad=self.zpad)
+        self.conv_in_b = f32(sd[p + "decoder.conv_in.bias"])
+        self.mid1 = res(p + "decoder.mid.block_1.", bin_, bin_)
+        self.mid2 = res(p + "decoder.mid.block_2.", bin_, bin_)
+        ak = p + "decoder.mid.attn_1."
+        c = bin_
+        self.attn = {"c": c, "gn": f32(sd[ak + "norm.weight"]), "bn": f32(sd[ak + "norm.bias"]),
+                     "wqkv": w16(torch.cat([sd[ak + "q.weight"].reshape(c, c), sd[ak + "k.weight"].reshape(c, c),
+                                            sd[ak + "v.weight"].reshape(c, c)], 0)),
+                     "bqkv": f32(torch.cat([sd[ak + "q.bias"], sd[ak + "k.bias"], sd[ak + "v.bias"]], 0)),
+                     "wo": w16(sd[ak + "proj_out.weight"].reshape(c, c)), "bo": f32(sd[ak + "proj_out.bias"])}
+        self.levels = []   # executed order: highest level index first
+        for i in reversed(range(len(mult))):
+            bout = ch * mult[i]
+            blocks = []
+            for j in range(nres + 1):
+                blocks.append(res(p + f"decoder.up.{i}.block.{j}.", bin_, bout))
+                bin_ = bout
+            up = None
+            if i != 0:
+                uk = p + f"decoder.up.{i}.upsample.conv."
+                up = {"w": ops.pack_conv_weight(sd[uk + "weight"].to(self.dev), self.dt), "b": f32(sd[uk + "bias"]), "c": bin_}
+            self.levels.append((blocks, up))
+        self.no_g, self.no_b = f32(sd[p + "decoder.norm_out.weight"]), f32(sd[p + "decoder.norm_out.bias"])
+        self.out_rows = 16
+        self.conv_out_w = ops.pack_conv_weight(sd[p + "decoder.conv_out.weight"].to(self.dev), self.dt, cout_pad=self.out_rows)
+        cb = torch.zeros(self.out_rows, dtype=torch.float32, device=self.dev)
+        cb[: self.out_ch] = f32(sd[p + "decoder.conv_out.bias"])
+        self.conv_out_b = cb
+
+    _res = VAEEncoderEngine._res
+    _attn = VAEEncoderEngine._attn
+
+    @torch.no_grad()
+    def decode(self, z):
+        """z: (B, z_channels, h, w) fp32 NCHW -> image (B, out_ch, 8h, 8w) fp32 NCHW."""
+        z16, geo = ops.nchw_to_nhwc(z.contiguous().float(), self.zpad, self.dt)
+        h0 = ops.linear(z16, self.pq_w, self.pq_b)                                       # post_quant_conv (1x1)
+        h, _ = ops.conv2d(h0, geo, self.conv_in_w, self.c_in, bias=self.conv_in_b, out_dtype=self.rt)
+        h = self._res(self.mid1, h, geo)
+        h = self._attn(h, geo)
+        h = self._res(self.mid2, h, geo)
+        for blocks, up in self.levels:
+            for w in blocks:
+                h = self._res(w, h, geo)
+            if up is not None:
+                h16 = h if h.dtype == self.dt else ops.cast(h, self.dt)
+                u, geo = ops.upsample2x(h16, geo)
+                h, _ = ops.conv2d(u, geo, up["w"], up["c"], bias=up["b"], out_dtype=self.rt)
+        a, _ = ops.groupnorm(h, geo, self.no_g, self.no_b, eps=1e-6, silu=True, out_dtype=self.dt)
+        y, _ = ops.conv2d(a, geo, self.conv_out_w, self.out_ch, bias=self.conv_out_b, out_dtype=torch.float32,
+                          cout_rows=self.out_rows)
+        return ops.nhwc_to_nchw(y, geo, self.out_ch)

@@ -48,6 +48,8 @@ int cb_abi_version(void);
 const char* cb_last_error(void);
 /* 1 if the current device is compute capability 10.x, else 0 (never throws). */
 int cb_device_ok(void);
+/* number of kernels this library has launched (or captured into a CUDA graph) in this process. */
+unsigned long long cb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * cb_gemm — tcgen05 tensor-core GEMM / implicit-GEMM convolution with TMA-staged operands.
@@ -158,7 +160,8 @@ int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
  *   modules.py:24-31: row r may attend columns <= r % causal_period).
  * cb_upsample2x_*: openaimodel.py:112-117 nearest x2.   cb_zero_insert2x: input of the stride-2 conv dgrad.
  * cb_nchw_to_nhwc / cb_nhwc_to_nchw: ddpm.py:344-350 layout glue (+ channel padding to a multiple of 8).
- * cb_mse_fwd_bwd: ddpm.py:294-307 + :1084-1096 (l2 loss, mean over all elements) and dL/dpred * gscale.
+ * cb_mse_fwd_bwd: ddpm.py:294-307 + :1084-1096: loss_simple[b] = mean over (C,H,W) of the squared error, and
+ *   d(mean_b loss_simple[b])/dpred * gscale.
  * cb_timestep_embedding: diffusionmodules/util.py:151-171.
  * ------------------------------------------------------------------------------------------- */
 int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, const void* y, int y_dtype, long long ldy, float b,
@@ -179,8 +182,8 @@ int cb_upsample2x_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int 
 int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H, int W, int C, void* stream);
 int cb_nchw_to_nhwc(const float* x, void* y, int y_dtype, int N, int C, int HW, int Cpad, void* stream);
 int cb_nhwc_to_nchw(const void* x, int x_dtype, float* y, int N, int C, int HW, int Cpad, void* stream);
-int cb_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* grad, long long n, float gscale,
-                   void* stream);
+int cb_mse_fwd_bwd(const float* pred, const float* target, float* loss /* [B] */, float* grad, int B, int per_sample,
+                   float gscale, void* stream);
 int cb_timestep_embedding(const long long* t, void* out, int o_dtype, int B, int dim, float max_period,
                           void* stream);
 
@@ -217,6 +220,12 @@ int cb_adamw_step(float* p, const float* g, float* m, float* v, long long n, flo
                   float eps, float weight_decay, int step, int* step_dev, void* stream);
 int cb_posterior_sample(const float* moments, const float* eps, float* z, int N, int Cz, int HW, float scale,
                         void* stream);
+/* cb_ddim_step: one DDIM update with classifier-free guidance, ldm/models/diffusion/ddim.py:166-204:
+ *   e = e_u + s*(e_c - e_u) (e_c may be NULL); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
+ *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise (noise may be NULL). */
+int cb_ddim_step(const float* x, const float* e_uncond, const float* e_cond, const float* noise, float* x_prev,
+                 float* pred_x0, long long n, float guidance_scale, float a_t, float a_prev, float sigma_t,
+                 float sqrt_one_minus_at, void* stream);
 /* cb_q_sample: DDPM.q_sample (ddpm.py:289-292) with the timestep read on the device: out = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise */
 int cb_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_ac, const float* sqrt_1mac,
                 float* out, int B, int per_sample, void* stream);
@@ -230,7 +239,7 @@ int cb_q_sample(const float* x0, const float* noise, const long long* t, const f
  * cb_channel_affine_act: eval BatchNorm2d as y = x*scale[c]+shift[c] and/or PReLU slope[c] (either may be NULL).
  * cb_l2norm_rows: F.normalize(v, dim=-1).
  * ------------------------------------------------------------------------------------------- */
-int cb_channel_affine_act(const void* x, void* y, int dtype, const float* scale, const float* shift,
+int cb_channel_affine_act(const void* x, int x_dtype, void* y, int y_dtype, const float* scale, const float* shift,
                           const float* slope, long long rows, int C, void* stream);
 int cb_face_warp_resize(const float* faces, void* out, int o_dtype, int B, int H, int W, int n_chunks, int out_hw,
                         int Cpad, const float* host_affine6, void* stream);

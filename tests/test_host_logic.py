@@ -1,0 +1,129 @@
+"""CPU: host-side integer logic, tokenizer, workload, mirror construction, and the world_size-2 data-parallel path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_placeholder_row_map_matches_reference_kats(golden_dir):
+    """Product-side mirror of helpers.py (celebbasis_b200.train_step) against fixtures from the reference itself."""
+    from celebbasis_b200.train_step import get_rep_pos, placeholder_row_map
+    cases = torch.load(os.path.join(golden_dir, "helpers_kat.pt"))
+    for i, c in enumerate(cases):
+        tok = c["tokens"].numpy()
+        pos = get_rep_pos(tok, c["rep_tokens"])
+        assert [p.tolist() for p in pos] == c["rep_pos"]
+        src, fin = placeholder_row_map(tok.shape[0], pos, c["reps"])
+        assert [f.tolist() for f in fin] == c["final_pos"]
+        got = tok[src] if i == 0 else src
+        assert got.tolist() == c["result"].tolist()
+
+
+def test_edge_cases_row_map():
+    from celebbasis_b200.train_step import build_inject_map, get_rep_pos, placeholder_row_map
+    # no placeholder: identity map, no z rows
+    src, fin = placeholder_row_map(77, [np.zeros(0, dtype=np.int64)], 2)
+    assert src.tolist() == list(range(77)) and fin[0].shape == (0, 2)
+    # reps == 1: rows stay, placeholder row replaced in place
+    ids = np.full((1, 77), 49407)
+    ids[0, :4] = [49406, 5, 48136, 6]
+    m, pos = build_inject_map(ids, 48136, 1, lambda b: b)
+    assert m[0, 2] == -1 and (m[0, :2] == [0, 1]).all() and m[0, 3] == 3
+    # placeholder in the last usable slot with reps == 2: the tail token is dropped
+    ids = np.full((1, 77), 49407)
+    ids[0, 0], ids[0, 75] = 49406, 48136
+    m, pos = build_inject_map(ids, 48136, 2, lambda b: b)
+    assert m[0, 75] == -1 and m[0, 76] == -2 and pos[0][0].tolist() == [[75, 76]]
+    # two occurrences
+    ids = np.full((1, 77), 49407)
+    ids[0, :6] = [49406, 48136, 7, 48136, 8, 9]
+    m, pos = build_inject_map(ids, 48136, 2, lambda b: b)
+    assert m[0, :8].tolist() == [0, -1, -2, 2, -1, -2, 4, 5] and pos[0][0].tolist() == [[1, 2], [4, 5]]
+
+
+def test_tokenizer_contract():
+    from celebbasis_b200.tokenizer import SyntheticCLIPTokenizer
+    tok = SyntheticCLIPTokenizer()
+    ids = tok(["a photo of a face of sks person", ""])["input_ids"]
+    assert ids.shape == (2, 77) and ids.dtype == torch.int64
+    assert ids[0, :5].tolist() == [49406, 320, 1125, 539, 320] and int(ids[0, 7]) == 48136 and int(ids[0, 9]) == 49407
+    assert ids[1].tolist() == [49406] + [49407] * 76
+    assert tok("a photo of Elon Musk")["input_ids"][0, :7].tolist() == [49406, 320, 1125, 539, 20406, 19063, 49407]
+
+
+def test_mirror_constructs_with_reference_keys():
+    """The host mirror exposes the reference's import paths, constructor keywords and state-dict keys."""
+    from celebbasis_b200 import synth, workload
+    from ldm.models.diffusion.ddpm import LatentDiffusion
+    from ldm.util import instantiate_from_config
+    params = workload.model_params("tiny")
+    params["cond_stage_config"]["params"]["num_hidden_layers"] = 2
+    model = instantiate_from_config({"target": "ldm.models.diffusion.ddpm.LatentDiffusion", "params": params})
+    assert isinstance(model, LatentDiffusion)
+    keys = set(model.state_dict().keys())
+    for k in ["model.diffusion_model.input_blocks.1.1.transformer_blocks.0.attn2.to_k.weight",
+              "model.diffusion_model.output_blocks.1.1.conv.weight", "model.diffusion_model.out.2.bias",
+              "first_stage_model.encoder.down.0.downsample.conv.weight", "first_stage_model.quant_conv.weight",
+              "first_stage_model.decoder.up.1.upsample.conv.bias",
+              "cond_stage_model.transformer.text_model.encoder.layers.1.self_attn.q_proj.weight",
+              "cond_stage_model.transformer.text_model.embeddings.position_embedding.weight",
+              "embedding_manager.meta_id_net.stylegan_mlp.net.0.weight",
+              "embedding_manager.meta_id_net.id_model.layer3.29.bn3.running_var", "betas", "alphas_cumprod"]:
+        assert k in keys, k
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert "embedding_manager.meta_id_net.stylegan_mlp.net.0.weight" in trainable
+    assert not any(n.startswith(("model.", "first_stage_model.", "cond_stage_model.")) for n in trainable)
+    # full-size UNet: 686 tensors / 859.52 M parameters like the reference
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    with torch.device("meta"):
+        u = UNetModel(**workload.model_params("full")["unet_config"]["params"])
+    assert len(u.state_dict()) == 686 and sum(p.numel() for p in u.parameters()) == 859520964
+
+
+def test_schedule_buffers_match_oracle():
+    from celebbasis_b200 import workload
+    from ldm.models.diffusion.ddpm import DDPM
+    from oracle import torch_ref
+    params = workload.model_params("tiny")
+    sched = torch_ref.make_schedule(1000, params["linear_start"], params["linear_end"])
+    m = DDPM(params["unet_config"], timesteps=1000, linear_start=params["linear_start"], linear_end=params["linear_end"],
+             use_ema=False, conditioning_key="crossattn")
+    assert torch.equal(m.sqrt_alphas_cumprod, sched["sqrt_alphas_cumprod"])
+    assert torch.equal(m.sqrt_one_minus_alphas_cumprod, sched["sqrt_one_minus_alphas_cumprod"])
+
+
+def _dp_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from celebbasis_b200 import dist as cbd
+    w, r, _ = cbd.init(backend="gloo")
+    assert (w, r) == (world, rank)
+    g = torch.full((1024 * 512 + 1024,), float(rank + 1))
+    cbd.allreduce_mean_(g)
+    owned = cbd.identity_shard(10)
+    coeff = torch.zeros(10, 2, 1, 4)
+    for i in owned:
+        coeff[i] = i + 1
+    full = cbd.gather_identity_state(coeff, owned, 10)
+    torch.save({"g0": g[0].item(), "gl": g[-1].item(), "owned": owned, "full": full, "lr": cbd.scaled_lr(5e-3, 1)},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gloo_world2(tmp_path):
+    """N>1 path on CPU: one collective on the flat gradient (mean), identity sharding, EMA gather, LR scaling."""
+    import torch.multiprocessing as mp
+    port = 29000 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    assert r0["g0"] == r1["g0"] == 1.5 and r0["gl"] == 1.5
+    assert r0["owned"] == [0, 2, 4, 6, 8] and r1["owned"] == [1, 3, 5, 7, 9]
+    expect = torch.arange(1, 11).float().view(10, 1, 1, 1).expand(10, 2, 1, 4)
+    assert torch.equal(r0["full"], expect) and torch.equal(r1["full"], expect)
+    assert abs(r0["lr"] - 2 * 5e-3) < 1e-12
