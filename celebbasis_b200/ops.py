@@ -30,6 +30,17 @@ def _L():
     return _lib.load()
 
 
+GEMM_RECORD = None   # when set to a list, every cb_gemm launch appends (bytes(GemmDesc), flops) -- bench.py roofline
+
+
+def _gemm(d, what):
+    if GEMM_RECORD is not None:
+        taps = d.kh * d.kw if d.conv else 1
+        M = d.img_n * d.out_h * d.out_w if d.conv else d.M
+        GEMM_RECORD.append((bytes(d), 2.0 * M * d.N * d.K * taps * d.batch))
+    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), what)
+
+
 class Geo:
     """Image geometry of a channels-last activation matrix."""
     __slots__ = ("n", "h", "w")
@@ -84,7 +95,7 @@ def linear(x, w, bias=None, *, out_dtype=None, out=None, act=CB_ACT_NONE, residu
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha, d.act = alpha, act
-    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(linear)")
+    _gemm(d, "cb_gemm(linear)")
     return out
 
 
@@ -103,7 +114,7 @@ def linear_dgrad(dy, w, *, out_dtype=None, out=None, residual=None, alpha=1.0):
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha = alpha
-    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(linear_dgrad)")
+    _gemm(d, "cb_gemm(linear_dgrad)")
     return out
 
 
@@ -139,7 +150,7 @@ def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha, d.act = 1.0, act
-    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(conv2d)")
+    _gemm(d, "cb_gemm(conv2d)")
     return out, ogeo
 
 
@@ -168,7 +179,7 @@ def conv2d_dgrad(dy, ogeo, wpack, cin, *, ksize=3, pad=(1, 1, 1, 1), out_dtype=N
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha = 1.0
-    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(conv2d_dgrad)")
+    _gemm(d, "cb_gemm(conv2d_dgrad)")
     return out, geo
 
 
@@ -182,7 +193,7 @@ def bmm(A, B, D, *, M, N, K, heads, images=1, lda, ldb, ldd, a_hs, b_hs, d_hs, a
     d.B, d.ldb, d.b_batch_stride, d.b_batch_stride2, d.b_major = B.data_ptr(), ldb, b_hs, b_is, b_major
     d.D, d.d_dtype, d.ldd, d.d_batch_stride, d.d_batch_stride2 = D.data_ptr(), _dt(D), ldd, d_hs, d_is
     d.alpha = alpha
-    _lib.check(_L().cb_gemm(ctypes.byref(d), _st()), "cb_gemm(bmm)")
+    _gemm(d, "cb_gemm(bmm)")
     return D
 
 

@@ -150,28 +150,36 @@ class CelebBasisStep:
         return ops.q_sample(z.contiguous(), noise.contiguous(), t.contiguous(), self.sqrt_ac, self.sqrt_1mac)
 
     # ------------------------------------------------------------------------------------------
+    def prepare(self, captions):
+        """Host side of the step: tokenise, locate the placeholder, build the row map (bit-exact integer path)."""
+        ids = self.tokenize(captions)
+        map_np, positions = build_inject_map(ids.numpy(), self.placeholder_token, self.es, lambda b: b)
+        return ids, map_np, positions
+
     def forward_backward(self, batch, draws, need_grad=True, ema_update=True):
         """batch: dict as face_id.py:598-644 yields (tensors on self.dev); draws: t (B,), noise, posterior_eps.
         Returns the loss (1-element device tensor).  Gradients of (W,b) land in self.grad."""
-        image = batch["image"]
-        B = image.shape[0]
+        ids, map_np, positions = self.prepare(batch["caption"])
+        ids_dev = ids.to(self.dev)
+        map_dev = torch.from_numpy(map_np).to(self.dev)
         io = batch["image_ori"]
-        faces, ids_person = io["faces"], io["ids"]
+        return self.run(batch["image"], io["faces"], io["ids"], ids_dev, map_dev, draws["t"], draws["noise"],
+                        draws["posterior_eps"], need_grad=need_grad, ema_update=ema_update, positions=positions, ids=ids)
+
+    def run(self, image, faces, ids_person, ids_dev, map_dev, t, noise, posterior_eps, *, need_grad=True,
+            ema_update=True, positions=None, ids=None):
+        """Device side of the step: only kernel launches on the current stream (CUDA-graph capturable)."""
+        B = image.shape[0]
         n_chunks = ids_person.shape[1]
-        z, _ = self.encode_first_stage(image, draws["posterior_eps"])
+        z, _ = self.encode_first_stage(image, posterior_eps)
         v = self.face_features(faces, n_chunks)                                  # (n_chunks*B, 512)
         pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
         zc = ops.celeb_basis_fwd(coef, self.basis)                               # (F, es, 768)
-        ids = self.tokenize(batch["caption"])
-        map_np, positions = build_inject_map(ids.numpy(), self.placeholder_token, self.es, lambda b: b)
-        ids_dev = ids.to(self.dev)
-        map_dev = torch.from_numpy(map_np).to(self.dev)
-        T = ids.shape[1]
+        T = ids_dev.shape[1]
         tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
         emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
         context = self.clip.forward(emb, B, need_grad=need_grad)                 # (B*T, 768) fp32
-        t = draws["t"]
-        noise = draws["noise"].contiguous()
+        noise = noise.contiguous()
         x_noisy = self.q_sample(z, t, noise)
         eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
         loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)   # (B,) per-sample losses

@@ -654,3 +654,79 @@ class OracleModel(nn.Module):
         out.update(loss=loss, z=z, moments=moments, context=context, eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
                    face_feat=v, positions=pos, emb=emb)
         return out
+
+
+# =================================================================================================
+# VAE decoder + DDIM (inference path: scripts/stable_txt2img.py -> ddim.py:57-204, autoencoder.py:330-333)
+# =================================================================================================
+class VaeUpsample(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class VaeDecoder(nn.Module):
+    def __init__(self, *, ch, out_ch, ch_mult, num_res_blocks, z_channels, **_):
+        super().__init__()
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        bin_ = ch * ch_mult[-1]
+        self.conv_in = nn.Conv2d(z_channels, bin_, 3, padding=1)
+        self.mid = nn.Module()
+        self.mid.block_1, self.mid.attn_1, self.mid.block_2 = VaeResnetBlock(bin_, bin_), VaeAttnBlock(bin_), VaeResnetBlock(bin_, bin_)
+        self.up = nn.ModuleList()
+        for i in reversed(range(self.num_resolutions)):
+            lvl = nn.Module()
+            lvl.block, lvl.attn = nn.ModuleList(), nn.ModuleList()
+            bout = ch * ch_mult[i]
+            for _ in range(num_res_blocks + 1):
+                lvl.block.append(VaeResnetBlock(bin_, bout))
+                bin_ = bout
+            if i != 0:
+                lvl.upsample = VaeUpsample(bin_)
+            self.up.insert(0, lvl)
+        self.norm_out = _vae_norm(bin_)
+        self.conv_out = nn.Conv2d(bin_, out_ch, 3, padding=1)
+
+    def forward(self, z):
+        h = self.conv_in(z)
+        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
+        for i in reversed(range(self.num_resolutions)):
+            for j in range(self.num_res_blocks + 1):
+                h = self.up[i].block[j](h)
+            if i != 0:
+                h = self.up[i].upsample(h)
+        return self.conv_out(_swish(self.norm_out(h)))
+
+
+class AutoencoderKLDecode(nn.Module):
+    """post_quant_conv + decoder of AutoencoderKL (keys: decoder.*, post_quant_conv.*)."""
+
+    def __init__(self, ddconfig, embed_dim):
+        super().__init__()
+        self.decoder = VaeDecoder(**ddconfig)
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+
+    def forward(self, z):
+        return self.decoder(self.post_quant_conv(z))
+
+
+def ddim_sample(unet, sched, cond, uncond, x_T, steps, scale, eta=0.0):
+    """ddim.py:57-204 with eta == 0 (02_start_test.sh): uniform timesteps (+1), CFG batch doubling."""
+    T = sched["alphas_cumprod"].shape[0]
+    c = T // steps
+    ts = np.asarray(list(range(0, T, c))) + 1
+    ac = sched["alphas_cumprod"].double().numpy()
+    a, a_prev = ac[ts], np.asarray([ac[0]] + ac[ts[:-1]].tolist())
+    x = x_T
+    for i, step in enumerate(np.flip(ts)):
+        idx = len(ts) - i - 1
+        t = torch.full((x.shape[0],), int(step), device=x.device, dtype=torch.long)
+        e_u, e_c = unet(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uncond, cond])).chunk(2)
+        e = e_u + scale * (e_c - e_u)
+        at, ap = float(a[idx]), float(a_prev[idx])
+        pred_x0 = (x - math.sqrt(1 - at) * e) / math.sqrt(at)
+        x = math.sqrt(ap) * pred_x0 + math.sqrt(1 - ap) * e
+    return x

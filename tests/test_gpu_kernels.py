@@ -1,0 +1,281 @@
+"""GPU: every kernel family of libcelebbasis_b200.so against a plain PyTorch fp32 reference of the same op
+(through the C-ABI).  Tolerances: fp16 operands / fp32 accumulate => relative Frobenius error < 2e-3 for GEMM-class
+ops (the operands are rounded to fp16 in BOTH implementations so only accumulation order differs -> ~2e-4),
+< 2e-3 for norm/pointwise ops whose outputs are stored in fp16; integer/index paths are bit-exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from celebbasis_b200 import lib
+    assert lib.load().cb_device_ok() == 1, "tests must run on an sm_100 device"
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def rnd(*shape, dtype=torch.float16, scale=1.0, seed=[0]):
+    seed[0] += 1
+    g = torch.Generator().manual_seed(seed[0])
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+# ---------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (4096, 320, 320), (77, 768, 768), (300, 64, 40), (64, 4, 320),
+                                   (1, 1280, 320), (1000, 1280, 2560)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_linear(dev, M, N, K, dtype):
+    from celebbasis_b200 import ops
+    x, w, b = rnd(M, K, dtype=dtype), rnd(N, K, dtype=dtype, scale=K ** -0.5), rnd(N, dtype=torch.float32)
+    y = ops.linear(x, w, b, out_dtype=torch.float32)
+    assert rel(y, x.float() @ w.float().t() + b) < 1e-3
+    dy = rnd(M, N, dtype=dtype)
+    dx = ops.linear_dgrad(dy, w, out_dtype=torch.float32)
+    assert rel(dx, dy.float() @ w.float()) < 1e-3
+
+
+def test_linear_epilogues(dev):
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import CB_ACT_GELU, CB_ACT_QUICK_GELU, CB_ACT_SILU
+    x, w, b = rnd(512, 640), rnd(640, 640, scale=640 ** -0.5), rnd(640, dtype=torch.float32)
+    r32 = rnd(512, 640, dtype=torch.float32)
+    base = x.float() @ w.float().t() + b
+    assert rel(ops.linear(x, w, b, out_dtype=torch.float32, act=CB_ACT_SILU, residual=r32), F.silu(base) + r32) < 1e-3
+    assert rel(ops.linear(x, w, b, out_dtype=torch.float32, act=CB_ACT_GELU), F.gelu(base)) < 1e-3
+    assert rel(ops.linear(x, w, b, act=CB_ACT_QUICK_GELU), base * torch.sigmoid(1.702 * base)) < 2e-3
+    assert rel(ops.linear(x, w, None, out_dtype=torch.float32, alpha=0.25), 0.25 * (x.float() @ w.float().t())) < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,pad", [
+    (1, 64, 64, 320, 320, 1, (1, 1, 1, 1)), (1, 8, 8, 1280, 1280, 1, (1, 1, 1, 1)), (2, 8, 8, 2560, 1280, 1, (1, 1, 1, 1)),
+    (1, 64, 64, 8, 320, 1, (1, 1, 1, 1)), (1, 64, 64, 320, 16, 1, (1, 1, 1, 1)),
+    (2, 56, 56, 64, 64, 1, (1, 1, 1, 1)), (3, 7, 7, 512, 512, 1, (1, 1, 1, 1)), (2, 14, 14, 256, 256, 1, (1, 1, 1, 1)),
+    (1, 256, 256, 128, 128, 1, (1, 1, 1, 1)), (1, 64, 64, 320, 320, 2, (1, 1, 1, 1)),
+    (1, 128, 128, 128, 128, 2, (0, 1, 0, 1)), (2, 112, 112, 64, 64, 2, (1, 1, 1, 1)), (1, 1, 1, 256, 256, 1, (1, 1, 1, 1)),
+    (2, 2, 2, 256, 128, 1, (1, 1, 1, 1))])
+def test_conv3x3(dev, n, h, w, cin, cout, stride, pad):
+    """Implicit-GEMM conv incl. zero padding via TMA OOB fill, stride 2 via traversal stride, ragged pixel boxes."""
+    from celebbasis_b200 import ops
+    x = rnd(n * h * w, cin)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    b = rnd(cout, dtype=torch.float32)
+    y, og = ops.conv2d(x, ops.Geo(n, h, w), ops.pack_conv_weight(wt, torch.float16), cout, bias=b, stride=stride,
+                       pad=pad, out_dtype=torch.float32)
+    xr = F.pad(x.float().view(n, h, w, cin).permute(0, 3, 1, 2), (pad[2], pad[3], pad[0], pad[1]))
+    ref = F.conv2d(xr, wt.float(), b, stride=stride).permute(0, 2, 3, 1).reshape(-1, cout)
+    assert y.shape == ref.shape and rel(y, ref) < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 640, 640), (1, 64, 64, 320, 320), (1, 16, 16, 1920, 1280),
+                                            (2, 8, 8, 1280, 1280)])
+def test_conv_dgrad(dev, n, h, w, cin, cout):
+    from celebbasis_b200 import ops
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+    dy = rnd(n * h * w, cout)
+    dx, _ = ops.conv2d_dgrad(dy, ops.Geo(n, h, w), ops.pack_conv_weight(wt, torch.float16), cin, out_dtype=torch.float32)
+    ref = F.conv_transpose2d(dy.float().view(n, h, w, cout).permute(0, 3, 1, 2), wt.float(), padding=1)
+    assert rel(dx, ref.permute(0, 2, 3, 1).reshape(-1, cin)) < 1e-3
+
+
+def test_conv_stride2_dgrad_via_zero_insertion(dev):
+    from celebbasis_b200 import ops
+    n, h, c = 1, 32, 320
+    wt = rnd(c, c, 3, 3, scale=(9 * c) ** -0.5)
+    dy = rnd(n * (h // 2) ** 2, c)
+    z, zg = ops.zero_insert2x(dy, ops.Geo(n, h // 2, h // 2))
+    dx, _ = ops.conv2d_dgrad(z, zg, ops.pack_conv_weight(wt, torch.float16), c, out_dtype=torch.float32)
+    ref = F.conv_transpose2d(dy.float().view(n, h // 2, h // 2, c).permute(0, 3, 1, 2), wt.float(), stride=2, padding=1,
+                             output_padding=1)
+    assert rel(dx, ref.permute(0, 2, 3, 1).reshape(-1, c)) < 1e-3
+
+
+@pytest.mark.parametrize("nq,nk,dh,heads,images", [(1024, 1024, 40, 8, 1), (256, 77, 160, 8, 2), (77, 77, 64, 12, 2),
+                                                   (64, 64, 160, 8, 1)])
+def test_attention_fwd_bwd(dev, nq, nk, dh, heads, images):
+    """q.k^T softmax p.v as batched tcgen05 GEMMs (K-major and MN-major operands), forward and backward."""
+    from celebbasis_b200.unet_engine import _Attn
+    C = heads * dh
+    q, k, v = rnd(images * nq, C), rnd(images * nk, C), rnd(images * nk, C)
+    do = rnd(images * nq, C)
+    o = torch.empty_like(q)
+    P = _Attn.fwd(q, k, v, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=dh ** -0.5, out=o)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    _Attn.bwd(do, q, k, v, P, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=dh ** -0.5, dq=dq, dk=dk, dv=dv)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    sp = lambda t, n: t.view(images, n, heads, dh).permute(0, 2, 1, 3)
+    att = torch.softmax(sp(qf, nq) @ sp(kf, nk).transpose(-1, -2) * dh ** -0.5, -1)
+    ref = (att @ sp(vf, nk)).permute(0, 2, 1, 3).reshape(images * nq, C)
+    ref.backward(do.float())
+    assert rel(o, ref) < 3e-3
+    assert rel(dq, qf.grad) < 6e-3 and rel(dk, kf.grad) < 6e-3 and rel(dv, vf.grad) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("n,hw,c,silu,eps,xdt", [(1, 4096, 320, True, 1e-5, torch.float32), (2, 64, 1280, True, 1e-5, torch.float32),
+                                                 (1, 1024, 960, False, 1e-6, torch.float32), (1, 4096, 128, True, 1e-6, torch.float16),
+                                                 (1, 1, 256, True, 1e-5, torch.float32)])
+def test_groupnorm_fwd_bwd(dev, n, hw, c, silu, eps, xdt):
+    from celebbasis_b200 import ops
+    x = rnd(n * hw, c, dtype=xdt, scale=2.0) + 0.5
+    g, b = rnd(c, dtype=torch.float32) * 0.1 + 1, rnd(c, dtype=torch.float32) * 0.1
+    dy = rnd(n * hw, c)
+    geo = ops.Geo(n, 1, hw)
+    y, st = ops.groupnorm(x, geo, g, b, eps=eps, silu=silu)
+    dx = ops.groupnorm_bwd(dy, x, geo, g, b, st, silu=silu)
+    xr = x.float().view(n, hw, c).permute(0, 2, 1).requires_grad_(True)
+    yr = F.group_norm(xr, 32, g, b, eps)
+    yr = F.silu(yr) if silu else yr
+    yr.backward(dy.float().view(n, hw, c).permute(0, 2, 1))
+    assert rel(y, yr.permute(0, 2, 1).reshape(n * hw, c)) < 1e-3
+    assert rel(dx, xr.grad.permute(0, 2, 1).reshape(n * hw, c)) < 2e-3
+    acc = torch.ones_like(dx)
+    ops.groupnorm_bwd(dy, x, geo, g, b, st, silu=silu, dx=acc, accumulate=True)
+    assert rel(acc, dx + 1) < 1e-5
+
+
+@pytest.mark.parametrize("m,c", [(4096, 320), (77, 768), (64, 1280), (3, 640)])
+def test_layernorm_fwd_bwd(dev, m, c):
+    from celebbasis_b200 import ops
+    x = rnd(m, c, dtype=torch.float32, scale=3.0)
+    g, b = rnd(c, dtype=torch.float32) * 0.1 + 1, rnd(c, dtype=torch.float32) * 0.1
+    dy = rnd(m, c)
+    y, st = ops.layernorm(x, g, b)
+    dx = ops.layernorm_bwd(dy, x, g, st)
+    xr = x.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (c,), g, b, 1e-5)
+    yr.backward(dy.float())
+    assert rel(y, yr) < 1e-3 and rel(dx, xr.grad) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------- pointwise
+def test_softmax_geglu_act_upsample(dev):
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import CB_ACT_QUICK_GELU, CB_ACT_SILU
+    s = rnd(300, 80, scale=3.0)
+    p = ops.softmax_(s.clone(), 300, 77, 80)
+    ref = torch.softmax(s[:, :77].float(), -1)
+    assert rel(p[:, :77], ref) < 2e-3 and float(p[:, 77:].abs().max()) == 0
+    pc = ops.softmax_(s[:231].clone(), 231, 77, 80, causal_period=77)
+    mask = torch.full((77, 77), float("-inf"), device=s.device).triu_(1)
+    refc = torch.softmax(s[:231, :77].float().view(3, 77, 77) + mask, -1).view(231, 77)
+    assert rel(pc[:, :77], refc) < 2e-3
+    dp = rnd(300, 80)
+    ds = ops.softmax_bwd_(dp.clone(), p, 300, 77, 80)
+    pf = p[:, :77].float()
+    assert rel(ds[:, :77], pf * (dp[:, :77].float() - (dp[:, :77].float() * pf).sum(-1, keepdim=True))) < 3e-3
+    x = rnd(256, 2560)
+    xr = x.float().requires_grad_(True)
+    a, gate = xr.chunk(2, -1)
+    yr = a * F.gelu(gate)
+    dy = rnd(256, 1280)
+    yr.backward(dy.float())
+    assert rel(ops.geglu(x), yr) < 1e-3 and rel(ops.geglu_bwd(dy, x), xr.grad) < 2e-3
+    for act, fn in ((CB_ACT_SILU, F.silu), (CB_ACT_QUICK_GELU, lambda t: t * torch.sigmoid(1.702 * t))):
+        v = rnd(77, 3072)
+        vr = v.float().requires_grad_(True)
+        o = fn(vr)
+        dv = rnd(77, 3072)
+        o.backward(dv.float())
+        assert rel(ops.act_fwd(v, act), o) < 1e-3 and rel(ops.act_bwd(dv, v, act), vr.grad) < 2e-3
+    u = rnd(2 * 8 * 8, 64)
+    up, g2 = ops.upsample2x(u, ops.Geo(2, 8, 8))
+    refu = F.interpolate(u.float().view(2, 8, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert torch.equal(up.float(), refu.permute(0, 2, 3, 1).reshape(-1, 64))
+    du = rnd(2 * 16 * 16, 64)
+    dref = F.avg_pool2d(du.float().view(2, 16, 16, 64).permute(0, 3, 1, 2), 2) * 4
+    assert rel(ops.upsample2x_bwd(du, ops.Geo(2, 8, 8), dx_dtype=torch.float32), dref.permute(0, 2, 3, 1).reshape(-1, 64)) < 1e-3
+
+
+def test_layout_loss_schedule_kernels(dev):
+    from celebbasis_b200 import ops
+    from oracle import torch_ref
+    x = rnd(2, 4, 8, 8, dtype=torch.float32)
+    y, geo = ops.nchw_to_nhwc(x, 8, torch.float32)
+    assert torch.equal(y.view(2, 64, 8)[:, :, :4], x.permute(0, 2, 3, 1).reshape(2, 64, 4)) and float(y[:, 4:].abs().max()) == 0
+    assert torch.equal(ops.nhwc_to_nchw(y, geo, 4), x)
+    pred, tgt = rnd(3, 4, 16, 16, dtype=torch.float32), rnd(3, 4, 16, 16, dtype=torch.float32)
+    loss, grad = ops.mse_fwd_bwd(pred, tgt)
+    pr = pred.clone().requires_grad_(True)
+    lr = ((pr - tgt) ** 2).mean(dim=[1, 2, 3])
+    lr.mean().backward()
+    assert rel(loss, lr) < 1e-5 and rel(grad, pr.grad) < 1e-5
+    t = torch.tensor([0, 1, 500, 999], device=x.device)
+    assert rel(ops.timestep_embedding(t, 320, dtype=torch.float32), torch_ref.timestep_embedding(t, 320)) < 1e-5
+    sched = torch_ref.make_schedule()
+    z, nz = rnd(4, 4, 8, 8, dtype=torch.float32), rnd(4, 4, 8, 8, dtype=torch.float32)
+    qs = ops.q_sample(z, nz, t, sched["sqrt_alphas_cumprod"].cuda(), sched["sqrt_one_minus_alphas_cumprod"].cuda())
+    assert rel(qs, torch_ref.q_sample(sched, z, t, nz)) < 1e-6
+    mom = rnd(2, 8, 4, 4, dtype=torch.float32, scale=3.0)
+    eps = rnd(2, 4, 4, 4, dtype=torch.float32)
+    assert rel(ops.posterior_sample(mom, eps, 0.18215), torch_ref.posterior_sample(mom, eps, 0.18215)) < 1e-6
+
+
+def test_celeb_embedding_path_and_adamw(dev):
+    """fp32 side kernels: MLP + L2 norm + basis contraction + inject, forward and gradient, vs the oracle functions."""
+    from celebbasis_b200 import ops, synth
+    from celebbasis_b200.train_step import build_inject_map
+    from oracle import torch_ref
+    Fn, es, K, D = 2, 2, 512, 768
+    v = F.normalize(rnd(Fn, 512, dtype=torch.float32), dim=-1)
+    W = rnd(es * K, 512, dtype=torch.float32).requires_grad_(True)
+    b = (rnd(es * K, dtype=torch.float32) * 0.1).requires_grad_(True)
+    basis = synth.synth_celeb_basis(seed=3).cuda()
+    pre, coef, nrm = ops.celeb_mlp_fwd(v, W.detach(), b.detach(), es)
+    z = ops.celeb_basis_fwd(coef, basis)
+    coef_r = torch_ref.celeb_mlp(v, W, b, es)
+    z_r = torch_ref.celeb_basis(coef_r, basis)
+    assert rel(coef, coef_r.view(Fn, es, K)) < 1e-5 and rel(z, z_r) < 1e-5
+    ids = torch.full((1, 77), 49407, dtype=torch.long)
+    ids[0, :6] = torch.tensor([49406, 320, 48136, 539, 48136, 7])
+    tok = rnd(1 * 77, D, dtype=torch.float32)
+    pos = rnd(77, D, dtype=torch.float32)
+    m, positions = build_inject_map(ids.numpy(), 48136, es, lambda i: i)
+    mdev = torch.from_numpy(m).cuda()
+    out = ops.embed_inject_fwd(tok, z.view(-1, D), mdev.view(-1), pos, 1, 77)
+    ref_rows, ref_pos = torch_ref.inject_embeddings(ids, tok.view(1, 77, D), z_r[:1], 48136, es)
+    assert [p.tolist() for p in positions[0]] == [p.tolist() for p in ref_pos[0]]
+    assert rel(out, (ref_rows[0] + pos)) < 1e-6
+    dout = rnd(77, D, dtype=torch.float32)
+    (ref_rows[0] * dout).sum().backward()
+    dz = ops.embed_inject_bwd(dout, mdev.view(-1), Fn * es, 1, 77)
+    dcoef = ops.celeb_basis_bwd(dz.view(Fn, es, D), basis)
+    dW, db = torch.empty_like(W), torch.empty_like(b)
+    ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, dW, db)
+    assert rel(dW, W.grad) < 1e-4 and rel(db, b.grad) < 1e-4
+    # AdamW == torch.optim.AdamW for 3 steps
+    p0 = rnd(1000, dtype=torch.float32)
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pt], lr=5e-3)
+    pm, mm, vv = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for i in range(3):
+        g = rnd(1000, dtype=torch.float32)
+        pt.grad = g.clone()
+        opt.step()
+        ops.adamw_step(pm, g, mm, vv, lr=5e-3, step_dev=step_dev)
+    assert rel(pm, pt.detach()) < 1e-6 and int(step_dev.item()) == 3
+
+
+def test_face_warp_resize(dev):
+    from celebbasis_b200 import ops
+    from celebbasis_b200.train_step import TRANS_MATRIX
+    from oracle import torch_ref
+    faces = torch.rand(2, 96, 96, 6, generator=torch.Generator().manual_seed(5)).cuda() * 2 - 1
+    out, geo = ops.face_warp_resize(faces, 2, TRANS_MATRIX, out_hw=112, cpad=8, dtype=torch.float32)
+    ref = torch_ref.face_preprocess(torch.cat(faces.chunk(2, -1), 0))
+    got = out.view(4, 112, 112, 8)
+    assert rel(got[..., :3], ref.permute(0, 2, 3, 1)) < 1e-4 and float(got[..., 3:].abs().max()) == 0
