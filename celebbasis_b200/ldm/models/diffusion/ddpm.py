@@ -59,7 +59,7 @@ class _MSEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pred, target):
-        need = pred.requires_grad and torch.is_grad_enabled()
+        need = ctx.needs_input_grad[0]     # (grad mode is off inside Function.forward; this reflects the call site)
         loss, grad = ops.mse_fwd_bwd(pred.float().contiguous(), target.float().contiguous(), 1.0, want_grad=need)
         ctx.B = pred.shape[0]
         if need:

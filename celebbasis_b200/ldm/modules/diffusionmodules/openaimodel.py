@@ -60,7 +60,7 @@ class ResBlock(nn.Module):
 class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, timesteps, context, engine):
-        need = context.requires_grad and torch.is_grad_enabled()
+        need = ctx.needs_input_grad[2]
         ctx.engine = engine
         ctx.need = need
         return engine.forward(x.float().contiguous(), timesteps.long().contiguous(), context.float().contiguous(),

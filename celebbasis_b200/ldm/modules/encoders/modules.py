@@ -94,7 +94,7 @@ class _CLIPTextModel(nn.Module):
 class _CLIPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, engine, batch):
-        need = emb.requires_grad and torch.is_grad_enabled()
+        need = ctx.needs_input_grad[0]
         ctx.engine, ctx.need, ctx.shape = engine, need, emb.shape
         out = engine.forward(emb.reshape(-1, emb.shape[-1]).float().contiguous(), batch, need_grad=need)
         return out.view(emb.shape)

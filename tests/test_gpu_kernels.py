@@ -35,7 +35,7 @@ def rnd(*shape, dtype=torch.float16, scale=1.0, seed=[0]):
 
 
 # ---------------------------------------------------------------------------------------------------- GEMM
-@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (4096, 320, 320), (77, 768, 768), (300, 64, 40), (64, 4, 320),
+@pytest.mark.parametrize("M,N,K", [(128, 160, 64), (4096, 320, 320), (77, 768, 768), (300, 64, 40), (64, 16, 320),
                                    (1, 1280, 320), (1000, 1280, 2560)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_linear(dev, M, N, K, dtype):
