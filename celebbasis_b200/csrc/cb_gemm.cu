@@ -48,6 +48,11 @@ struct GemmParams {
     int act;
     unsigned idesc;
     unsigned a_bytes, b_bytes;
+    // split-K: the k-iterations of one output tile are spread over `splits` CTAs; fp32 partial tiles go to `ws`,
+    // the last CTA to arrive (per-tile counter) reduces them in split order and runs the epilogue.
+    int splits, kiters_per_split;
+    float* ws;
+    unsigned* counters;
 };
 
 template <int BN>
@@ -208,7 +213,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int m_tile = blockIdx.y;
-    const int bz = blockIdx.z;
+    const int sp = blockIdx.z % p.splits;
+    const int bz = blockIdx.z / p.splits;
     const int zi = bz % p.batch_inner;
     const int zo = bz / p.batch_inner;
 
@@ -245,14 +251,17 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int kiters = p.taps * p.kchunks;
+    const int kiters_all = p.taps * p.kchunks;
+    const int it0 = sp * p.kiters_per_split;
+    const int it1 = min(kiters_all, it0 + p.kiters_per_split);
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
+            for (int it = it0; it < it1; ++it) {
+                const int li = it - it0;
+                const int s = li % kStages;
+                const uint32_t ph = (li / kStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), p.a_bytes + p.b_bytes);
                 const int tap = it / p.kchunks;
@@ -283,9 +292,10 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
+            for (int it = it0; it < it1; ++it) {
+                const int li = it - it0;
+                const int s = li % kStages;
+                const uint32_t ph = (li / kStages) & 1;
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
                 const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
@@ -297,7 +307,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                 : umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
                     const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
                                                 : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
-                    umma_f16(tmem_base, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(tmem_base, adesc, bdesc, p.idesc, (li > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above retire
             }
@@ -327,12 +337,62 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (p.splits == 1) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t acc[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
-            tmem_ld_wait();
-            epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+                tmem_ld_wait();
+                epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
+            }
+        } else {
+            // ---- split-K: publish this CTA's fp32 partial tile, last arriver reduces + finishes ----
+            const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
+            float* wt = p.ws + (static_cast<size_t>(tile_id) * p.splits) * (BM * BN);
+            float* mine = wt + static_cast<size_t>(sp) * (BM * BN) + static_cast<size_t>(r) * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+                tmem_ld_wait();
+                if (row_valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(mine + c * 32 + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __shared__ unsigned s_last;
+            if (threadIdx.x == 64) {
+                const unsigned prev = atomicAdd(p.counters + tile_id, 1u);
+                s_last = (prev == static_cast<unsigned>(p.splits) - 1u) ? 1u : 0u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_last) {
+                __threadfence();
+                if (row_valid) {
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float sum[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+                        for (int s2 = 0; s2 < p.splits; ++s2) {
+                            const float* src = wt + static_cast<size_t>(s2) * (BM * BN) + static_cast<size_t>(r) * BN + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
+                            }
+                        }
+                        uint32_t acc[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
+                        epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
+                    }
+                }
+                if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
+            }
         }
     }
 
@@ -559,7 +619,32 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         p.vec_ok = ok ? 1 : 0;
     }
 
-    dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)d.batch);
+    // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----
+    p.splits = 1;
+    p.kiters_per_split = p.taps * p.kchunks;
+    {
+        const int kiters = p.taps * p.kchunks;
+        const long long tiles = (long long)ceil_div(d.N, BN) * m_tiles * d.batch;
+        const int sms = device_sm_count();
+        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8) {
+            int want = (int)((2LL * sms + tiles - 1) / tiles);
+            int by_k = kiters / 4;
+            int sp = want < by_k ? want : by_k;
+            if (sp > 32) sp = 32;
+            const long long counters_bytes = 65536;
+            const long long avail = d.splitk_ws_bytes - counters_bytes;
+            while (sp > 1 && tiles * sp * (long long)(BM * BN * 4) > avail) --sp;
+            if (sp > 1 && tiles <= counters_bytes / 4) {
+                const int per = ceil_div(kiters, sp);
+                sp = ceil_div(kiters, per);
+                p.splits = sp;
+                p.kiters_per_split = per;
+                p.counters = reinterpret_cast<unsigned*>(d.splitk_ws);
+                p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(d.splitk_ws) + counters_bytes);
+            }
+        }
+    }
+    dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)(d.batch * p.splits));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (!a_mn && !b_mn) {
         if (BN == 64) return launch<64, false, false>(tA, tB, p, grid, st);

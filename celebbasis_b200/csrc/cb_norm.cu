@@ -38,44 +38,59 @@ __device__ __forceinline__ float silu_grad(float z) {
     return s * (1.0f + z * (1.0f - s));
 }
 
-constexpr int kGnThreads = 256;
-constexpr int kGnMaxPairsPerThread = 8;  // C <= 2*256*8 = 4096
+constexpr int kGnThreads = 256;           // upper bound; the launch uses PW*RY threads (see gn_shape)
+constexpr int kGnMaxChunks = 8;           // channel-pair chunks per thread: C <= 2*PW*8
+
+// Thread mapping shared by the four GroupNorm kernels: a block is a (RY x PW) grid of threads; tx owns channel
+// pairs {tx + j*PW}, ty strides over the rows of the block's row range.  PW is the largest divisor of C/2 that is
+// <= 256, so every thread is busy for C = 128 (PW 64, RY 4) as well as C = 320 (PW 160, RY 1) or C = 2560 (PW 256).
+struct GnShape { int pw, ry, chunks; };
+static inline GnShape gn_shape(int C) {
+    const int npairs = C >> 1;
+    int pw = npairs < 256 ? npairs : 256;
+    while (npairs % pw) --pw;
+    GnShape s;
+    s.pw = pw;
+    s.ry = 256 / pw > 0 ? 256 / pw : 1;
+    s.chunks = npairs / pw;
+    return s;
+}
 
 // ---- GroupNorm statistics: ws[(n*G+g)*2 + {0,1}] += {sum, sumsq} (fp64) ---------------------------
 template <typename TX>
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C, int G, int rows_per_block) {
+gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C, int G, int rows_per_block, int PW,
+                int RY, int chunks) {
     __shared__ float s_sum[64], s_sq[64];
     const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
     const int cpg = C / G;
-    const int npairs = C >> 1;
     if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
     __syncthreads();
-    float a1[kGnMaxPairsPerThread], a2[kGnMaxPairsPerThread];
+    float a1[kGnMaxChunks], a2[kGnMaxChunks];
 #pragma unroll
-    for (int i = 0; i < kGnMaxPairsPerThread; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
-    const TX* xb = x + ((size_t)n * HW) * C;
-    for (int r = r0; r < r1; ++r) {
+    for (int j = 0; j < kGnMaxChunks; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+    const TX* xb = x + ((size_t)n * HW) * C + 2 * tx;
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += RY) {
         const TX* xr = xb + (size_t)r * C;
 #pragma unroll
-        for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
-            const int pr = threadIdx.x + i * kGnThreads;
-            if (pr < npairs) {
-                const float2 v = Vec2<TX>::ld(xr + 2 * pr);
-                a1[i] += v.x + v.y;
-                a2[i] += v.x * v.x + v.y * v.y;
+        for (int j = 0; j < kGnMaxChunks; ++j) {
+            if (j < chunks) {
+                const float2 v = Vec2<TX>::ld(xr + 2 * j * PW);
+                a1[j] += v.x + v.y;
+                a2[j] += v.x * v.x + v.y * v.y;
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
-        const int pr = threadIdx.x + i * kGnThreads;
-        if (pr < npairs) {
-            const int g = (2 * pr) / cpg;
-            atomicAdd(&s_sum[g], a1[i]);
-            atomicAdd(&s_sq[g], a2[i]);
+    for (int j = 0; j < kGnMaxChunks; ++j) {
+        if (j < chunks) {
+            const int g = (2 * (tx + j * PW)) / cpg;
+            atomicAdd(&s_sum[g], a1[j]);
+            atomicAdd(&s_sq[g], a2[j]);
         }
     }
     __syncthreads();
@@ -90,9 +105,11 @@ template <typename TX, typename TY>
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const double* __restrict__ ws, float* __restrict__ mean_out,
-                float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act, int rows_per_block) {
+                float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act, int rows_per_block, int PW,
+                int RY, int chunks) {
     __shared__ float s_mean[64], s_rstd[64];
     const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int cpg = C / G;
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
@@ -110,17 +127,15 @@ gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __res
     __syncthreads();
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
-    const int npairs = C >> 1;
     const size_t base = ((size_t)n * HW) * C;
-    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
-        const int pr = threadIdx.x + i * kGnThreads;
-        if (pr >= npairs) break;
-        const int c = 2 * pr;
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
         const int g = c / cpg;
         const float m = s_mean[g], rs = s_rstd[g];
         const float g0 = gamma[c] * rs, g1 = gamma[c + 1] * rs;
         const float b0 = beta[c] - m * g0, b1 = beta[c + 1] - m * g1;
-        for (int r = r0; r < r1; ++r) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += RY) {
             const size_t off = base + (size_t)r * C + c;
             float2 v = Vec2<TX>::ld(x + off);
             v.x = v.x * g0 + b0;
@@ -136,25 +151,25 @@ template <typename TX, typename TG>
 __global__ void __launch_bounds__(kGnThreads)
 gn_bwd_stats_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    double* __restrict__ ws, int HW, int C, int G, int act, int rows_per_block) {
+                    double* __restrict__ ws, int HW, int C, int G, int act, int rows_per_block, int PW, int RY,
+                    int chunks) {
     __shared__ float s_1[64], s_2[64];
     const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int cpg = C / G;
-    const int npairs = C >> 1;
     if (threadIdx.x < 64) { s_1[threadIdx.x] = 0.f; s_2[threadIdx.x] = 0.f; }
     __syncthreads();
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
     const size_t base = ((size_t)n * HW) * C;
-    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
-        const int pr = threadIdx.x + i * kGnThreads;
-        if (pr >= npairs) break;
-        const int c = 2 * pr;
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
         const int g = c / cpg;
         const float m = mean[n * G + g], rs = rstd[n * G + g];
         const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
         float a1 = 0.f, a2 = 0.f;
-        for (int r = r0; r < r1; ++r) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += RY) {
             const size_t off = base + (size_t)r * C + c;
             const float2 xv = Vec2<TX>::ld(x + off);
             float2 d = Vec2<TG>::ld(dy + off);
@@ -183,9 +198,10 @@ __global__ void __launch_bounds__(kGnThreads)
 gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const double* __restrict__ ws, TD* __restrict__ dx, int HW, int C, int G, int act,
-                    int accumulate, int rows_per_block) {
+                    int accumulate, int rows_per_block, int PW, int RY, int chunks) {
     __shared__ float s_1[64], s_2[64];
     const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int cpg = C / G;
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
@@ -193,19 +209,17 @@ gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
         s_2[threadIdx.x] = (float)(ws[((size_t)n * G + threadIdx.x) * 2 + 1] / cnt);
     }
     __syncthreads();
-    const int npairs = C >> 1;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
     const size_t base = ((size_t)n * HW) * C;
-    for (int i = 0; i < kGnMaxPairsPerThread; ++i) {
-        const int pr = threadIdx.x + i * kGnThreads;
-        if (pr >= npairs) break;
-        const int c = 2 * pr;
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
         const int g = c / cpg;
         const float m = mean[n * G + g], rs = rstd[n * G + g];
         const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
         const float m1 = s_1[g], m2 = s_2[g];
-        for (int r = r0; r < r1; ++r) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += RY) {
             const size_t off = base + (size_t)r * C + c;
             const float2 xv = Vec2<TX>::ld(x + off);
             float2 d = Vec2<TG>::ld(dy + off);
@@ -330,7 +344,7 @@ ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* 
 }
 
 static inline int gn_rows_per_block(int HW, int N) {
-    const int target_blocks = 2 * device_sm_count();
+    const int target_blocks = 4 * device_sm_count();
     int per_img = ceil_div(target_blocks, N);
     if (per_img < 1) per_img = 1;
     int rpb = ceil_div(HW, per_img);
@@ -351,7 +365,7 @@ using namespace cb;
 static int gn_check(int N, int HW, int C, int G) {
     CB_REQUIRE(N > 0 && HW > 0 && C > 0 && G > 0 && G <= 64 && C % G == 0, CB_ERR_ARG, "groupnorm: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
     CB_REQUIRE((C / G) % 2 == 0, CB_ERR_ARG, "groupnorm: channels per group must be even (C=%d G=%d)", C, G);
-    CB_REQUIRE(C <= 2 * kGnThreads * kGnMaxPairsPerThread, CB_ERR_ARG, "groupnorm: C=%d too large", C);
+    CB_REQUIRE(gn_shape(C).chunks <= kGnMaxChunks, CB_ERR_ARG, "groupnorm: C=%d not supported by the thread mapping", C);
     return 0;
 }
 
@@ -364,9 +378,11 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
     const int rpb = gn_rows_per_block(HW, N);
     dim3 grid(ceil_div(HW, rpb), N);
-    CB_DISPATCH_2(x_dtype, TX, gn_stats_kernel<TX><<<grid, kGnThreads, 0, st>>>((const TX*)x, ws, HW, C, G, rpb));
+    const GnShape gs = gn_shape(C);
+    const int nthr = gs.pw * gs.ry;
+    CB_DISPATCH_2(x_dtype, TX, gn_stats_kernel<TX><<<grid, nthr, 0, st>>>((const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
-        gn_apply_kernel<TX, TY><<<grid, kGnThreads, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb)));
+        gn_apply_kernel<TX, TY><<<grid, nthr, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);
     return 0;
@@ -381,16 +397,18 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
     const int rpb = gn_rows_per_block(HW, N);
     dim3 grid(ceil_div(HW, rpb), N);
+    const GnShape gs = gn_shape(C);
+    const int nthr = gs.pw * gs.ry;
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-        gn_bwd_stats_kernel<TX, TG><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb)));
+        gn_bwd_stats_kernel<TX, TG><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
     // dx dtype: f32 or the gradient dtype
     if (dx_dtype == CB_F32) {
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            gn_bwd_apply_kernel<TX, TG, float><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb)));
+            gn_bwd_apply_kernel<TX, TG, float><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     } else {
         CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            gn_bwd_apply_kernel<TX, TG, TG><<<grid, kGnThreads, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb)));
+            gn_bwd_apply_kernel<TX, TG, TG><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     }
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);

@@ -33,7 +33,22 @@ def _L():
 GEMM_RECORD = None   # when set to a list, every cb_gemm launch appends (bytes(GemmDesc), flops) -- bench.py roofline
 
 
+SPLITK_WS_BYTES = 96 << 20
+_splitk_ws = {}
+
+
+def _splitk_workspace(device):
+    """One zero-initialised split-K workspace per device; every stream-ordered cb_gemm launch may share it."""
+    ws = _splitk_ws.get(device)
+    if ws is None:
+        ws = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
+        _splitk_ws[device] = ws
+    return ws
+
+
 def _gemm(d, what):
+    ws = _splitk_workspace(torch.cuda.current_device())
+    d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), SPLITK_WS_BYTES
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M
