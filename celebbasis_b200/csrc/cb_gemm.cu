@@ -48,8 +48,8 @@ struct GemmParams {
     int act;
     unsigned idesc;
     unsigned a_bytes, b_bytes;
-    // split-K: the k-iterations of one output tile are spread over `splits` CTAs; fp32 partial tiles go to `ws`,
-    // the last CTA to arrive (per-tile counter) reduces them in split order and runs the epilogue.
+    // split-K: the k-iterations of one output tile are spread over `splits` CTAs which red.add their fp32 partials
+    // into the tile's accumulator in `ws`; the last CTA to arrive (per-tile counter) runs the epilogue.
     int splits, kiters_per_split;
     float* ws;
     unsigned* counters;
@@ -346,10 +346,11 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
             }
         } else {
-            // ---- split-K: publish this CTA's fp32 partial tile, last arriver reduces + finishes ----
+            // ---- split-K: every CTA adds its fp32 partial tile into one L2-resident accumulator tile with vector
+            //      reductions (red.global.add.v4.f32, spread over all L2 slices); the last CTA to arrive (per-tile
+            //      counter) reads the sum, runs the epilogue and re-zeroes tile + counter for the next launch.
             const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
-            float* wt = p.ws + (static_cast<size_t>(tile_id) * p.splits) * (BM * BN);
-            float* mine = wt + static_cast<size_t>(sp) * (BM * BN) + static_cast<size_t>(r) * BN;
+            float* mine = p.ws + static_cast<size_t>(tile_id) * (BM * BN) + static_cast<size_t>(r) * BN;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
@@ -358,7 +359,10 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row_valid) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(mine + c * 32 + j) = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
+                                     "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                                     "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
+                                     : "memory");
                 }
             }
             __threadfence();
@@ -374,20 +378,14 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row_valid) {
 #pragma unroll 1
                     for (int c = 0; c < BN / 32; ++c) {
-                        float sum[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sum[j] = 0.f;
-                        for (int s2 = 0; s2 < p.splits; ++s2) {
-                            const float* src = wt + static_cast<size_t>(s2) * (BM * BN) + static_cast<size_t>(r) * BN + c * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j));
-                                sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
-                            }
-                        }
                         uint32_t acc[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(mine + c * 32 + j));
+                            acc[j] = __float_as_uint(v.x); acc[j + 1] = __float_as_uint(v.y);
+                            acc[j + 2] = __float_as_uint(v.z); acc[j + 3] = __float_as_uint(v.w);
+                            __stcg(reinterpret_cast<float4*>(mine + c * 32 + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                        }
                         epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
                     }
                 }
@@ -633,8 +631,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
             if (sp > 32) sp = 32;
             const long long counters_bytes = 65536;
             const long long avail = d.splitk_ws_bytes - counters_bytes;
-            while (sp > 1 && tiles * sp * (long long)(BM * BN * 4) > avail) --sp;
-            if (sp > 1 && tiles <= counters_bytes / 4) {
+            if (sp > 1 && tiles <= counters_bytes / 4 && tiles * (long long)(BM * BN * 4) <= avail) {
                 const int per = ceil_div(kiters, sp);
                 sp = ceil_div(kiters, per);
                 p.splits = sp;

@@ -125,11 +125,11 @@ typedef struct cb_gemm_desc {
     int32_t batch_inner;
     int64_t a_batch_stride2, b_batch_stride2, d_batch_stride2, r_batch_stride2;
 
-    /* optional split-K workspace (caller-owned, >= 64 KiB + partial tiles; its first 64 KiB must be zero before the
-     * first use and is left zero by every launch).  With it, shapes whose tile grid cannot fill the SMs (bs=1
-     * low-resolution layers: M <= 256 rows against 1280-2560 channel weights) spread their k-loop over several CTAs;
-     * the last CTA of a tile reduces the fp32 partials in split order (deterministic) and runs the epilogue.
-     * NULL disables split-K.  Launches sharing a workspace must be stream-ordered. */
+    /* optional split-K workspace (caller-owned, 64 KiB of counters + one fp32 accumulator tile per output tile; it
+     * must be ALL ZERO before its first use and every launch leaves it all zero).  With it, shapes whose tile grid
+     * cannot fill the SMs (bs=1 low-resolution layers: M <= 256 rows against 1280-2560 channel weights) spread
+     * their k-loop over several CTAs that red.global.add their fp32 partial tiles into the accumulator; the last
+     * CTA of a tile runs the epilogue.  NULL disables split-K.  Launches sharing a workspace must be stream-ordered. */
     void* splitk_ws;
     int64_t splitk_ws_bytes;
 } cb_gemm_desc;
