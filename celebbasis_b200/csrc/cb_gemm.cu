@@ -19,7 +19,6 @@ namespace cb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 3;
 constexpr int kThreads = 192;
 
 struct GemmParams {
@@ -55,13 +54,13 @@ struct GemmParams {
     unsigned* counters;
 };
 
-template <int BN>
+template <int BN, int kStages>
 struct TileCfg {
     static constexpr int kTmemCols = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 128;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -195,11 +194,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, BN <= 160 ? 2 : 1)
+// kStages = 3: two CTAs per SM share the smem (large grids); kStages = 6: one CTA per SM with a deeper ring
+// (grids of <= one CTA per SM, where a single CTA must cover the whole TMA latency by itself).
+template <int BN, bool A_MN, bool B_MN, int kStages>
+__global__ void __launch_bounds__(kThreads, kStages <= 3 ? 2 : 1)
 cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, kStages>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1 KiB alignment
     const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
@@ -444,11 +445,11 @@ int make_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    using Cfg = TileCfg<BN>;
+template <int BN, bool A_MN, bool B_MN, int kStages>
+static int launch_s(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = TileCfg<BN, kStages>;
     static bool attr_done = false;
-    auto kern = cb_gemm_kernel<BN, A_MN, B_MN>;
+    auto kern = cb_gemm_kernel<BN, A_MN, B_MN, kStages>;
     if (!attr_done) {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
@@ -457,6 +458,13 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
     CB_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    if (ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
+    return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
 }
 
 static int pick_bn(const cb_gemm_desc& d) {
@@ -625,10 +633,11 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         const long long tiles = (long long)ceil_div(d.N, BN) * m_tiles * d.batch;
         const int sms = device_sm_count();
         if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8) {
-            int want = (int)((2LL * sms + tiles - 1) / tiles);
+            // at most one CTA per SM in a single wave (each then runs the 6-stage ring), >= 4 k-iterations per split
+            int want = (int)(sms / tiles);
             int by_k = kiters / 4;
             int sp = want < by_k ? want : by_k;
-            if (sp > 32) sp = 32;
+            if (sp > 64) sp = 64;
             const long long counters_bytes = 65536;
             const long long avail = d.splitk_ws_bytes - counters_bytes;
             if (sp > 1 && tiles <= counters_bytes / 4 && tiles * (long long)(BM * BN * 4) <= avail) {
