@@ -52,6 +52,7 @@ struct GemmParams {
     int splits, kiters_per_split;
     float* ws;
     unsigned* counters;
+    unsigned long long* dbg;  // optional per-CTA timeline (8 x u64 globaltimer ns per CTA), NULL in production
 };
 
 template <int BN, int kStages>
@@ -62,6 +63,12 @@ struct TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
@@ -212,6 +219,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    unsigned long long* dbg = p.dbg ? p.dbg + 8ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = gtimer();
     const int n0 = blockIdx.x * BN;
     const int m_tile = blockIdx.y;
     const int sp = blockIdx.z % p.splits;
@@ -251,6 +260,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (dbg && threadIdx.x == 0) dbg[1] = gtimer();
 
     const int kiters_all = p.taps * p.kchunks;
     const int it0 = sp * p.kiters_per_split;
@@ -298,6 +308,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = li % kStages;
                 const uint32_t ph = (li / kStages) & 1;
                 mbar_wait(full_bar(s), ph);
+                if (dbg && li == 0) dbg[2] = gtimer();
+                if (dbg && li == 3) dbg[6] = gtimer();
                 tc_fence_after();
                 const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
                 const uint32_t b_src = a_src + Cfg::kABytes;
@@ -313,6 +325,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above retire
             }
             umma_commit(tmem_full_bar);
+            if (dbg) dbg[3] = gtimer();
         }
     } else {
         // ===================== epilogue =====================
@@ -337,6 +350,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
         const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
         mbar_wait(tmem_full_bar, 0);
+        if (dbg && threadIdx.x == 64) dbg[4] = gtimer();
         tc_fence_after();
         if (p.splits == 1) {
 #pragma unroll 1
@@ -397,6 +411,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[5] = gtimer();
     if (warp == 1) {
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
@@ -611,6 +626,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.r_bs2 = d.r_batch_stride2;
     p.alpha = d.alpha;
     p.act = d.act;
+    p.dbg = reinterpret_cast<unsigned long long*>(d.debug_timeline);
     p.idesc = umma_idesc_f16(BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
     {
         const int des = d.d_dtype == CB_F32 ? 4 : 2;

@@ -38,6 +38,7 @@ class GemmDesc(ctypes.Structure):
         ("a_batch_stride2", ctypes.c_int64), ("b_batch_stride2", ctypes.c_int64),
         ("d_batch_stride2", ctypes.c_int64), ("r_batch_stride2", ctypes.c_int64),
         ("splitk_ws", ctypes.c_void_p), ("splitk_ws_bytes", ctypes.c_int64),
+        ("debug_timeline", ctypes.c_void_p),
     ]
 
 

@@ -30,6 +30,7 @@ def _L():
     return _lib.load()
 
 
+GEMM_DEBUG_TIMELINE = None   # device int64 tensor (8 per CTA) to receive per-CTA timestamps (tools/gemm_timeline.py)
 GEMM_RECORD = None   # when set to a list, every cb_gemm launch appends (bytes(GemmDesc), flops) -- bench.py roofline
 
 
@@ -49,6 +50,8 @@ def _splitk_workspace(device):
 def _gemm(d, what):
     ws = _splitk_workspace(torch.cuda.current_device())
     d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), SPLITK_WS_BYTES
+    if GEMM_DEBUG_TIMELINE is not None:
+        d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M

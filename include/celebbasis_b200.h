@@ -132,6 +132,10 @@ typedef struct cb_gemm_desc {
      * CTA of a tile runs the epilogue.  NULL disables split-K.  Launches sharing a workspace must be stream-ordered. */
     void* splitk_ws;
     int64_t splitk_ws_bytes;
+
+    /* profiling aid, NULL in production: device buffer of 8 x uint64 per CTA receiving %globaltimer stamps
+     * {start, setup done, first stage full, last MMA issued, accumulator ready, exit, 4th stage full, -}. */
+    void* debug_timeline;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

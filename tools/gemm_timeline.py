@@ -1,0 +1,40 @@
+"""Per-CTA %globaltimer timeline of one cb_gemm launch (setup / first load / main loop / epilogue)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from celebbasis_b200 import ops
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+rnd = lambda *s: torch.randn(*s, generator=g).half().to(dev)
+
+def report(name, fn, ncta_max=4096):
+    fn(); fn()
+    torch.cuda.synchronize()
+    buf = torch.zeros(ncta_max * 8, dtype=torch.int64, device=dev)
+    ops.GEMM_DEBUG_TIMELINE = buf
+    fn()
+    torch.cuda.synchronize()
+    ops.GEMM_DEBUG_TIMELINE = None
+    t = buf.view(-1, 8).cpu()
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    f = lambda c: (t[:, c].float() - float(t0)) / 1000.0
+    d = lambda a, b: ((t[:, b] - t[:, a]).float() / 1000.0)
+    print(f"{name}: ctas={t.shape[0]} start[min/max]={f(0).min():.1f}/{f(0).max():.1f}us end_max={f(5).max():.1f}us | "
+          f"setup={d(0,1).mean():.2f} first_full={d(1,2).mean():.2f} stage0->3={d(2,6).mean():.2f} mainloop_issue={d(2,3).mean():.2f} "
+          f"mma_drain={d(3,4).mean():.2f} epilogue={d(4,5).mean():.2f} (max {d(4,5).max():.2f}) total_cta={d(0,5).mean():.2f} (max {d(0,5).max():.2f})")
+
+def conv(n, h, cin, cout):
+    x = rnd(n * h * h, cin)
+    w = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, generator=g).to(dev) * 0.02, torch.float16)
+    out = torch.empty(n * h * h, cout, dtype=torch.float16, device=dev)
+    report(f"conv {n}x{h}x{h} {cin}->{cout}", lambda: ops.conv2d(x, ops.Geo(n, h, h), w, cout, out=out))
+
+def lin(M, N, K):
+    x, w = rnd(M, K), rnd(N, K)
+    out = torch.empty(M, N, dtype=torch.float16, device=dev)
+    report(f"linear {M}x{N}x{K}", lambda: ops.linear(x, w, out=out))
+
+conv(1, 64, 320, 320); conv(1, 32, 640, 640); conv(1, 8, 1280, 1280); conv(1, 128, 512, 512)
+lin(4096, 320, 320); lin(4096, 2560, 320); lin(77, 768, 768); lin(1024, 640, 640)
