@@ -11,6 +11,7 @@
 // other's MMA main loop.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cb_common.cuh"
@@ -37,6 +38,7 @@ struct GemmParams {
     int batch_inner;
     int d_transposed;
     int vec_ok;
+    int staged_ok;   // smem-staged coalesced epilogue usable (vec_ok, not transposed)
     const float* bias;
     int bias_row_div;
     long long ldbias;
@@ -52,6 +54,7 @@ struct GemmParams {
     int splits, kiters_per_split;
     float* ws;
     unsigned* counters;
+    int dbg_mode;             // tuning aid (env CB_GEMM_DBG_MODE): 1 exit after setup, 2 skip epilogue, 3 exit at once
     unsigned long long* dbg;  // optional per-CTA timeline (8 x u64 globaltimer ns per CTA), NULL in production
 };
 
@@ -219,6 +222,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (p.dbg_mode == 3) return;
     unsigned long long* dbg = p.dbg ? p.dbg + 8ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = gtimer();
     const int n0 = blockIdx.x * BN;
@@ -262,7 +266,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     if (dbg && threadIdx.x == 0) dbg[1] = gtimer();
 
-    const int kiters_all = p.taps * p.kchunks;
+    const int kiters_all = p.dbg_mode == 1 ? 0 : p.taps * p.kchunks;
     const int it0 = sp * p.kiters_per_split;
     const int it1 = min(kiters_all, it0 + p.kiters_per_split);
 
@@ -349,10 +353,72 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
         const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
         const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
-        mbar_wait(tmem_full_bar, 0);
+        if (p.dbg_mode != 1) mbar_wait(tmem_full_bar, 0);
         if (dbg && threadIdx.x == 64) dbg[4] = gtimer();
         tc_fence_after();
-        if (p.splits == 1) {
+        const int ncols_tile = min(BN, p.N - n0);
+        if (p.dbg_mode == 1 || p.dbg_mode == 2) {
+        } else if (p.splits == 1 && p.staged_ok && (ncols_tile & 7) == 0) {
+            // ---- staged epilogue: TMEM -> regs (alpha, bias, activation in fp32) -> shared memory (the pipeline
+            //      stages are free once the accumulator is complete) -> fully coalesced 16-byte global stores with
+            //      the residual read coalesced the same way.  Rows are padded by 16 B => conflict-free st.shared.v4.
+            constexpr int kRowF = BN + 4;                       // floats per staged row
+            float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+            long long* s_grow = reinterpret_cast<long long*>(stage + BM * kRowF);
+            if (lane == 0 || true) s_grow[r] = row_valid ? grow : -1;
+            float* my = stage + r * kRowF;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                if (c * 32 >= ncols_tile) break;
+                uint32_t acc[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    float f[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) f[j] = __uint_as_float(acc[g4 * 4 + j]) * p.alpha;
+                    const int col = n0 + c * 32 + g4 * 4;
+                    if (p.bias && row_valid && col < p.N) {
+                        const float4 b = *reinterpret_cast<const float4*>(p.bias + brow * p.ldbias + col);
+                        f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w;
+                    }
+                    if (p.act != CB_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) f[j] = apply_act(f[j], p.act);
+                    }
+                    *reinterpret_cast<float4*>(my + c * 32 + g4 * 4) = make_float4(f[0], f[1], f[2], f[3]);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
+            const int upr = ncols_tile >> 3;                    // 8-column units per row
+            const int total = BM * upr;
+            for (int u = et; u < total; u += 128) {
+                const int row = u / upr;
+                const int cu = (u - row * upr) * 8;
+                const long long gr = s_grow[row];
+                if (gr < 0) continue;
+                const float* src = stage + row * kRowF + cu;
+                float f[8];
+                const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+                f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
+                const int col = n0 + cu;
+                if (p.R) {
+                    float rr[8];
+                    const long long ridx = r_off + gr * p.ldr + col;
+                    if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, rr);
+                    else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, rr);
+                    else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, rr);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += rr[j];
+                }
+                const long long didx = d_off + gr * p.ldd + col;
+                if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
+                else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
+                else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
+            }
+        } else if (p.splits == 1) {
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
@@ -478,7 +544,9 @@ static int launch_s(const CUtensorMap& tA, const CUtensorMap& tB, const GemmPara
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    if (ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
+    static const int force = getenv("CB_GEMM_STAGES") ? atoi(getenv("CB_GEMM_STAGES")) : 0;   // tuning aid
+    if (force == 3) return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
+    if (force == 6 || ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
     return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
 }
 
@@ -627,6 +695,10 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.alpha = d.alpha;
     p.act = d.act;
     p.dbg = reinterpret_cast<unsigned long long*>(d.debug_timeline);
+    {
+        static const int mode = getenv("CB_GEMM_DBG_MODE") ? atoi(getenv("CB_GEMM_DBG_MODE")) : 0;
+        p.dbg_mode = mode;
+    }
     p.idesc = umma_idesc_f16(BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
     {
         const int des = d.d_dtype == CB_F32 ? 4 : 2;
@@ -639,6 +711,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         }
         if (d.bias) ok = ok && ((reinterpret_cast<uintptr_t>(d.bias) & 15u) == 0) && ((d.ldbias * 4) % 16 == 0);
         p.vec_ok = ok ? 1 : 0;
+        p.staged_ok = (ok && !d.d_transposed) ? 1 : 0;
     }
 
     // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----
