@@ -38,7 +38,6 @@ struct GemmParams {
     int batch_inner;
     int d_transposed;
     int vec_ok;
-    int staged_ok;   // smem-staged coalesced epilogue usable (vec_ok, not transposed)
     const float* bias;
     int bias_row_div;
     long long ldbias;
@@ -149,57 +148,45 @@ __device__ __forceinline__ void store_any(void* base, int dtype, long long idx, 
     else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
 }
 
-// Epilogue for one 32-column chunk held by one thread (one output row).
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], bool row_valid,
-                                               long long grow, long long brow, int col0, long long d_off, long long r_off) {
-    if (!row_valid) return;
-    const int ncols = min(32, p.N - col0);
-    if (ncols <= 0) return;
-    const bool fast = p.vec_ok && ncols == 32 && !p.d_transposed;
-    if (fast) {
+// Epilogue for 8 consecutive columns of one output row (one thread).  Kept deliberately small: the epilogue runs once
+// per CTA, so its cost is dominated by cold instruction fetch (~300 cycles per 128 B line of straight-line code).
+__device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[8], long long grow, long long brow, int col,
+                                             long long d_off, long long r_off, int ncols) {
+    if (p.bias) {
+        if (ncols == 8) {
+            float b[8];
+            load8<float>(p.bias + brow * p.ldbias + col, b);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
-            const int col = col0 + g * 8;
-            if (p.bias) {
-                float b[8];
-                load8<float>(p.bias + brow * p.ldbias + col, b);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += b[j];
-            }
-            if (p.act != CB_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
-            }
-            if (p.R) {
-                float r[8];
-                const long long ridx = r_off + grow * p.ldr + col;
-                if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
-                else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, r);
-                else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += r[j];
-            }
-            const long long didx = d_off + grow * p.ldd + col;
-            if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
-            else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
-            else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
+            for (int j = 0; j < 8; ++j) f[j] += b[j];
+        } else {
+            for (int j = 0; j < ncols; ++j) f[j] += p.bias[brow * p.ldbias + col + j];
         }
-    } else {
+    }
+    if (p.act != CB_ACT_NONE) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < ncols) {
-                const int col = col0 + j;
-                float v = __uint_as_float(acc[j]) * p.alpha;
-                if (p.bias) v += p.bias[brow * p.ldbias + col];
-                v = apply_act(v, p.act);
-                if (p.R) v += load_any(p.R, p.r_dtype, r_off + grow * p.ldr + col);
-                const long long didx = p.d_transposed ? (d_off + (long long)col * p.ldd + grow)
-                                                      : (d_off + grow * p.ldd + col);
-                store_any(p.D, p.d_dtype, didx, v);
-            }
+        for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+    }
+    if (ncols == 8 && p.vec_ok && !p.d_transposed) {
+        if (p.R) {
+            float r[8];
+            const long long ridx = r_off + grow * p.ldr + col;
+            if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
+            else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, r);
+            else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        const long long didx = d_off + grow * p.ldd + col;
+        if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
+        else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
+        else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
+    } else {
+        for (int j = 0; j < ncols; ++j) {
+            float v = f[j];
+            if (p.R) v += load_any(p.R, p.r_dtype, r_off + grow * p.ldr + col + j);
+            const long long didx = p.d_transposed ? (d_off + (long long)(col + j) * p.ldd + grow)
+                                                  : (d_off + grow * p.ldd + col + j);
+            store_any(p.D, p.d_dtype, didx, v);
         }
     }
 }
@@ -224,7 +211,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     if (p.dbg_mode == 3) return;
     unsigned long long* dbg = p.dbg ? p.dbg + 8ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
-    if (dbg && threadIdx.x == 0) dbg[0] = gtimer();
+    if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[7] = gtimer(); }
     const int n0 = blockIdx.x * BN;
     const int m_tile = blockIdx.y;
     const int sp = blockIdx.z % p.splits;
@@ -259,12 +246,13 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     }
+    __syncwarp();   // warp 0 diverged on lane 0: reconverge before the aligned block barrier
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-    if (dbg && threadIdx.x == 0) dbg[1] = gtimer();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     const int kiters_all = p.dbg_mode == 1 ? 0 : p.taps * p.kchunks;
     const int it0 = sp * p.kiters_per_split;
@@ -312,8 +300,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = li % kStages;
                 const uint32_t ph = (li / kStages) & 1;
                 mbar_wait(full_bar(s), ph);
-                if (dbg && li == 0) dbg[2] = gtimer();
-                if (dbg && li == 3) dbg[6] = gtimer();
+                if (dbg && li == 0) dbg[2] = clock64();
                 tc_fence_after();
                 const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
                 const uint32_t b_src = a_src + Cfg::kABytes;
@@ -329,7 +316,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above retire
             }
             umma_commit(tmem_full_bar);
-            if (dbg) dbg[3] = gtimer();
+            if (dbg) dbg[3] = clock64();
         }
     } else {
         // ===================== epilogue =====================
@@ -354,77 +341,23 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
         const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
         if (p.dbg_mode != 1) mbar_wait(tmem_full_bar, 0);
-        if (dbg && threadIdx.x == 64) dbg[4] = gtimer();
+        if (dbg && threadIdx.x == 64) dbg[4] = clock64();
         tc_fence_after();
         const int ncols_tile = min(BN, p.N - n0);
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (p.dbg_mode == 1 || p.dbg_mode == 2) {
-        } else if (p.splits == 1 && p.staged_ok && (ncols_tile & 7) == 0) {
-            // ---- staged epilogue: TMEM -> regs (alpha, bias, activation in fp32) -> shared memory (the pipeline
-            //      stages are free once the accumulator is complete) -> fully coalesced 16-byte global stores with
-            //      the residual read coalesced the same way.  Rows are padded by 16 B => conflict-free st.shared.v4.
-            constexpr int kRowF = BN + 4;                       // floats per staged row
-            float* stage = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
-            long long* s_grow = reinterpret_cast<long long*>(stage + BM * kRowF);
-            if (lane == 0 || true) s_grow[r] = row_valid ? grow : -1;
-            float* my = stage + r * kRowF;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (c * 32 >= ncols_tile) break;
-                uint32_t acc[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    float f[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) f[j] = __uint_as_float(acc[g4 * 4 + j]) * p.alpha;
-                    const int col = n0 + c * 32 + g4 * 4;
-                    if (p.bias && row_valid && col < p.N) {
-                        const float4 b = *reinterpret_cast<const float4*>(p.bias + brow * p.ldbias + col);
-                        f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w;
-                    }
-                    if (p.act != CB_ACT_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) f[j] = apply_act(f[j], p.act);
-                    }
-                    *reinterpret_cast<float4*>(my + c * 32 + g4 * 4) = make_float4(f[0], f[1], f[2], f[3]);
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
-            const int upr = ncols_tile >> 3;                    // 8-column units per row
-            const int total = BM * upr;
-            for (int u = et; u < total; u += 128) {
-                const int row = u / upr;
-                const int cu = (u - row * upr) * 8;
-                const long long gr = s_grow[row];
-                if (gr < 0) continue;
-                const float* src = stage + row * kRowF + cu;
-                float f[8];
-                const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
-                f[0] = a0.x; f[1] = a0.y; f[2] = a0.z; f[3] = a0.w; f[4] = a1.x; f[5] = a1.y; f[6] = a1.z; f[7] = a1.w;
-                const int col = n0 + cu;
-                if (p.R) {
-                    float rr[8];
-                    const long long ridx = r_off + gr * p.ldr + col;
-                    if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, rr);
-                    else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, rr);
-                    else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, rr);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += rr[j];
-                }
-                const long long didx = d_off + gr * p.ldd + col;
-                if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
-                else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
-                else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
-            }
         } else if (p.splits == 1) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+            for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
+                uint32_t acc[8];
+                tmem_ld_32x8(trow + c8 * 8, acc);
                 tmem_ld_wait();
-                epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
+                if (row_valid) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
+                    epilogue_group8(p, f, grow, brow, n0 + c8 * 8, d_off, r_off, min(8, ncols_tile - c8 * 8));
+                }
             }
         } else {
             // ---- split-K: every CTA adds its fp32 partial tile into one L2-resident accumulator tile with vector
@@ -433,14 +366,14 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
             float* mine = p.ws + static_cast<size_t>(tile_id) * (BM * BN) + static_cast<size_t>(r) * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+            for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
+                uint32_t acc[8];
+                tmem_ld_32x8(trow + c8 * 8, acc);
                 tmem_ld_wait();
                 if (row_valid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
+                    for (int j = 0; j < 8; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c8 * 8 + j),
                                      "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
                                      "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
                                      : "memory");
@@ -458,16 +391,15 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __threadfence();
                 if (row_valid) {
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        uint32_t acc[32];
+                    for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
+                        float f[8];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(mine + c * 32 + j));
-                            acc[j] = __float_as_uint(v.x); acc[j + 1] = __float_as_uint(v.y);
-                            acc[j + 2] = __float_as_uint(v.z); acc[j + 3] = __float_as_uint(v.w);
-                            __stcg(reinterpret_cast<float4*>(mine + c * 32 + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                        for (int j = 0; j < 8; j += 4) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(mine + c8 * 8 + j));
+                            f[j] = v.x * p.alpha; f[j + 1] = v.y * p.alpha; f[j + 2] = v.z * p.alpha; f[j + 3] = v.w * p.alpha;
+                            __stcg(reinterpret_cast<float4*>(mine + c8 * 8 + j), make_float4(0.f, 0.f, 0.f, 0.f));
                         }
-                        epilogue_chunk(p, acc, row_valid, grow, brow, n0 + c * 32, d_off, r_off);
+                        epilogue_group8(p, f, grow, brow, n0 + c8 * 8, d_off, r_off, min(8, ncols_tile - c8 * 8));
                     }
                 }
                 if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
@@ -475,9 +407,11 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
 
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
+    __syncwarp();   // warps 0/1 ran single-lane role loops: reconverge before the aligned block barrier
     tc_fence_before();
     __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[5] = gtimer();
+    if (dbg && threadIdx.x == 0) dbg[6] = clock64();
     if (warp == 1) {
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
@@ -711,7 +645,6 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         }
         if (d.bias) ok = ok && ((reinterpret_cast<uintptr_t>(d.bias) & 15u) == 0) && ((d.ldbias * 4) % 16 == 0);
         p.vec_ok = ok ? 1 : 0;
-        p.staged_ok = (ok && !d.d_transposed) ? 1 : 0;
     }
 
     // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----

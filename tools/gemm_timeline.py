@@ -18,12 +18,14 @@ def report(name, fn, ncta_max=4096):
     ops.GEMM_DEBUG_TIMELINE = None
     t = buf.view(-1, 8).cpu()
     t = t[t[:, 0] > 0]
-    t0 = t[:, 0].min()
-    f = lambda c: (t[:, c].float() - float(t0)) / 1000.0
-    d = lambda a, b: ((t[:, b] - t[:, a]).float() / 1000.0)
-    print(f"{name}: ctas={t.shape[0]} start[min/max]={f(0).min():.1f}/{f(0).max():.1f}us end_max={f(5).max():.1f}us | "
-          f"setup={d(0,1).mean():.2f} first_full={d(1,2).mean():.2f} stage0->3={d(2,6).mean():.2f} mainloop_issue={d(2,3).mean():.2f} "
-          f"mma_drain={d(3,4).mean():.2f} epilogue={d(4,5).mean():.2f} (max {d(4,5).max():.2f}) total_cta={d(0,5).mean():.2f} (max {d(0,5).max():.2f})")
+    GHZ = 1.965
+    d = lambda a, b: ((t[:, b] - t[:, a]).double() / GHZ / 1000.0)
+    g0 = t[:, 7].min()
+    print(f"{name}: ctas={t.shape[0]} cta_start_spread={(t[:, 7].max() - g0) / 1000:.2f}us | per-CTA (SM clock @1.965GHz, mean/max us): "
+          f"setup={d(0,1).mean():.2f} first_full={d(1,2).mean():.2f} mainloop_issue={d(2,3).mean():.2f}/{d(2,3).max():.2f} "
+          f"mma_drain={d(3,4).mean():.2f} epilogue={d(4,5).mean():.2f}/{d(4,5).max():.2f} tail_sync={d(5,6).mean():.2f} "
+          f"total={d(0,6).mean():.2f}/{d(0,6).max():.2f}")
+
 
 def conv(n, h, cin, cout):
     x = rnd(n * h * h, cin)
