@@ -350,13 +350,20 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
                 uint32_t acc[8];
-                tmem_ld_32x8(trow + c8 * 8, acc);
-                tmem_ld_wait();
-                if (row_valid) {
+                if (p.dbg_mode != 5) {
+                    tmem_ld_32x8(trow + c8 * 8, acc);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = 0x3f800000u + c8;
+                }
+                if (row_valid && p.dbg_mode != 4) {
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
                     epilogue_group8(p, f, grow, brow, n0 + c8 * 8, d_off, r_off, min(8, ncols_tile - c8 * 8));
+                } else if (p.dbg_mode == 4 && acc[0] == 0x12345678u) {
+                    reinterpret_cast<unsigned*>(p.D)[0] = acc[1];   // keep the loads alive
                 }
             }
         } else {
@@ -654,7 +661,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         const int kiters = p.taps * p.kchunks;
         const long long tiles = (long long)ceil_div(d.N, BN) * m_tiles * d.batch;
         const int sms = device_sm_count();
-        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8) {
+        // (L2 reductions serialise per address, so split-K only pays when the output tile is small: <= 512 rows)
+        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8 && (long long)p.M * d.batch <= 512) {
             // at most one CTA per SM in a single wave (each then runs the 6-stage ring), >= 4 k-iterations per split
             int want = (int)(sms / tiles);
             int by_k = kiters / 4;
