@@ -348,22 +348,21 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.dbg_mode == 1 || p.dbg_mode == 2) {
         } else if (p.splits == 1) {
 #pragma unroll 1
-            for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
-                uint32_t acc[8];
-                if (p.dbg_mode != 5) {
-                    tmem_ld_32x8(trow + c8 * 8, acc);
-                    tmem_ld_wait();
-                } else {
+            for (int c = 0; c * 32 < ncols_tile; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(trow + c * 32, acc);      // one TMEM round trip per 32 columns
+                tmem_ld_wait();
+                if (row_valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = 0x3f800000u + c8;
-                }
-                if (row_valid && p.dbg_mode != 4) {
-                    float f[8];
+                    for (int g = 0; g < 4; ++g) {
+                        const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                        if (nc > 0) {
+                            float f[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
-                    epilogue_group8(p, f, grow, brow, n0 + c8 * 8, d_off, r_off, min(8, ncols_tile - c8 * 8));
-                } else if (p.dbg_mode == 4 && acc[0] == 0x12345678u) {
-                    reinterpret_cast<unsigned*>(p.D)[0] = acc[1];   // keep the loads alive
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
+                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc);
+                        }
+                    }
                 }
             }
         } else {
@@ -373,14 +372,14 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
             float* mine = p.ws + static_cast<size_t>(tile_id) * (BM * BN) + static_cast<size_t>(r) * BN;
 #pragma unroll 1
-            for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
-                uint32_t acc[8];
-                tmem_ld_32x8(trow + c8 * 8, acc);
+            for (int c = 0; c * 32 < ncols_tile; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(trow + c * 32, acc);
                 tmem_ld_wait();
                 if (row_valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c8 * 8 + j),
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
                                      "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
                                      "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
                                      : "memory");
@@ -662,7 +661,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         const long long tiles = (long long)ceil_div(d.N, BN) * m_tiles * d.batch;
         const int sms = device_sm_count();
         // (L2 reductions serialise per address, so split-K only pays when the output tile is small: <= 512 rows)
-        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8 && (long long)p.M * d.batch <= 512) {
+        const bool small_out = (long long)p.M * d.batch <= 512;
+        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8 && (small_out || sms / tiles >= 4)) {
             // at most one CTA per SM in a single wave (each then runs the 6-stage ring), >= 4 k-iterations per split
             int want = (int)(sms / tiles);
             int by_k = kiters / 4;
