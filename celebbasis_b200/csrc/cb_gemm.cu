@@ -397,15 +397,21 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __threadfence();
                 if (row_valid) {
 #pragma unroll 1
-                    for (int c8 = 0; c8 * 8 < ncols_tile; ++c8) {
-                        float f[8];
+                    for (int c = 0; c * 32 < ncols_tile; ++c) {
+                        float4 v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j += 4) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(mine + c8 * 8 + j));
-                            f[j] = v.x * p.alpha; f[j + 1] = v.y * p.alpha; f[j + 2] = v.z * p.alpha; f[j + 3] = v.w * p.alpha;
-                            __stcg(reinterpret_cast<float4*>(mine + c8 * 8 + j), make_float4(0.f, 0.f, 0.f, 0.f));
+                        for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + c * 32 + j * 4));   // 8 loads in flight
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) __stcg(reinterpret_cast<float4*>(mine + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                            if (nc > 0) {
+                                float f[8] = {v[2 * g].x * p.alpha, v[2 * g].y * p.alpha, v[2 * g].z * p.alpha, v[2 * g].w * p.alpha,
+                                              v[2 * g + 1].x * p.alpha, v[2 * g + 1].y * p.alpha, v[2 * g + 1].z * p.alpha, v[2 * g + 1].w * p.alpha};
+                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc);
+                            }
                         }
-                        epilogue_group8(p, f, grow, brow, n0 + c8 * 8, d_off, r_off, min(8, ncols_tile - c8 * 8));
                     }
                 }
                 if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
