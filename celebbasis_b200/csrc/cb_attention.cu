@@ -1,0 +1,405 @@
+// cb_attention_fwd — fused scaled-dot-product attention forward for sm_100a (flash style).
+//
+// Replaces the materialised `sim = einsum(q,k)*scale; attn = sim.softmax(-1); out = einsum(attn, v)` of
+// ldm/modules/attention.py:178-191 (and the CLIP layers' masked variant, encoders/modules.py:24-31): the
+// (heads x N x N) score tensor -- 512 MiB fp32 per 4096-token block in the reference -- never reaches HBM unless
+// the caller asks for the probabilities (training keeps them for the backward pass).
+//
+// One CTA = 128 query rows of one (image, head):
+//   warp 0     : TMA producer -- Q once, then K_j / V_j blocks of 128 keys through a 2-stage mbarrier ring
+//   warp 1     : single-thread tcgen05.mma issuer: S_j = Q K_j^T into one of two TMEM score buffers,
+//                O += P_j V_j (V read MN-major straight from its [keys][d] layout) into the TMEM output tile
+//   warps 2..5 : one thread per query row: tcgen05.ld of the score row, online softmax (running max / sum in
+//                registers, exp2 with the scale folded in), rescale of the TMEM output tile when the max moves,
+//                P_j written as the next MMA's K-major SWIZZLE_128B A operand in shared memory;
+//                finally O / l -> HBM and logsumexp.
+// Head dims 40 / 64 / 80 / 128 (any multiple of 8 up to 128): the tensor maps declare the head's d columns as the
+// K extent, so TMA zero-fills the rest of each 64-column box and the MMAs run on 16-column multiples.
+#include <string.h>
+
+#include "cb_common.cuh"
+
+namespace cb {
+
+constexpr int kAttnThreads = 192;
+constexpr int kBQ = 128;    // query rows per CTA
+constexpr int kBKV = 128;   // keys per block
+
+struct AttnParams {
+    int nq, nk, heads, images;
+    int d, dpad16;          // head dim, head dim rounded up to 16
+    int dboxes;             // 64-column boxes per row of Q/K/V (1 or 2)
+    int causal;
+    int two_pass;           // pass A: row max / sum only; pass B: normalised probabilities (needed when P is stored)
+    float scale_log2e;      // scale * log2(e)
+    void* O;
+    int o_dtype;
+    long long ldo;          // elements between consecutive query rows of O
+    float* lse;             // [images][heads][nq] natural-log sum-exp (scaled scores), or NULL
+    void* P;                // optional probabilities [images*heads][nq][ldp] (same 16-bit dtype as the operands)
+    long long ldp;
+    int p_is_bf16;
+    unsigned idesc_s, idesc_o;
+};
+
+template <int DBOX>  // number of 64-column boxes of the head dim (1: d <= 64, 2: d <= 128)
+struct AttnCfg {
+    static constexpr int kQBytes = DBOX * kBQ * 128;
+    static constexpr int kKBytes = DBOX * kBKV * 128;
+    static constexpr int kVBytes = DBOX * kBKV * 128;
+    static constexpr int kPBytes = 2 * kBQ * 128;          // 128 keys = 2 chunks of 64
+    static constexpr int kStages = 2;
+    static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024 + 256;
+    static constexpr int kTmemCols = 512;                  // S0 [0,128) S1 [128,256) O [256, 256+dpad)
+};
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int DBOX>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+    using Cfg = AttnCfg<DBOX>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sQ = base;
+    const uint32_t sKV = sQ + Cfg::kQBytes;                                 // stage s: K at sKV + s*(K+V), V after K
+    const uint32_t sP = sKV + Cfg::kStages * (Cfg::kKBytes + Cfg::kVBytes);
+    const uint32_t bars = sP + Cfg::kPBytes;
+    // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, pv_done ; then the TMEM slot
+    const uint32_t bar_q = bars;
+    auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
+    auto bar_s_full = [&](int b) { return bars + 8u * (5 + b); };
+    auto bar_s_empty = [&](int b) { return bars + 8u * (7 + b); };
+    const uint32_t bar_p_full = bars + 8u * 9;
+    const uint32_t bar_pv_done = bars + 8u * 10;
+    const uint32_t tmem_slot = bars + 8u * 11;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBQ;
+    const int head = blockIdx.y, img = blockIdx.z;
+    int nblk = (p.nk + kBKV - 1) / kBKV;
+    if (p.causal) nblk = min(nblk, (min(q0 + kBQ, p.nq) + kBKV - 1) / kBKV);
+    const int nstat = p.two_pass ? nblk : 0;      // leading statistics-only virtual blocks
+    const int nv = nstat + nblk;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(bar_q, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_kv_full(s), 1);
+            mbar_init(bar_kv_empty(s), 1);
+            mbar_init(bar_s_full(s), 1);
+            mbar_init(bar_s_empty(s), 128);
+        }
+        mbar_init(bar_p_full, 128);
+        mbar_init(bar_pv_done, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+    const uint32_t tS0 = tmem, tO = tmem + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ============================ TMA producer ============================
+            mbar_arrive_expect_tx(bar_q, Cfg::kQBytes);
+#pragma unroll
+            for (int b = 0; b < DBOX; ++b) tma_load_4d(sQ + b * (kBQ * 128), &tmQ, bar_q, b * 64, q0, head, img);
+            for (int vj = 0; vj < nv; ++vj) {
+                const int s = vj & 1;
+                const uint32_t ph = (vj >> 1) & 1;
+                const bool full = vj >= nstat;
+                const int j = full ? vj - nstat : vj;
+                mbar_wait(bar_kv_empty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bar_kv_full(s), Cfg::kKBytes + (full ? Cfg::kVBytes : 0));
+                const uint32_t dK = sKV + s * (Cfg::kKBytes + Cfg::kVBytes), dV = dK + Cfg::kKBytes;
+#pragma unroll
+                for (int b = 0; b < DBOX; ++b) {
+                    tma_load_4d(dK + b * (kBKV * 128), &tmK, bar_kv_full(s), b * 64, j * kBKV, head, img);
+                    if (full) tma_load_4d(dV + b * (kBKV * 128), &tmV, bar_kv_full(s), b * 64, j * kBKV, head, img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ============================ MMA issuer ============================
+            const int ks_qk = p.dpad16 / 16;
+            auto issue_S = [&](int vj) {
+                const int s = vj & 1, b = vj & 1;
+                mbar_wait(bar_kv_full(s), (vj >> 1) & 1);
+                mbar_wait(bar_s_empty(b), ((vj >> 1) & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t aK = sKV + s * (Cfg::kKBytes + Cfg::kVBytes);
+                for (int k = 0; k < ks_qk; ++k) {
+                    const uint32_t off = (k >> 2) * (kBQ * 128) + (k & 3) * 32;   // 64-col box, then 16-col step
+                    umma_f16(tS0 + b * 128, umma_smem_desc_sw128(sQ + off, 16, 1024),
+                             umma_smem_desc_sw128(aK + off, 16, 1024), p.idesc_s, k > 0 ? 1u : 0u);
+                }
+                umma_commit(bar_s_full(b));
+                if (vj < nstat) umma_commit(bar_kv_empty(s));   // statistics pass: K stage is free once S is done
+            };
+            mbar_wait(bar_q, 0);
+            if (nv > 0) issue_S(0);
+            for (int vj = 0; vj < nv; ++vj) {
+                if (vj + 1 < nv) issue_S(vj + 1);          // next block's scores overlap this block's softmax
+                if (vj < nstat) continue;
+                const int fj = vj - nstat;
+                const int s = vj & 1;
+                mbar_wait(bar_p_full, fj & 1);
+                tc_fence_after();
+                const uint32_t aV = sKV + s * (Cfg::kKBytes + Cfg::kVBytes) + Cfg::kKBytes;
+                for (int k = 0; k < kBKV / 16; ++k) {
+                    // A = P [128 rows][128 keys] K-major: 64-key chunk (k>>2), 16-key step (k&3)
+                    const uint64_t ad = umma_smem_desc_sw128(sP + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 16, 1024);
+                    // B = V [128 keys][d] read MN-major: 16 keys = 2 groups of 8 rows (SBO 1024), 64-col chunks at LBO
+                    const uint64_t bd = umma_smem_desc_sw128(aV + k * 2048, kBKV * 128, 1024);
+                    umma_f16(tO, ad, bd, p.idesc_o, (fj > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bar_kv_empty(s));   // K_j / V_j stage reusable
+                umma_commit(bar_pv_done);       // P buffer reusable, O stable
+            }
+        }
+    } else {
+        // ============================ softmax / epilogue: one thread per query row ============================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int qrow = q0 + r;
+        const bool row_ok = qrow < p.nq;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        float m = -INFINITY, l = 0.f;
+        const int et = threadIdx.x - 64;
+        const int ocols = DBOX * 64;
+        float inv_l = 1.f;
+        for (int vj = 0; vj < nv; ++vj) {
+            const int b = vj & 1;
+            const bool full = vj >= nstat;
+            const int j = full ? vj - nstat : vj;
+            mbar_wait(bar_s_full(b), (vj >> 1) & 1);
+            tc_fence_after();
+            uint32_t sc[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS0 + b * 128 + lane_off + c * 32, sc[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_s_empty(b));                    // score buffer may be overwritten by S_{vj+2}
+            const int kbase = j * kBKV;
+            int kvalid = min(kBKV, p.nk - kbase);
+            if (p.causal) kvalid = min(kvalid, qrow - kbase + 1);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = (c * 32 + i < kvalid) ? __uint_as_float(sc[c][i]) * p.scale_log2e : -INFINITY;
+                    sc[c][i] = __float_as_uint(v);
+                    mx = fmaxf(mx, v);
+                }
+            const bool online = !(p.two_pass && full);      // running max / sum still being built
+            float m_use = m;
+            if (online) {
+                const float m_new = fmaxf(m, mx);
+                m_use = (m_new == -INFINITY) ? 0.f : m_new;
+                const float corr = exp2f(m - m_use);        // 0 on the first block (m = -inf)
+                l *= corr;
+                if (full) {
+                    // one-pass mode: the previous P.V must be complete, then the TMEM output tile is rescaled
+                    if (j > 0) mbar_wait(bar_pv_done, (j - 1) & 1);
+                    tc_fence_after();
+                    const bool need = __any_sync(0xffffffffu, j > 0 && corr != 1.f);   // tcgen05.ld/st are warp-collective
+                    if (need) {
+                        for (int c = 0; c * 32 < ocols; ++c) {
+                            uint32_t o[32];
+                            tmem_ld_32x32(tO + lane_off + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                            tmem_st_32x32(tO + lane_off + c * 32, o);
+                        }
+                        tmem_st_wait();
+                    }
+                }
+                m = m_use;
+            } else if (j > 0) {
+                mbar_wait(bar_pv_done, (j - 1) & 1);        // two-pass mode: only the P buffer hand-over
+                tc_fence_after();
+            }
+            if (!full) {                                    // statistics pass: accumulate the row sum only
+                float rs = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) rs += exp2f(__uint_as_float(sc[c][i]) - m_use);
+                l += rs;
+                if (vj == nstat - 1) inv_l = l > 0.f ? 1.f / l : 0.f;
+                continue;
+            }
+            // P = exp2(s - m) (normalised by 1/l in two-pass mode): swizzled K-major A tile in smem (+ optional HBM copy)
+            float rs = 0.f;
+            uint16_t* prow = (p.P && row_ok)
+                                 ? reinterpret_cast<uint16_t*>(p.P) +
+                                       ((static_cast<long long>(img) * p.heads + head) * p.nq + qrow) * p.ldp + kbase
+                                 : nullptr;
+            const float pscale = p.two_pass ? inv_l : 1.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        e[i] = exp2f(__uint_as_float(sc[c][g * 8 + i]) - m_use) * pscale;
+                        rs += e[i];
+                    }
+                    uint4 pk;
+                    if (p.p_is_bf16) {
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(e[2 * i], e[2 * i + 1]);
+                    } else {
+                        __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
+                    }
+                    const int key8 = c * 4 + g;                               // 8-key group 0..15
+                    const uint32_t dst = sP + (key8 >> 3) * (kBQ * 128) + r * 128 + (((key8 & 7) ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z),
+                                 "r"(pk.w)
+                                 : "memory");
+                    if (prow && kbase + key8 * 8 < p.ldp) *reinterpret_cast<uint4*>(prow + key8 * 8) = pk;
+                }
+            }
+            if (online) l += rs;
+            fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(bar_p_full);
+        }
+        // ---- epilogue: O / l, logsumexp ----
+        if (nblk > 0) mbar_wait(bar_pv_done, (nblk - 1) & 1);
+        tc_fence_after();
+        const float inv = p.two_pass ? 1.f : (l > 0.f ? 1.f / l : 0.f);
+        if (row_ok && p.lse && et >= 0)
+            p.lse[(static_cast<long long>(img) * p.heads + head) * p.nq + qrow] = (m + log2f(l)) * 0.6931471805599453f;
+        for (int c = 0; c * 32 < ocols; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + lane_off + c * 32, o);
+            tmem_ld_wait();
+            if (row_ok) {
+                const long long orow = (static_cast<long long>(img) * p.nq + qrow) * p.ldo + static_cast<long long>(head) * p.d;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int col = c * 32 + g * 8;
+                    if (col < p.d) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv;
+                        uint4 pk;
+                        if (p.o_dtype == CB_BF16) {
+                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        } else {
+                            __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + orow + col) = pk;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem);
+}
+
+int make_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr);
+
+template <int DBOX>
+static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, dim3 grid,
+                       cudaStream_t st) {
+    using Cfg = AttnCfg<DBOX>;
+    static bool done = false;
+    auto kern = cb_attention_fwd_kernel<DBOX>;
+    if (!done) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        done = true;
+    }
+    kern<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(q, k, v, p);
+    CB_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                                void* O, long long ldo, float* lse, void* P, long long ldp, int dtype, int images,
+                                int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
+    CB_REQUIRE(dtype == CB_F16 || dtype == CB_BF16, CB_ERR_ARG, "attention_fwd: dtype must be f16/bf16");
+    CB_REQUIRE(Q && K && V && O && images > 0 && heads > 0 && nq > 0 && nk > 0, CB_ERR_ARG, "attention_fwd: bad args");
+    CB_REQUIRE(d >= 8 && d <= 128 && d % 8 == 0, CB_ERR_ARG, "attention_fwd: head dim %d unsupported (8..128, multiple of 8)", d);
+    CB_REQUIRE((ldo * 2) % 16 == 0 && ((long long)d * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(O) & 15u) == 0,
+               CB_ERR_ALIGN, "attention_fwd: O alignment");
+    const int es = 2;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.nq = nq; p.nk = nk; p.heads = heads; p.images = images;
+    p.d = d; p.dpad16 = (d + 15) / 16 * 16; p.dboxes = d <= 64 ? 1 : 2;
+    p.causal = causal;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.O = O; p.o_dtype = dtype; p.ldo = ldo; p.lse = lse;
+    p.P = P; p.ldp = ldp; p.p_is_bf16 = dtype == CB_BF16;
+    p.two_pass = P != nullptr ? 1 : 0;
+    if (P) CB_REQUIRE(ldp >= nk && ldp % 8 == 0 && (reinterpret_cast<uintptr_t>(P) & 15u) == 0, CB_ERR_ALIGN, "attention_fwd: P row pitch must be a multiple of 8 elements >= nk");
+    // S = Q K^T : M=128, N=128 keys, both K-major.  O = P V : M=128, N=dpad16, A K-major, B (V) MN-major.
+    p.idesc_s = umma_idesc_f16(128, 128, dtype == CB_BF16, false, false);
+    p.idesc_o = umma_idesc_f16(128, p.dboxes * 64, dtype == CB_BF16, false, true);   // N = whole 64-col chunks (zero-filled past d)
+    CUtensorMap tq, tk, tv;
+    uint32_t estr[4] = {1, 1, 1, 1};
+    uint32_t box[4] = {64, 128, 1, 1};
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)nq, (uint64_t)heads, (uint64_t)images};
+        uint64_t str[3] = {(uint64_t)ldq * es, (uint64_t)d * es, (uint64_t)nq * ldq * es};
+        int rc = make_tmap(&tq, dtype, 4, Q, dims, str, box, estr);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d, (uint64_t)nk, (uint64_t)heads, (uint64_t)images};
+        uint64_t str[3] = {(uint64_t)ldk * es, (uint64_t)d * es, (uint64_t)nk * ldk * es};
+        int rc = make_tmap(&tk, dtype, 4, K, dims, str, box, estr);
+        if (rc) return rc;
+        uint64_t strv[3] = {(uint64_t)ldv * es, (uint64_t)d * es, (uint64_t)nk * ldv * es};
+        rc = make_tmap(&tv, dtype, 4, V, dims, strv, box, estr);
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned)ceil_div(nq, kBQ), (unsigned)heads, (unsigned)images);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p.dboxes == 1) return launch_attn<1>(tq, tk, tv, p, grid, st);
+    return launch_attn<2>(tq, tk, tv, p, grid, st);
+}

@@ -510,3 +510,19 @@ def ddim_step(x, e_uncond, e_cond, noise, *, scale, a_t, a_prev, sigma_t, sqrt_o
     _lib.check(_L().cb_ddim_step(_p(x), _p(e_uncond), _p(e_cond), _p(noise), _p(x_prev), _p(pred_x0), x.numel(),
                                  scale, a_t, a_prev, sigma_t, sqrt_one_minus_at, _st()), "cb_ddim_step")
     return x_prev, pred_x0
+
+
+def attention_fwd(q, k, v, out, *, images, heads, dh, nq, nk, scale, causal=False, want_p=False, want_lse=False):
+    """Fused flash attention forward (cb_attention_fwd).  q/k/v/out are row-strided 2-D views whose head h lives in
+    columns [h*dh, (h+1)*dh).  Returns (P or None, lse or None); P is [images*heads*nq][round_up(nk, 8)]."""
+    P = lse = None
+    ldp = 0
+    if want_p:
+        ldp = (nk + 7) // 8 * 8
+        P = torch.empty(images * heads * nq, ldp, dtype=q.dtype, device=q.device)
+    if want_lse:
+        lse = torch.empty(images * heads * nq, dtype=torch.float32, device=q.device)
+    _lib.check(_L().cb_attention_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                     _p(lse), _p(P), ldp, _dt(q), images, heads, nq, nk, dh, scale, 1 if causal else 0,
+                                     _st()), "cb_attention_fwd")
+    return P, lse

@@ -30,8 +30,15 @@ def _round_up(a, b):
 class _Attn:
     """softmax(q k^T * scale) v for (image, head) batches; probabilities are kept for backward."""
 
+    FLASH = True   # fused tcgen05 flash kernel for head dims <= 128 (set False to force the materialised path)
+
     @staticmethod
-    def fwd(q, k, v, *, images, heads, dh, nq, nk, scale, out, causal=False):
+    def fwd(q, k, v, *, images, heads, dh, nq, nk, scale, out, causal=False, need_p=True):
+        """Returns the probabilities [images*heads*nq][round_up(nk,8)] when need_p (kept for the backward pass)."""
+        if _Attn.FLASH and dh <= 128 and dh % 8 == 0:
+            P, _ = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
+                                     causal=causal, want_p=need_p)
+            return P
         ldp = _round_up(nk, 8)
         P = torch.empty(images * heads * nq, ldp, dtype=q.dtype, device=q.device)
         ops.bmm(q, k, P, M=nq, N=nk, K=dh, heads=heads, images=images, lda=q.stride(0), ldb=k.stride(0), ldd=ldp,

@@ -257,6 +257,22 @@ int cb_face_warp_resize(const float* faces, void* out, int o_dtype, int B, int H
                         int Cpad, const float* host_affine6, void* stream);
 int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * cb_attention_fwd -- fused softmax(Q K^T * scale [+ causal mask]) V on tcgen05 (flash style): the scores live in
+ * TMEM, K/V blocks of 128 keys are TMA-staged in shared memory, the softmax is one thread per query row.
+ * Replaces ldm/modules/attention.py:178-191 (CrossAttention: self and cross) and the masked CLIP attention driven
+ * from ldm/modules/encoders/modules.py:24-31,320-340.
+ *   Q [images*nq][ldq], K/V [images*nk][ldk/ldv], O [images*nq][ldo]: head h occupies columns [h*d, (h+1)*d);
+ *   16-bit operands (dtype), d a multiple of 8 up to 128; strides in elements.
+ *   lse (optional) [images][heads][nq] fp32: log-sum-exp of the scaled scores.
+ *   P (optional) [images*heads][nq][ldp] 16-bit: the normalised probabilities, written for a backward pass that
+ *   wants them (two-pass mode: pass 1 row max/sum, pass 2 probabilities + P.V); ldp multiple of 8, >= nk,
+ *   columns nk..ldp-1 are written as 0.
+ * ------------------------------------------------------------------------------------------- */
+int cb_attention_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv, void* O,
+                     long long ldo, float* lse, void* P, long long ldp, int dtype, int images, int heads, int nq,
+                     int nk, int d, float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
