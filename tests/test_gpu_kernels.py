@@ -279,3 +279,32 @@ def test_face_warp_resize(dev):
     ref = torch_ref.face_preprocess(torch.cat(faces.chunk(2, -1), 0))
     got = out.view(4, 112, 112, 8)
     assert rel(got[..., :3], ref.permute(0, 2, 3, 1)) < 1e-4 and float(got[..., 3:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("nq,nk,dh,heads,images,causal", [(4096, 4096, 40, 8, 1, False), (1024, 1024, 80, 8, 1, False),
+                                                          (1024, 77, 80, 8, 2, False), (4096, 77, 40, 8, 1, False),
+                                                          (77, 77, 64, 12, 2, True), (300, 200, 128, 2, 1, False),
+                                                          (64, 64, 40, 8, 1, False)])
+@pytest.mark.parametrize("want_p", [False, True])
+def test_flash_attention_fwd(dev, nq, nk, dh, heads, images, causal, want_p):
+    """cb_attention_fwd (scores in TMEM, online softmax, P.V in TMEM) vs softmax(QK^T*scale)V in fp32; one-pass
+    (inference) and two-pass (probabilities exported for the backward) modes."""
+    from celebbasis_b200 import ops
+    C = heads * dh
+    q, k, v = rnd(images * nq, C), rnd(images * nk, C), rnd(images * nk, C)
+    o = torch.full((images * nq, C), float("nan"), dtype=torch.float16, device="cuda")
+    P, lse = ops.attention_fwd(q, k, v, o, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=dh ** -0.5,
+                               causal=causal, want_p=want_p, want_lse=True)
+    sp = lambda t, n: t.float().view(images, n, heads, dh).permute(0, 2, 1, 3)
+    s = sp(q, nq) @ sp(k, nk).transpose(-1, -2) * dh ** -0.5
+    if causal:
+        s = s + torch.full((nq, nk), float("-inf"), device="cuda").triu_(1)
+    att = torch.softmax(s, -1)
+    ref = (att @ sp(v, nk)).permute(0, 2, 1, 3).reshape(images * nq, C)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o, ref) < 3e-3
+    assert rel(lse, torch.logsumexp(s, -1).reshape(-1)) < 1e-4
+    if want_p:
+        ldp = (nk + 7) // 8 * 8
+        pr = P.view(images, heads, nq, ldp)
+        assert rel(pr[..., :nk], att) < 3e-3 and float(pr[..., nk:].abs().max() if ldp > nk else 0) == 0
