@@ -23,7 +23,7 @@ namespace cb {
 
 constexpr int kAttnThreads = 192;
 constexpr int kBQ = 128;    // query rows per CTA
-constexpr int kBKV = 128;   // keys per block
+constexpr int kBKV = 64;    // keys per block (64 scores per softmax thread keeps 2-4 CTAs resident per SM)
 
 struct AttnParams {
     int nq, nk, heads, images;
@@ -47,10 +47,11 @@ struct AttnCfg {
     static constexpr int kQBytes = DBOX * kBQ * 128;
     static constexpr int kKBytes = DBOX * kBKV * 128;
     static constexpr int kVBytes = DBOX * kBKV * 128;
-    static constexpr int kPBytes = 2 * kBQ * 128;          // 128 keys = 2 chunks of 64
+    static constexpr int kPBytes = kBQ * 128;              // 64 keys = one 128-byte chunk per query row
     static constexpr int kStages = 2;
     static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024 + 256;
-    static constexpr int kTmemCols = 512;                  // S0 [0,128) S1 [128,256) O [256, 256+dpad)
+    static constexpr int kTmemCols = DBOX == 1 ? 128 : 256;   // S [0,64)  O [64, 64 + DBOX*64)
+    static constexpr int kMinBlocks = 2;
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -64,10 +65,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int DBOX>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, AttnCfg<DBOX>::kMinBlocks)
 cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
     using Cfg = AttnCfg<DBOX>;
@@ -81,8 +87,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t bar_q = bars;
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
     auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
-    auto bar_s_full = [&](int b) { return bars + 8u * (5 + b); };
-    auto bar_s_empty = [&](int b) { return bars + 8u * (7 + b); };
+    const uint32_t bar_s_full = bars + 8u * 5;
+    const uint32_t bar_s_empty = bars + 8u * 7;
     const uint32_t bar_p_full = bars + 8u * 9;
     const uint32_t bar_pv_done = bars + 8u * 10;
     const uint32_t tmem_slot = bars + 8u * 11;
@@ -103,9 +109,9 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_kv_full(s), 1);
             mbar_init(bar_kv_empty(s), 1);
-            mbar_init(bar_s_full(s), 1);
-            mbar_init(bar_s_empty(s), 128);
         }
+        mbar_init(bar_s_full, 1);
+        mbar_init(bar_s_empty, 128);
         mbar_init(bar_p_full, 128);
         mbar_init(bar_pv_done, 1);
         mbar_fence_init();
@@ -118,7 +124,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tc_fence_after();
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-    const uint32_t tS0 = tmem, tO = tmem + 256;
+    const uint32_t tS0 = tmem, tO = tmem + 64;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -146,17 +152,18 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             // ============================ MMA issuer ============================
             const int ks_qk = p.dpad16 / 16;
             auto issue_S = [&](int vj) {
-                const int s = vj & 1, b = vj & 1;
+                const int s = vj & 1;
                 mbar_wait(bar_kv_full(s), (vj >> 1) & 1);
-                mbar_wait(bar_s_empty(b), ((vj >> 1) & 1) ^ 1u);
+                mbar_wait(bar_s_empty, (vj & 1) ^ 1u);      // softmax has copied the previous scores to registers
                 tc_fence_after();
                 const uint32_t aK = sKV + s * (Cfg::kKBytes + Cfg::kVBytes);
                 for (int k = 0; k < ks_qk; ++k) {
-                    const uint32_t off = (k >> 2) * (kBQ * 128) + (k & 3) * 32;   // 64-col box, then 16-col step
-                    umma_f16(tS0 + b * 128, umma_smem_desc_sw128(sQ + off, 16, 1024),
-                             umma_smem_desc_sw128(aK + off, 16, 1024), p.idesc_s, k > 0 ? 1u : 0u);
+                    const uint32_t offq = (k >> 2) * (kBQ * 128) + (k & 3) * 32;    // 64-col box, then 16-col step
+                    const uint32_t offk = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                    umma_f16(tS0, umma_smem_desc_sw128(sQ + offq, 16, 1024), umma_smem_desc_sw128(aK + offk, 16, 1024),
+                             p.idesc_s, k > 0 ? 1u : 0u);
                 }
-                umma_commit(bar_s_full(b));
+                umma_commit(bar_s_full);
                 if (vj < nstat) umma_commit(bar_kv_empty(s));   // statistics pass: K stage is free once S is done
             };
             mbar_wait(bar_q, 0);
@@ -170,8 +177,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 tc_fence_after();
                 const uint32_t aV = sKV + s * (Cfg::kKBytes + Cfg::kVBytes) + Cfg::kKBytes;
                 for (int k = 0; k < kBKV / 16; ++k) {
-                    // A = P [128 rows][128 keys] K-major: 64-key chunk (k>>2), 16-key step (k&3)
-                    const uint64_t ad = umma_smem_desc_sw128(sP + (k >> 2) * (kBQ * 128) + (k & 3) * 32, 16, 1024);
+                    // A = P [128 rows][64 keys] K-major: 16-key step k
+                    const uint64_t ad = umma_smem_desc_sw128(sP + k * 32, 16, 1024);
                     // B = V [128 keys][d] read MN-major: 16 keys = 2 groups of 8 rows (SBO 1024), 64-col chunks at LBO
                     const uint64_t bd = umma_smem_desc_sw128(aV + k * 2048, kBKV * 128, 1024);
                     umma_f16(tO, ad, bd, p.idesc_o, (fj > 0 || k > 0) ? 1u : 0u);
@@ -192,23 +199,22 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int ocols = DBOX * 64;
         float inv_l = 1.f;
         for (int vj = 0; vj < nv; ++vj) {
-            const int b = vj & 1;
             const bool full = vj >= nstat;
             const int j = full ? vj - nstat : vj;
-            mbar_wait(bar_s_full(b), (vj >> 1) & 1);
+            mbar_wait(bar_s_full, vj & 1);
             tc_fence_after();
-            uint32_t sc[4][32];
+            uint32_t sc[2][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS0 + b * 128 + lane_off + c * 32, sc[c]);
+            for (int c = 0; c < 2; ++c) tmem_ld_32x32(tS0 + lane_off + c * 32, sc[c]);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(bar_s_empty(b));                    // score buffer may be overwritten by S_{vj+2}
+            mbar_arrive(bar_s_empty);                       // the score tile may be overwritten by S_{vj+1}
             const int kbase = j * kBKV;
             int kvalid = min(kBKV, p.nk - kbase);
             if (p.causal) kvalid = min(kvalid, qrow - kbase + 1);
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float v = (c * 32 + i < kvalid) ? __uint_as_float(sc[c][i]) * p.scale_log2e : -INFINITY;
@@ -220,7 +226,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (online) {
                 const float m_new = fmaxf(m, mx);
                 m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                const float corr = exp2f(m - m_use);        // 0 on the first block (m = -inf)
+                const float corr = fast_exp2(m - m_use);    // 0 on the first block (m = -inf)
                 l *= corr;
                 if (full) {
                     // one-pass mode: the previous P.V must be complete, then the TMEM output tile is rescaled
@@ -247,9 +253,9 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (!full) {                                    // statistics pass: accumulate the row sum only
                 float rs = 0.f;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) rs += exp2f(__uint_as_float(sc[c][i]) - m_use);
+                    for (int i = 0; i < 32; ++i) rs += fast_exp2(__uint_as_float(sc[c][i]) - m_use);
                 l += rs;
                 if (vj == nstat - 1) inv_l = l > 0.f ? 1.f / l : 0.f;
                 continue;
@@ -262,13 +268,13 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                                  : nullptr;
             const float pscale = p.two_pass ? inv_l : 1.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float e[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        e[i] = exp2f(__uint_as_float(sc[c][g * 8 + i]) - m_use) * pscale;
+                        e[i] = fast_exp2(__uint_as_float(sc[c][g * 8 + i]) - m_use) * pscale;
                         rs += e[i];
                     }
                     uint4 pk;
@@ -281,8 +287,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
                         for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
                     }
-                    const int key8 = c * 4 + g;                               // 8-key group 0..15
-                    const uint32_t dst = sP + (key8 >> 3) * (kBQ * 128) + r * 128 + (((key8 & 7) ^ (r & 7)) << 4);
+                    const int key8 = c * 4 + g;                               // 8-key group 0..7
+                    const uint32_t dst = sP + r * 128 + ((key8 ^ (r & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z),
                                  "r"(pk.w)
                                  : "memory");
@@ -378,11 +384,12 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
     p.two_pass = P != nullptr ? 1 : 0;
     if (P) CB_REQUIRE(ldp >= nk && ldp % 8 == 0 && (reinterpret_cast<uintptr_t>(P) & 15u) == 0, CB_ERR_ALIGN, "attention_fwd: P row pitch must be a multiple of 8 elements >= nk");
     // S = Q K^T : M=128, N=128 keys, both K-major.  O = P V : M=128, N=dpad16, A K-major, B (V) MN-major.
-    p.idesc_s = umma_idesc_f16(128, 128, dtype == CB_BF16, false, false);
+    p.idesc_s = umma_idesc_f16(128, kBKV, dtype == CB_BF16, false, false);
     p.idesc_o = umma_idesc_f16(128, p.dboxes * 64, dtype == CB_BF16, false, true);   // N = whole 64-col chunks (zero-filled past d)
     CUtensorMap tq, tk, tv;
     uint32_t estr[4] = {1, 1, 1, 1};
-    uint32_t box[4] = {64, 128, 1, 1};
+    uint32_t box[4] = {64, kBQ, 1, 1};
+    uint32_t boxkv[4] = {64, kBKV, 1, 1};
     {
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)nq, (uint64_t)heads, (uint64_t)images};
         uint64_t str[3] = {(uint64_t)ldq * es, (uint64_t)d * es, (uint64_t)nq * ldq * es};
@@ -392,10 +399,10 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
     {
         uint64_t dims[4] = {(uint64_t)d, (uint64_t)nk, (uint64_t)heads, (uint64_t)images};
         uint64_t str[3] = {(uint64_t)ldk * es, (uint64_t)d * es, (uint64_t)nk * ldk * es};
-        int rc = make_tmap(&tk, dtype, 4, K, dims, str, box, estr);
+        int rc = make_tmap(&tk, dtype, 4, K, dims, str, boxkv, estr);
         if (rc) return rc;
         uint64_t strv[3] = {(uint64_t)ldv * es, (uint64_t)d * es, (uint64_t)nk * ldv * es};
-        rc = make_tmap(&tv, dtype, 4, V, dims, strv, box, estr);
+        rc = make_tmap(&tv, dtype, 4, V, dims, strv, boxkv, estr);
         if (rc) return rc;
     }
     dim3 grid((unsigned)ceil_div(nq, kBQ), (unsigned)heads, (unsigned)images);
