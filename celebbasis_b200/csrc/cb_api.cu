@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, error reporting, device probe.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "cb_common.cuh"
 
@@ -29,6 +30,11 @@ int device_sm_count() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
     return n;
+}
+
+bool pdl_enabled() {
+    static const bool on = !(getenv("CB_PDL") && atoi(getenv("CB_PDL")) == 0);
+    return on;
 }
 
 static unsigned long long g_launches = 0;

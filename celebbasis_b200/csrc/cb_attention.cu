@@ -125,6 +125,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
     const uint32_t tS0 = tmem, tO = tmem + 64;
+    pdl_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -354,7 +355,7 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         done = true;
     }
-    kern<<<grid, kAttnThreads, Cfg::kSmemBytes, st>>>(q, k, v, p);
+CB_LAUNCH((kern), grid, kAttnThreads, Cfg::kSmemBytes, st, q, k, v, p);
     CB_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;

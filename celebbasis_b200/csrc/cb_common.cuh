@@ -41,6 +41,30 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 int device_sm_count();
 void count_launches(int n);  // bookkeeping for cb_launch_count()
+bool pdl_enabled();          // programmatic dependent launch on (default) unless CB_PDL=0
+
+#if defined(__CUDACC__)
+// Every kernel is launched with the programmatic-stream-serialization attribute: its CTAs may be scheduled while the
+// previous kernel in the stream drains (prologue overlap); the kernel itself calls pdl_sync() before touching memory
+// the predecessor may still be writing.  Also valid under stream capture (programmatic graph edges).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define CB_LAUNCH(kern, grid, block, smem, st, ...) \
+    ::cb::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), (st), ##__VA_ARGS__)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -52,6 +76,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Programmatic dependent launch: let the next kernel's CTAs be scheduled, then wait until the previous kernel in the
+// stream has completed and its writes are visible.  No-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;

@@ -59,6 +59,7 @@ template <> struct V4<__nv_bfloat16> {
 template <typename TX, typename TY, typename TO>
 __global__ void axpby2d_kernel(const TX* __restrict__ x, long long ldx, float a, const TY* __restrict__ y,
                                long long ldy, float b, TO* __restrict__ o, long long ldo, long long rows, int cols4) {
+    pdl_sync();
     const long long total = rows * cols4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -104,10 +105,12 @@ __device__ __forceinline__ float act_grad(float x, int act) {
 }
 
 __global__ void act_fwd_kernel(const void* x, int xdt, void* y, int ydt, size_t n, int act) {
+    pdl_sync();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         st_any(y, ydt, i, act_fwd(ld_any(x, xdt, i), act));
 }
 __global__ void act_bwd_kernel(const void* dy, int gdt, const void* x, int xdt, void* dx, int ddt, size_t n, int act) {
+    pdl_sync();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         st_any(dx, ddt, i, ld_any(dy, gdt, i) * act_grad(ld_any(x, xdt, i), act));
 }
@@ -115,6 +118,7 @@ __global__ void act_bwd_kernel(const void* dy, int gdt, const void* x, int xdt, 
 // ---- GEGLU: out[m][f] = in[m][f] * gelu(in[m][F+f])  (ldm/modules/attention.py:37-45) ------------------------
 template <typename T>
 __global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, long long M, int F) {
+    pdl_sync();
     const int f4 = F >> 2;
     const long long total = M * f4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -132,6 +136,7 @@ __global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, 
 template <typename T, typename TG>
 __global__ void geglu_bwd_kernel(const TG* __restrict__ dout, const T* __restrict__ in, TG* __restrict__ din,
                                  long long M, int F) {
+    pdl_sync();
     const int f4 = F >> 2;
     const long long total = M * f4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -158,6 +163,7 @@ __global__ void geglu_bwd_kernel(const TG* __restrict__ dout, const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(128)
 softmax_fwd_kernel(const T* __restrict__ s, T* __restrict__ p, int ncols, int ld, int causal_period) {
+    pdl_sync();
     __shared__ float red[4];
     const long long row = blockIdx.x;
     const T* sr = s + row * ld;
@@ -187,6 +193,7 @@ softmax_fwd_kernel(const T* __restrict__ s, T* __restrict__ p, int ncols, int ld
 template <typename T, typename TG>
 __global__ void __launch_bounds__(128)
 softmax_bwd_kernel(const TG* __restrict__ dp, const T* __restrict__ p, TG* __restrict__ ds, int ncols, int ld) {
+    pdl_sync();
     __shared__ float red[4];
     const long long row = blockIdx.x;
     const TG* dr = dp + row * ld;
@@ -207,6 +214,7 @@ softmax_bwd_kernel(const TG* __restrict__ dp, const T* __restrict__ p, TG* __res
 // ---- nearest 2x upsample (openaimodel.py:112-117 F.interpolate(scale_factor=2, mode="nearest")) ------------
 template <typename T>
 __global__ void upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C4) {
+    pdl_sync();
     const long long total = (long long)N * (2 * H) * (2 * W) * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -225,6 +233,7 @@ __global__ void upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y
 template <typename TG, typename TD>
 __global__ void upsample2x_bwd_kernel(const TG* __restrict__ dy, TD* __restrict__ dx, int N, int H, int W, int C4,
                                       int accumulate) {
+    pdl_sync();
     const long long total = (long long)N * H * W * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -255,6 +264,7 @@ __global__ void upsample2x_bwd_kernel(const TG* __restrict__ dy, TD* __restrict_
 // zero-insertion (input of the stride-2 conv dgrad): z[n][2h][2w] = dy[n][h][w], other positions 0
 template <typename T>
 __global__ void zero_insert2x_kernel(const T* __restrict__ dy, T* __restrict__ z, int N, int H, int W, int C4) {
+    pdl_sync();
     const long long total = (long long)N * (2 * H) * (2 * W) * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -272,6 +282,7 @@ __global__ void zero_insert2x_kernel(const T* __restrict__ dy, T* __restrict__ z
 // ---- layout: NCHW fp32 <-> NHWC (channel-padded) (ddpm.py:344-350 rearrange 'b h w c -> b c h w') ------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, int ydt, int N, int C, int HW,
                                     int Cpad) {
+    pdl_sync();
     const long long total = (long long)N * HW * Cpad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -285,6 +296,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restric
 }
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, float* __restrict__ y, int N, int C, int HW,
                                     int Cpad) {
+    pdl_sync();
     const long long total = (long long)N * C * HW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -302,6 +314,7 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int xdt, float* 
 __global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                    float* __restrict__ loss, float* __restrict__ grad, int per_sample, float ginv,
                                    float gscale) {
+    pdl_sync();
     __shared__ float red[8];
     const int b = blockIdx.y;
     const size_t base = (size_t)b * per_sample;
@@ -324,6 +337,7 @@ __global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* 
 // ---- sinusoidal timestep embedding (diffusionmodules/util.py:151-171) ----------------------------------------
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, void* __restrict__ out, int odt, int B,
                                           int dim, float max_period) {
+    pdl_sync();
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
@@ -340,6 +354,7 @@ template <typename T, typename TY>
 __global__ void channel_affine_act_kernel(const T* __restrict__ x, TY* __restrict__ y, const float* __restrict__ scale,
                                           const float* __restrict__ shift, const float* __restrict__ slope,
                                           long long rows, int C4) {
+    pdl_sync();
     const long long total = rows * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -380,6 +395,7 @@ __device__ __forceinline__ float warp_src(const float* __restrict__ img, int H, 
 __global__ void face_warp_resize_kernel(const float* __restrict__ faces, void* __restrict__ out, int odt, int B, int H,
                                         int W, int n_chunks, int out_hw, int Cpad, float m00, float m01, float m02,
                                         float m10, float m11, float m12) {
+    pdl_sync();
     const int total = n_chunks * B * out_hw * out_hw * Cpad;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -417,6 +433,7 @@ __global__ void face_warp_resize_kernel(const float* __restrict__ faces, void* _
 
 // ---- row L2 normalise: F.normalize(x, dim=-1, p=2) (meta_net.py:264) ------------------------------------------
 __global__ void l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int D) {
+    pdl_sync();
     __shared__ float red[8];
     const float* xr = x + (size_t)blockIdx.x * D;
     float q = 0.f;
@@ -462,7 +479,7 @@ extern "C" int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, co
     const int grid = grid_for(rows * c4, 256);
     if (y == nullptr) y_dtype = x_dtype;
     CB_DISPATCH(x_dtype, TX, CB_DISPATCH(y_dtype, TY, CB_DISPATCH(o_dtype, TO,
-        axpby2d_kernel<TX, TY, TO><<<grid, 256, 0, st>>>((const TX*)x, ldx, a, (const TY*)y, ldy, b, (TO*)out, ldo, rows, c4))));
+CB_LAUNCH((axpby2d_kernel<TX, TY, TO>), grid, 256, 0, st, (const TX*)x, ldx, a, (const TY*)y, ldy, b, (TO*)out, ldo, rows, c4))));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -470,7 +487,7 @@ extern "C" int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, co
 
 extern "C" int cb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long n, int act, void* stream) {
     CB_REQUIRE(n > 0, CB_ERR_ARG, "act_fwd: n<=0");
-    act_fwd_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, y, y_dtype, (size_t)n, act);
+CB_LAUNCH((act_fwd_kernel), grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, x_dtype, y, y_dtype, (size_t)n, act);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -478,7 +495,7 @@ extern "C" int cb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, long
 extern "C" int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
                           long long n, int act, void* stream) {
     CB_REQUIRE(n > 0, CB_ERR_ARG, "act_bwd: n<=0");
-    act_bwd_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, dy_dtype, x, x_dtype, dx, dx_dtype, (size_t)n, act);
+CB_LAUNCH((act_bwd_kernel), grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), dy, dy_dtype, x, x_dtype, dx, dx_dtype, (size_t)n, act);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -487,7 +504,7 @@ extern "C" int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dty
 extern "C" int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, void* stream) {
     CB_REQUIRE(M > 0 && F > 0 && F % 4 == 0, CB_ERR_ARG, "geglu_fwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_DISPATCH16(dtype, T, geglu_fwd_kernel<T><<<grid_for(M * (F / 4), 256), 256, 0, st>>>((const T*)in, (T*)out, M, F));
+    CB_DISPATCH16(dtype, T,CB_LAUNCH((geglu_fwd_kernel<T>), grid_for(M * (F / 4), 256), 256, 0, st, (const T*)in, (T*)out, M, F));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -497,7 +514,7 @@ extern "C" int cb_geglu_bwd(const void* dout, const void* in, void* din, int dty
     CB_REQUIRE(M > 0 && F > 0 && F % 4 == 0, CB_ERR_ARG, "geglu_bwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH16(dtype, T, CB_DISPATCH16(g_dtype, TG,
-        geglu_bwd_kernel<T, TG><<<grid_for(M * (F / 4), 256), 256, 0, st>>>((const TG*)dout, (const T*)in, (TG*)din, M, F)));
+CB_LAUNCH((geglu_bwd_kernel<T, TG>), grid_for(M * (F / 4), 256), 256, 0, st, (const TG*)dout, (const T*)in, (TG*)din, M, F)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -507,7 +524,7 @@ extern "C" int cb_softmax_fwd(const void* s, void* p, int dtype, long long rows,
                               void* stream) {
     CB_REQUIRE(rows > 0 && ncols > 0 && ld >= ncols, CB_ERR_ARG, "softmax_fwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_DISPATCH16(dtype, T, softmax_fwd_kernel<T><<<(unsigned)rows, 128, 0, st>>>((const T*)s, (T*)p, ncols, ld, causal_period));
+    CB_DISPATCH16(dtype, T,CB_LAUNCH((softmax_fwd_kernel<T>), (unsigned)rows, 128, 0, st, (const T*)s, (T*)p, ncols, ld, causal_period));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -517,7 +534,7 @@ extern "C" int cb_softmax_bwd(const void* dp, const void* p, void* ds, int p_dty
     CB_REQUIRE(rows > 0 && ncols > 0 && ld >= ncols, CB_ERR_ARG, "softmax_bwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH16(p_dtype, T, CB_DISPATCH16(g_dtype, TG,
-        softmax_bwd_kernel<T, TG><<<(unsigned)rows, 128, 0, st>>>((const TG*)dp, (const T*)p, (TG*)ds, ncols, ld)));
+CB_LAUNCH((softmax_bwd_kernel<T, TG>), (unsigned)rows, 128, 0, st, (const TG*)dp, (const T*)p, (TG*)ds, ncols, ld)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -527,7 +544,7 @@ extern "C" int cb_upsample2x_fwd(const void* x, void* y, int dtype, int N, int H
     CB_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, CB_ERR_ARG, "upsample2x_fwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)N * 4 * H * W * (C / 4);
-    CB_DISPATCH(dtype, T, upsample2x_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C / 4));
+    CB_DISPATCH(dtype, T,CB_LAUNCH((upsample2x_fwd_kernel<T>), grid_for(total, 256), 256, 0, st, (const T*)x, (T*)y, N, H, W, C / 4));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -538,7 +555,7 @@ extern "C" int cb_upsample2x_bwd(const void* dy, int dy_dtype, void* dx, int dx_
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)N * H * W * (C / 4);
     CB_DISPATCH(dy_dtype, TG, CB_DISPATCH(dx_dtype, TD,
-        upsample2x_bwd_kernel<TG, TD><<<grid_for(total, 256), 256, 0, st>>>((const TG*)dy, (TD*)dx, N, H, W, C / 4, accumulate)));
+CB_LAUNCH((upsample2x_bwd_kernel<TG, TD>), grid_for(total, 256), 256, 0, st, (const TG*)dy, (TD*)dx, N, H, W, C / 4, accumulate)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -547,7 +564,7 @@ extern "C" int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H
     CB_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, CB_ERR_ARG, "zero_insert2x: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long long total = (long long)N * 4 * H * W * (C / 4);
-    CB_DISPATCH(dtype, T, zero_insert2x_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)dy, (T*)z, N, H, W, C / 4));
+    CB_DISPATCH(dtype, T,CB_LAUNCH((zero_insert2x_kernel<T>), grid_for(total, 256), 256, 0, st, (const T*)dy, (T*)z, N, H, W, C / 4));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -555,14 +572,14 @@ extern "C" int cb_zero_insert2x(const void* dy, void* z, int dtype, int N, int H
 
 extern "C" int cb_nchw_to_nhwc(const float* x, void* y, int y_dtype, int N, int C, int HW, int Cpad, void* stream) {
     CB_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C, CB_ERR_ARG, "nchw_to_nhwc: bad shape");
-    nchw_to_nhwc_kernel<<<grid_for((long long)N * HW * Cpad, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, y_dtype, N, C, HW, Cpad);
+CB_LAUNCH((nchw_to_nhwc_kernel), grid_for((long long)N * HW * Cpad, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, y, y_dtype, N, C, HW, Cpad);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_nhwc_to_nchw(const void* x, int x_dtype, float* y, int N, int C, int HW, int Cpad, void* stream) {
     CB_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C, CB_ERR_ARG, "nhwc_to_nchw: bad shape");
-    nhwc_to_nchw_kernel<<<grid_for((long long)N * HW * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, x_dtype, y, N, C, HW, Cpad);
+CB_LAUNCH((nhwc_to_nchw_kernel), grid_for((long long)N * HW * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, x_dtype, y, N, C, HW, Cpad);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -575,7 +592,7 @@ extern "C" int cb_mse_fwd_bwd(const float* pred, const float* target, float* los
     CB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * B, st));
     int gx = ceil_div(per_sample, 256);
     if (gx > 64) gx = 64;
-    mse_fwd_bwd_kernel<<<dim3(gx, B), 256, 0, st>>>(pred, target, loss, grad, per_sample,
+CB_LAUNCH((mse_fwd_bwd_kernel), dim3(gx, B), 256, 0, st, pred, target, loss, grad, per_sample,
                                                     1.f / ((float)B * (float)per_sample), gscale);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
@@ -586,7 +603,7 @@ extern "C" int cb_timestep_embedding(const long long* t, void* out, int o_dtype,
                                      void* stream) {
     CB_REQUIRE(B > 0 && dim >= 2, CB_ERR_ARG, "timestep_embedding: bad shape");
     const int n = B * (dim / 2);
-    timestep_embedding_kernel<<<ceil_div(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, out, o_dtype, B, dim, max_period);
+CB_LAUNCH((timestep_embedding_kernel), ceil_div(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream), t, out, o_dtype, B, dim, max_period);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -597,7 +614,7 @@ extern "C" int cb_channel_affine_act(const void* x, int x_dtype, void* y, int y_
     CB_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, CB_ERR_ARG, "channel_affine_act: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH(x_dtype, T, CB_DISPATCH(y_dtype, TY,
-        channel_affine_act_kernel<T, TY><<<grid_for(rows * (C / 4), 256), 256, 0, st>>>((const T*)x, (TY*)y, scale, shift, slope, rows, C / 4)));
+CB_LAUNCH((channel_affine_act_kernel<T, TY>), grid_for(rows * (C / 4), 256), 256, 0, st, (const T*)x, (TY*)y, scale, shift, slope, rows, C / 4)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -607,7 +624,7 @@ extern "C" int cb_face_warp_resize(const float* faces, void* out, int o_dtype, i
                                    int out_hw, int Cpad, const float* host_affine6, void* stream) {
     CB_REQUIRE(B > 0 && H > 1 && W > 1 && n_chunks > 0 && out_hw > 1 && Cpad >= 3 && host_affine6, CB_ERR_ARG, "face_warp_resize: bad args");
     const int total = n_chunks * B * out_hw * out_hw * Cpad;
-    face_warp_resize_kernel<<<ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+CB_LAUNCH((face_warp_resize_kernel), ceil_div(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
         faces, out, o_dtype, B, H, W, n_chunks, out_hw, Cpad, host_affine6[0], host_affine6[1], host_affine6[2],
         host_affine6[3], host_affine6[4], host_affine6[5]);
     CB_CUDA(cudaGetLastError());
@@ -617,7 +634,7 @@ extern "C" int cb_face_warp_resize(const float* faces, void* out, int o_dtype, i
 
 extern "C" int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* stream) {
     CB_REQUIRE(rows > 0 && D > 0, CB_ERR_ARG, "l2norm_rows: bad shape");
-    l2norm_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, D);
+CB_LAUNCH((l2norm_rows_kernel), rows, 256, 0, reinterpret_cast<cudaStream_t>(stream), x, y, D);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;

@@ -22,6 +22,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 
 __global__ void embedding_gather_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                         float* __restrict__ out, int n, int D, int V) {
+    pdl_sync();
     const int row = blockIdx.x;
     long long id = ids[row];
     if (id < 0) id = 0;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256)
 celeb_mlp_fwd_kernel(const float* __restrict__ v, const float* __restrict__ W, const float* __restrict__ b,
                      float* __restrict__ pre, float* __restrict__ coef, float* __restrict__ nrm, int in_dim, int K,
                      int es, float slope) {
+    pdl_sync();
     extern __shared__ float sm[];  // [in_dim] face vector + [K] activations
     __shared__ float red[8];
     float* sv = sm;
@@ -69,6 +71,7 @@ celeb_mlp_fwd_kernel(const float* __restrict__ v, const float* __restrict__ W, c
 __global__ void __launch_bounds__(256)
 celeb_basis_fwd_kernel(const float* __restrict__ coef, const float* __restrict__ basis, float* __restrict__ z, int K,
                        int D, int es) {
+    pdl_sync();
     extern __shared__ float sc[];  // [K]
     const int e = blockIdx.x % es;
     for (int k = threadIdx.x; k < K; k += 256) sc[k] = coef[(size_t)blockIdx.x * K + k];
@@ -85,6 +88,7 @@ celeb_basis_fwd_kernel(const float* __restrict__ coef, const float* __restrict__
 __global__ void __launch_bounds__(256)
 celeb_basis_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ basis, float* __restrict__ dcoef, int K,
                        int D, int es) {
+    pdl_sync();
     extern __shared__ float sd[];  // [D]
     const int e = blockIdx.x % es;
     for (int c = threadIdx.x; c < D; c += 256) sd[c] = dz[(size_t)blockIdx.x * D + c];
@@ -104,6 +108,7 @@ celeb_basis_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ b
 __global__ void __launch_bounds__(256)
 celeb_mlp_bwd_pre_kernel(const float* __restrict__ dcoef, const float* __restrict__ coef, const float* __restrict__ nrm,
                          const float* __restrict__ pre, float* __restrict__ dpre, int K, float slope, float gscale) {
+    pdl_sync();
     __shared__ float red[8];
     float dot = 0.f;
     for (int j = threadIdx.x; j < K; j += 256)
@@ -120,6 +125,7 @@ celeb_mlp_bwd_pre_kernel(const float* __restrict__ dcoef, const float* __restric
 // dW[o][i] = sum_f dpre[f][o] * v[f][i] ; db[o] = sum_f dpre[f][o]
 __global__ void celeb_mlp_bwd_w_kernel(const float* __restrict__ dpre, const float* __restrict__ v,
                                        float* __restrict__ dW, float* __restrict__ db, int F, int out_dim, int in_dim) {
+    pdl_sync();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= out_dim * in_dim) return;
     const int o = idx / in_dim, i = idx - o * in_dim;
@@ -137,6 +143,7 @@ __global__ void celeb_mlp_bwd_w_kernel(const float* __restrict__ dpre, const flo
 __global__ void embed_inject_fwd_kernel(const float* __restrict__ tok, const float* __restrict__ z,
                                         const int* __restrict__ map, const float* __restrict__ pos,
                                         float* __restrict__ out, int T, int D) {
+    pdl_sync();
     const int row = blockIdx.x;  // b*T + i
     const int b = row / T, i = row - b * T;
     const int m = map[row];
@@ -145,6 +152,7 @@ __global__ void embed_inject_fwd_kernel(const float* __restrict__ tok, const flo
 }
 __global__ void embed_inject_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ map,
                                         float* __restrict__ dz, int D) {
+    pdl_sync();
     const int row = blockIdx.x;
     const int m = map[row];
     if (m >= 0) return;
@@ -155,6 +163,7 @@ __global__ void embed_inject_bwd_kernel(const float* __restrict__ dout, const in
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
                              float bc1, float bc2_sqrt, const int* __restrict__ step_dev) {
+    pdl_sync();
     if (step_dev) {  // graph-replay friendly: the step counter lives on the device
         const float t = (float)(*step_dev + 1);
         bc1 = 1.f - powf(b1, t);
@@ -173,11 +182,13 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
-__global__ void bump_step_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void bump_step_kernel(int* step_dev) {
+    pdl_sync(); *step_dev += 1; }
 
 // z = scale * (mean + exp(0.5*clamp(logvar,-30,20)) * eps); moments NCHW [N][2*Cz][HW]
 __global__ void posterior_sample_kernel(const float* __restrict__ moments, const float* __restrict__ eps,
                                         float* __restrict__ z, int N, int Cz, int HW, float scale) {
+    pdl_sync();
     const long long total = (long long)N * Cz * HW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i % HW);
@@ -195,6 +206,7 @@ __global__ void posterior_sample_kernel(const float* __restrict__ moments, const
 __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                 const long long* __restrict__ t, const float* __restrict__ sqrt_ac,
                                 const float* __restrict__ sqrt_1mac, float* __restrict__ out, int per_sample) {
+    pdl_sync();
     const int b = blockIdx.y;
     const float a = sqrt_ac[t[b]], s = sqrt_1mac[t[b]];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
@@ -208,6 +220,7 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ noise, float* __restrict__ x_prev, float* __restrict__ pred_x0,
                                  long long n, float scale, float sqrt_at, float sqrt_aprev, float sigma, float sqrt_1m_at,
                                  float dir_coef) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float e = e_u[i];
         if (e_c) e = e + scale * (e_c[i] - e);
@@ -230,7 +243,7 @@ extern "C" int cb_ddim_step(const float* x, const float* e_uncond, const float* 
     const float dir = sqrtf(fmaxf(1.f - a_prev - sigma_t * sigma_t, 0.f));
     long long blocks = (n + 255) / 256;
     if (blocks > 1184) blocks = 1184;
-    ddim_step_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+CB_LAUNCH((ddim_step_kernel), (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), 
         x, e_uncond, e_cond, noise, x_prev, pred_x0, n, guidance_scale, sqrtf(a_t), sqrtf(a_prev), sigma_t,
         sqrt_one_minus_at, dir);
     CB_CUDA(cudaGetLastError());
@@ -242,7 +255,7 @@ extern "C" int cb_q_sample(const float* x0, const float* noise, const long long*
                            const float* sqrt_1mac, float* out, int B, int per_sample, void* stream) {
     CB_REQUIRE(B > 0 && per_sample > 0, CB_ERR_ARG, "q_sample: bad shape");
     dim3 grid((unsigned)((per_sample + 255) / 256 > 64 ? 64 : (per_sample + 255) / 256), (unsigned)B);
-    q_sample_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
+CB_LAUNCH((q_sample_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -251,7 +264,7 @@ extern "C" int cb_q_sample(const float* x0, const float* noise, const long long*
 extern "C" int cb_embedding_gather(const long long* ids, const float* table, float* out, int n, int D, int V,
                                    void* stream) {
     CB_REQUIRE(n > 0 && D > 0 && D % 4 == 0 && V > 0, CB_ERR_ARG, "embedding_gather: bad shape");
-    embedding_gather_kernel<<<n, 192, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, table, out, n, D, V);
+CB_LAUNCH((embedding_gather_kernel), n, 192, 0, reinterpret_cast<cudaStream_t>(stream), ids, table, out, n, D, V);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -260,7 +273,7 @@ extern "C" int cb_embedding_gather(const long long* ids, const float* table, flo
 extern "C" int cb_celeb_mlp_fwd(const float* v, const float* W, const float* b, float* pre, float* coef, float* nrm,
                                 int F, int in_dim, int K, int es, float slope, void* stream) {
     CB_REQUIRE(F > 0 && in_dim > 0 && K > 0 && es > 0 && (in_dim + K) * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_mlp_fwd: bad shape");
-    celeb_mlp_fwd_kernel<<<F * es, 256, (in_dim + K) * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+CB_LAUNCH((celeb_mlp_fwd_kernel), F * es, 256, (in_dim + K) * sizeof(float), reinterpret_cast<cudaStream_t>(stream), 
         v, W, b, pre, coef, nrm, in_dim, K, es, slope);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
@@ -270,7 +283,7 @@ extern "C" int cb_celeb_mlp_fwd(const float* v, const float* W, const float* b, 
 extern "C" int cb_celeb_basis_fwd(const float* coef, const float* basis, float* z, int F, int es, int K, int D,
                                   void* stream) {
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && K * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_fwd: bad shape");
-    celeb_basis_fwd_kernel<<<F * es, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(coef, basis, z, K, D, es);
+CB_LAUNCH((celeb_basis_fwd_kernel), F * es, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream), coef, basis, z, K, D, es);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -279,7 +292,7 @@ extern "C" int cb_celeb_basis_fwd(const float* coef, const float* basis, float* 
 extern "C" int cb_celeb_basis_bwd(const float* dz, const float* basis, float* dcoef, int F, int es, int K, int D,
                                   void* stream) {
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && D * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_bwd: bad shape");
-    celeb_basis_bwd_kernel<<<F * es, 256, D * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(dz, basis, dcoef, K, D, es);
+CB_LAUNCH((celeb_basis_bwd_kernel), F * es, 256, D * sizeof(float), reinterpret_cast<cudaStream_t>(stream), dz, basis, dcoef, K, D, es);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -290,9 +303,9 @@ extern "C" int cb_celeb_mlp_bwd(const float* dcoef, const float* coef, const flo
                                 float slope, float gscale, void* stream) {
     CB_REQUIRE(F > 0 && in_dim > 0 && K > 0 && es > 0, CB_ERR_ARG, "celeb_mlp_bwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    celeb_mlp_bwd_pre_kernel<<<F * es, 256, 0, st>>>(dcoef, coef, nrm, pre, dpre_ws, K, slope, gscale);
+CB_LAUNCH((celeb_mlp_bwd_pre_kernel), F * es, 256, 0, st, dcoef, coef, nrm, pre, dpre_ws, K, slope, gscale);
     const int out_dim = es * K;
-    celeb_mlp_bwd_w_kernel<<<ceil_div(out_dim * in_dim, 256), 256, 0, st>>>(dpre_ws, v, dW, db, F, out_dim, in_dim);
+CB_LAUNCH((celeb_mlp_bwd_w_kernel), ceil_div(out_dim * in_dim, 256), 256, 0, st, dpre_ws, v, dW, db, F, out_dim, in_dim);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);
     return 0;
@@ -301,7 +314,7 @@ extern "C" int cb_celeb_mlp_bwd(const float* dcoef, const float* coef, const flo
 extern "C" int cb_embed_inject_fwd(const float* tok, const float* z, const int* map, const float* pos, float* out,
                                    int B, int T, int D, void* stream) {
     CB_REQUIRE(B > 0 && T > 0 && D > 0, CB_ERR_ARG, "embed_inject_fwd: bad shape");
-    embed_inject_fwd_kernel<<<B * T, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tok, z, map, pos, out, T, D);
+CB_LAUNCH((embed_inject_fwd_kernel), B * T, 256, 0, reinterpret_cast<cudaStream_t>(stream), tok, z, map, pos, out, T, D);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -312,7 +325,7 @@ extern "C" int cb_embed_inject_bwd(const float* dout, const int* map, float* dz,
     CB_REQUIRE(B > 0 && T > 0 && D > 0 && n_z_rows > 0, CB_ERR_ARG, "embed_inject_bwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n_z_rows * D, st));
-    embed_inject_bwd_kernel<<<B * T, 256, 0, st>>>(dout, map, dz, D);
+CB_LAUNCH((embed_inject_bwd_kernel), B * T, 256, 0, st, dout, map, dz, D);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -326,8 +339,8 @@ extern "C" int cb_adamw_step(float* p, const float* g, float* m, float* v, long 
     long long blocks = (n + 255) / 256;
     if (blocks > 1184) blocks = 1184;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    adamw_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, step_dev);
-    if (step_dev) bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+CB_LAUNCH((adamw_kernel), (unsigned)blocks, 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, step_dev);
+    if (step_dev)CB_LAUNCH((bump_step_kernel), 1, 1, 0, st, step_dev);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);
     return 0;
@@ -337,7 +350,7 @@ extern "C" int cb_posterior_sample(const float* moments, const float* eps, float
                                    float scale, void* stream) {
     CB_REQUIRE(N > 0 && Cz > 0 && HW > 0, CB_ERR_ARG, "posterior_sample: bad shape");
     const long long total = (long long)N * Cz * HW;
-    posterior_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(moments, eps, z, N, Cz, HW, scale);
+CB_LAUNCH((posterior_sample_kernel), (unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), moments, eps, z, N, Cz, HW, scale);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;

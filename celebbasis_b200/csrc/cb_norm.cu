@@ -61,6 +61,7 @@ template <typename TX>
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C, int G, int rows_per_block, int PW,
                 int RY, int chunks) {
+    pdl_sync();
     __shared__ float s_sum[64], s_sq[64];
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
@@ -107,6 +108,7 @@ gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __res
                 const float* __restrict__ beta, const double* __restrict__ ws, float* __restrict__ mean_out,
                 float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act, int rows_per_block, int PW,
                 int RY, int chunks) {
+    pdl_sync();
     __shared__ float s_mean[64], s_rstd[64];
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
@@ -153,6 +155,7 @@ gn_bwd_stats_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                     double* __restrict__ ws, int HW, int C, int G, int act, int rows_per_block, int PW, int RY,
                     int chunks) {
+    pdl_sync();
     __shared__ float s_1[64], s_2[64];
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
@@ -199,6 +202,7 @@ gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const double* __restrict__ ws, TD* __restrict__ dx, int HW, int C, int G, int act,
                     int accumulate, int rows_per_block, int PW, int RY, int chunks) {
+    pdl_sync();
     __shared__ float s_1[64], s_2[64];
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(128)
 ln_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
               const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C,
               float eps) {
+    pdl_sync();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -298,6 +303,7 @@ __global__ void __launch_bounds__(128)
 ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, TD* __restrict__ dx, int M, int C,
               int accumulate) {
+    pdl_sync();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -380,9 +386,9 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     dim3 grid(ceil_div(HW, rpb), N);
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
-    CB_DISPATCH_2(x_dtype, TX, gn_stats_kernel<TX><<<grid, nthr, 0, st>>>((const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));
+    CB_DISPATCH_2(x_dtype, TX,CB_LAUNCH((gn_stats_kernel<TX>), grid, nthr, 0, st, (const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
-        gn_apply_kernel<TX, TY><<<grid, nthr, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_apply_kernel<TX, TY>), grid, nthr, 0, st, (const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);
     return 0;
@@ -400,15 +406,15 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-        gn_bwd_stats_kernel<TX, TG><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_bwd_stats_kernel<TX, TG>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
     // dx dtype: f32 or the gradient dtype
     if (dx_dtype == CB_F32) {
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            gn_bwd_apply_kernel<TX, TG, float><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, float>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     } else {
         CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            gn_bwd_apply_kernel<TX, TG, TG><<<grid, nthr, 0, st>>>((const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, TG>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     }
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);
@@ -421,7 +427,7 @@ extern "C" int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(ceil_div(M, 4));
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
-        ln_fwd_kernel<TX, TY><<<grid, 128, 0, st>>>((const TX*)x, (TY*)y, gamma, beta, mean_out, rstd_out, M, C, eps)));
+CB_LAUNCH((ln_fwd_kernel<TX, TY>), grid, 128, 0, st, (const TX*)x, (TY*)y, gamma, beta, mean_out, rstd_out, M, C, eps)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -435,11 +441,11 @@ extern "C" int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int
     dim3 grid(ceil_div(M, 4));
     if (dx_dtype == CB_F32) {
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            ln_bwd_kernel<TX, TG, float><<<grid, 128, 0, st>>>((const TG*)dy, (const TX*)x, gamma, mean, rstd, (float*)dx, M, C, accumulate)));
+CB_LAUNCH((ln_bwd_kernel<TX, TG, float>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (float*)dx, M, C, accumulate)));
     } else {
         CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "layernorm_bwd: dx dtype must be f32 or equal dy dtype");
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-            ln_bwd_kernel<TX, TG, TG><<<grid, 128, 0, st>>>((const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, M, C, accumulate)));
+CB_LAUNCH((ln_bwd_kernel<TX, TG, TG>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, M, C, accumulate)));
     }
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
