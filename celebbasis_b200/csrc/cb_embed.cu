@@ -32,59 +32,79 @@ __global__ void embedding_gather_kernel(const long long* __restrict__ ids, const
     for (int c = threadIdx.x; c < D / 4; c += blockDim.x) dst[c] = src[c];
 }
 
-// block per (face f, token e): pre = v W^T + b ; act = leaky(pre) ; coef = act / max(||act||, 1e-12)
+// pre[f][o] = v[f] . W[o] + b[o]: one warp per output row o (all faces at once), 8 outputs per block => out_dim/8 blocks
+constexpr int kMaxFaces = 16;
 __global__ void __launch_bounds__(256)
-celeb_mlp_fwd_kernel(const float* __restrict__ v, const float* __restrict__ W, const float* __restrict__ b,
-                     float* __restrict__ pre, float* __restrict__ coef, float* __restrict__ nrm, int in_dim, int K,
-                     int es, float slope) {
+celeb_mlp_pre_kernel(const float* __restrict__ v, const float* __restrict__ W, const float* __restrict__ b,
+                     float* __restrict__ pre, int F, int in_dim, int out_dim) {
     pdl_sync();
-    extern __shared__ float sm[];  // [in_dim] face vector + [K] activations
-    __shared__ float red[8];
-    float* sv = sm;
-    float* sa = sm + in_dim;
-    const int f = blockIdx.x / es, e = blockIdx.x % es;
-    for (int i = threadIdx.x; i < in_dim; i += 256) sv[i] = v[(size_t)f * in_dim + i];
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < K; j += 8) {
-        const int o = e * K + j;
-        const float* wr = W + (size_t)o * in_dim;
-        float acc = 0.f;
-        for (int i = lane; i < in_dim; i += 32) acc += wr[i] * sv[i];
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float p = acc + b[o];
-            pre[(size_t)f * es * K + o] = p;
-            sa[j] = p > 0.f ? p : slope * p;
+    const int o = blockIdx.x * 8 + warp;
+    if (o >= out_dim) return;
+    float acc[kMaxFaces];
+#pragma unroll
+    for (int f = 0; f < kMaxFaces; ++f) acc[f] = 0.f;
+    const float* wr = W + (size_t)o * in_dim;
+    for (int i = lane; i < in_dim; i += 32) {
+        const float w = wr[i];
+#pragma unroll
+        for (int f = 0; f < kMaxFaces; ++f)
+            if (f < F) acc[f] += w * v[(size_t)f * in_dim + i];
+    }
+#pragma unroll
+    for (int f = 0; f < kMaxFaces; ++f) {
+        if (f < F) {
+            const float t = warp_sum(acc[f]);
+            if (lane == 0) pre[(size_t)f * out_dim + o] = t + b[o];
         }
     }
-    __syncthreads();
+}
+
+// block per (face f, token e): act = leaky(pre) ; coef = act / max(||act||, 1e-12)
+__global__ void __launch_bounds__(256)
+celeb_mlp_norm_kernel(const float* __restrict__ pre, float* __restrict__ coef, float* __restrict__ nrm, int K, float slope) {
+    pdl_sync();
+    __shared__ float red[8];
     float q = 0.f;
-    for (int j = threadIdx.x; j < K; j += 256) q += sa[j] * sa[j];
+    for (int j = threadIdx.x; j < K; j += 256) {
+        const float pv = pre[(size_t)blockIdx.x * K + j];
+        const float a = pv > 0.f ? pv : slope * pv;
+        q += a * a;
+    }
     q = block_sum_256(q, red);
     const float n = fmaxf(sqrtf(q), 1e-12f);
     if (threadIdx.x == 0) nrm[blockIdx.x] = n;
-    for (int j = threadIdx.x; j < K; j += 256) coef[(size_t)blockIdx.x * K + j] = sa[j] / n;
+    for (int j = threadIdx.x; j < K; j += 256) {
+        const float pv = pre[(size_t)blockIdx.x * K + j];
+        coef[(size_t)blockIdx.x * K + j] = (pv > 0.f ? pv : slope * pv) / n;
+    }
 }
 
-// z[f][e][c] = sum_k coef[f][e][k] * basis[e][1+k][c] + basis[e][0][c]
-__global__ void __launch_bounds__(256)
+// z[f][e][c] = sum_k coef[f][e][k] * basis[e][1+k][c] + basis[e][0][c]; grid (F*es, D/128)
+__global__ void __launch_bounds__(128)
 celeb_basis_fwd_kernel(const float* __restrict__ coef, const float* __restrict__ basis, float* __restrict__ z, int K,
                        int D, int es) {
     pdl_sync();
     extern __shared__ float sc[];  // [K]
     const int e = blockIdx.x % es;
-    for (int k = threadIdx.x; k < K; k += 256) sc[k] = coef[(size_t)blockIdx.x * K + k];
+    for (int k = threadIdx.x; k < K; k += 128) sc[k] = coef[(size_t)blockIdx.x * K + k];
     __syncthreads();
     const float* be = basis + (size_t)e * (K + 1) * D;
-    for (int c = threadIdx.x; c < D; c += 256) {
-        float acc = be[c];
-        for (int k = 0; k < K; ++k) acc += sc[k] * be[(size_t)(k + 1) * D + c];
-        z[(size_t)blockIdx.x * D + c] = acc;
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    if (c >= D) return;
+    float a0 = be[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 3 < K; k += 4) {
+        a0 += sc[k] * be[(size_t)(k + 1) * D + c];
+        a1 += sc[k + 1] * be[(size_t)(k + 2) * D + c];
+        a2 += sc[k + 2] * be[(size_t)(k + 3) * D + c];
+        a3 += sc[k + 3] * be[(size_t)(k + 4) * D + c];
     }
+    for (; k < K; ++k) a0 += sc[k] * be[(size_t)(k + 1) * D + c];
+    z[(size_t)blockIdx.x * D + c] = (a0 + a1) + (a2 + a3);
 }
 
-// dcoef[f][e][k] = sum_c dz[f][e][c] * basis[e][1+k][c]   (warp per k)
+// dcoef[f][e][k] = sum_c dz[f][e][c] * basis[e][1+k][c]   (warp per k; grid (F*es, 16))
 __global__ void __launch_bounds__(256)
 celeb_basis_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ basis, float* __restrict__ dcoef, int K,
                        int D, int es) {
@@ -95,7 +115,9 @@ celeb_basis_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ b
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* be = basis + (size_t)e * (K + 1) * D;
-    for (int k = warp; k < K; k += 8) {
+    const int kper = (K + gridDim.y - 1) / gridDim.y;
+    const int k0 = blockIdx.y * kper, k1 = min(K, k0 + kper);
+    for (int k = k0 + warp; k < k1; k += 8) {
         const float* br = be + (size_t)(k + 1) * D;
         float acc = 0.f;
         for (int c = lane; c < D; c += 32) acc += sd[c] * br[c];
@@ -272,18 +294,20 @@ CB_LAUNCH((embedding_gather_kernel), n, 192, 0, reinterpret_cast<cudaStream_t>(s
 
 extern "C" int cb_celeb_mlp_fwd(const float* v, const float* W, const float* b, float* pre, float* coef, float* nrm,
                                 int F, int in_dim, int K, int es, float slope, void* stream) {
-    CB_REQUIRE(F > 0 && in_dim > 0 && K > 0 && es > 0 && (in_dim + K) * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_mlp_fwd: bad shape");
-CB_LAUNCH((celeb_mlp_fwd_kernel), F * es, 256, (in_dim + K) * sizeof(float), reinterpret_cast<cudaStream_t>(stream), 
-        v, W, b, pre, coef, nrm, in_dim, K, es, slope);
+    CB_REQUIRE(F > 0 && F <= kMaxFaces && in_dim > 0 && K > 0 && es > 0, CB_ERR_ARG, "celeb_mlp_fwd: bad shape (F <= %d)", kMaxFaces);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int out_dim = es * K;
+    CB_LAUNCH((celeb_mlp_pre_kernel), ceil_div(out_dim, 8), 256, 0, st, v, W, b, pre, F, in_dim, out_dim);
+    CB_LAUNCH((celeb_mlp_norm_kernel), F * es, 256, 0, st, (const float*)pre, coef, nrm, K, slope);
     CB_CUDA(cudaGetLastError());
-    cb::count_launches(1);
+    cb::count_launches(2);
     return 0;
 }
 
 extern "C" int cb_celeb_basis_fwd(const float* coef, const float* basis, float* z, int F, int es, int K, int D,
                                   void* stream) {
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && K * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_fwd: bad shape");
-CB_LAUNCH((celeb_basis_fwd_kernel), F * es, 256, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream), coef, basis, z, K, D, es);
+    CB_LAUNCH((celeb_basis_fwd_kernel), dim3(F * es, ceil_div(D, 128)), 128, K * sizeof(float), reinterpret_cast<cudaStream_t>(stream), coef, basis, z, K, D, es);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
@@ -292,7 +316,7 @@ CB_LAUNCH((celeb_basis_fwd_kernel), F * es, 256, K * sizeof(float), reinterpret_
 extern "C" int cb_celeb_basis_bwd(const float* dz, const float* basis, float* dcoef, int F, int es, int K, int D,
                                   void* stream) {
     CB_REQUIRE(F > 0 && es > 0 && K > 0 && D > 0 && D * 4 <= 48 * 1024, CB_ERR_ARG, "celeb_basis_bwd: bad shape");
-CB_LAUNCH((celeb_basis_bwd_kernel), F * es, 256, D * sizeof(float), reinterpret_cast<cudaStream_t>(stream), dz, basis, dcoef, K, D, es);
+    CB_LAUNCH((celeb_basis_bwd_kernel), dim3(F * es, 16), 256, D * sizeof(float), reinterpret_cast<cudaStream_t>(stream), dz, basis, dcoef, K, D, es);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;

@@ -497,13 +497,40 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
     return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
 }
 
-static int pick_bn(const cb_gemm_desc& d) {
+// Measured on B200 (tools/gemm_timeline.py): one SM pulls ~80 GB/s of operand tiles out of L2, i.e. a k-iteration of a
+// 128 x BN tile costs ~(128+BN)*128 B / 80 GB/s (0.45 us at BN=160) while its MMAs take 0.17 us; a split-K reduction
+// costs ~1 ns per 150 fp32 adds in L2 plus ~3 us of hand-off.  The tile width and the split are chosen to minimise
+// that estimate for the launch at hand.
+static double tile_time_us(int bn, long long tiles, int kiters, int sms) {
+    const double t_iter = (128.0 + bn) * 128.0 / 80e3;          // us per k-iteration per CTA
+    const long long waves = (tiles + sms - 1) / sms;
+    return (double)waves * kiters * t_iter;
+}
+
+static int pick_bn(const cb_gemm_desc& d, int m_tiles, int kiters) {
     const int N = d.N;
-    if (d.b_major == CB_MAJOR_MN) return N <= 64 ? 64 : 128;
-    if (N % 160 == 0) return 160;
-    if (N <= 64) return 64;
-    if (N % 128 == 0 || N > 160) return 128;
-    return N <= 128 ? 128 : 160;
+    const int sms = device_sm_count();
+    int cands[3];
+    int nc = 0;
+    if (d.b_major == CB_MAJOR_MN) {
+        if (N <= 64) return 64;
+        cands[nc++] = 128;
+        cands[nc++] = 64;
+    } else {
+        if (N <= 64) return 64;
+        cands[nc++] = 160;
+        cands[nc++] = 128;
+        cands[nc++] = 64;
+    }
+    int best = cands[0];
+    double best_t = 1e30;
+    for (int i = 0; i < nc; ++i) {
+        const int bn = cands[i];
+        const long long tiles = (long long)ceil_div(N, bn) * m_tiles * d.batch;
+        double t = tile_time_us(bn, tiles, kiters, sms) + 0.02 * ceil_div(N, bn);   // tie-break: fewer, wider tiles
+        if (t < best_t) { best_t = t; best = bn; }
+    }
+    return best;
 }
 
 }  // namespace cb
@@ -602,7 +629,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         }
     }
 
-    const int BN = pick_bn(d);
+    const int BN = pick_bn(d, m_tiles, p.taps * p.kchunks);
     p.b_bytes = (unsigned)BN * BK * es;
     {
         const uint64_t brows_total = (uint64_t)(d.conv ? (int64_t)p.taps * d.b_tap_rows : (b_mn ? d.K : d.N));
@@ -668,19 +695,23 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         const long long tiles = (long long)ceil_div(d.N, BN) * m_tiles * d.batch;
         const int sms = device_sm_count();
         // (L2 reductions serialise per address, so split-K only pays when the output tile is small: <= 512 rows)
-        const bool small_out = (long long)p.M * d.batch <= 512;
-        if (d.splitk_ws != nullptr && tiles * 2 <= sms && kiters >= 8 && (small_out || sms / tiles >= 4)) {
-            // at most one CTA per SM in a single wave (each then runs the 6-stage ring), >= 4 k-iterations per split
-            int want = (int)(sms / tiles);
-            int by_k = kiters / 4;
-            int sp = want < by_k ? want : by_k;
-            if (sp > 64) sp = 64;
-            const long long counters_bytes = 65536;
-            const long long avail = d.splitk_ws_bytes - counters_bytes;
-            if (sp > 1 && tiles <= counters_bytes / 4 && tiles * (long long)(BM * BN * 4) <= avail) {
+        const long long counters_bytes = 65536;
+        const long long avail = d.splitk_ws_bytes - counters_bytes;
+        if (d.splitk_ws != nullptr && tiles < sms && kiters >= 8 && tiles <= counters_bytes / 4 &&
+            tiles * (long long)(BM * BN * 4) <= avail) {
+            const double out_elems = (double)p.M * d.batch * d.N;
+            double best_t = tile_time_us(BN, tiles, kiters, sms);
+            int best_sp = 1;
+            const int max_sp = (int)(sms / tiles) < 64 ? (int)(sms / tiles) : 64;
+            for (int sp = 2; sp <= max_sp; ++sp) {
                 const int per = ceil_div(kiters, sp);
-                sp = ceil_div(kiters, per);
-                p.splits = sp;
+                if (per < 4) break;
+                const double t = per * ((128.0 + BN) * 128.0 / 80e3) + out_elems * sp / 150e3 + 3.0;
+                if (t < best_t) { best_t = t; best_sp = sp; }
+            }
+            if (best_sp > 1) {
+                const int per = ceil_div(kiters, best_sp);
+                p.splits = ceil_div(kiters, per);
                 p.kiters_per_split = per;
                 p.counters = reinterpret_cast<unsigned*>(d.splitk_ws);
                 p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(d.splitk_ws) + counters_bytes);

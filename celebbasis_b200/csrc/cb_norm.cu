@@ -245,6 +245,185 @@ gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
     }
 }
 
+// ---- single-kernel GroupNorm for tensors that fit in the SMs' shared memory (every UNet activation at bs=1) -----
+// grid = (row blocks, images) with at most one CTA per SM, so all CTAs are co-resident: each CTA loads its rows ONCE
+// into shared memory while accumulating the group sums, publishes them with fp64 atomics, waits on a grid-wide
+// arrival counter, then normalises straight out of shared memory.  x is read from HBM/L2 once instead of twice and
+// the statistics + apply passes are one launch.
+__device__ __forceinline__ void grid_arrive_and_wait(unsigned* counter, unsigned expected) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(counter) < expected) { __nanosleep(64); }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kGnThreads)
+gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, double* __restrict__ ws, unsigned* __restrict__ counter,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act,
+                    int rows_per_block, int PW, int RY, int chunks) {
+    pdl_sync();
+    extern __shared__ __align__(16) unsigned char gn_smem[];
+    TX* sx = reinterpret_cast<TX*>(gn_smem);
+    __shared__ float s_a[64], s_b[64];
+    const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const int cpg = C / G;
+    if (threadIdx.x < 64) { s_a[threadIdx.x] = 0.f; s_b[threadIdx.x] = 0.f; }
+    __syncthreads();
+    float a1[kGnMaxChunks], a2[kGnMaxChunks];
+#pragma unroll
+    for (int j = 0; j < kGnMaxChunks; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+    const TX* xb = x + ((size_t)n * HW) * C + 2 * tx;
+#pragma unroll 2
+    for (int r = r0 + ty; r < r1; r += RY) {
+        const TX* xr = xb + (size_t)r * C;
+        TX* sr = sx + (size_t)(r - r0) * C + 2 * tx;
+#pragma unroll
+        for (int j = 0; j < kGnMaxChunks; ++j) {
+            if (j < chunks) {
+                const float2 v = Vec2<TX>::ld(xr + 2 * j * PW);
+                Vec2<TX>::st(sr + 2 * j * PW, v);
+                a1[j] += v.x + v.y;
+                a2[j] += v.x * v.x + v.y * v.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kGnMaxChunks; ++j) {
+        if (j < chunks) {
+            const int g = (2 * (tx + j * PW)) / cpg;
+            atomicAdd(&s_a[g], a1[j]);
+            atomicAdd(&s_b[g], a2[j]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_a[threadIdx.x]);
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_b[threadIdx.x]);
+    }
+    grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        const double m = __ldcg(&ws[((size_t)n * G + threadIdx.x) * 2]) / cnt;
+        double var = __ldcg(&ws[((size_t)n * G + threadIdx.x) * 2 + 1]) / cnt - m * m;
+        if (var < 0) var = 0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        s_a[threadIdx.x] = (float)m;
+        s_b[threadIdx.x] = rs;
+        if (blockIdx.x == 0) {
+            mean_out[n * G + threadIdx.x] = (float)m;
+            rstd_out[n * G + threadIdx.x] = rs;
+        }
+    }
+    __syncthreads();
+    const size_t base = ((size_t)n * HW) * C;
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
+        const int g = c / cpg;
+        const float m = s_a[g], rs = s_b[g];
+        const float g0 = gamma[c] * rs, g1 = gamma[c + 1] * rs;
+        const float b0 = beta[c] - m * g0, b1 = beta[c + 1] - m * g1;
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += RY) {
+            float2 v = Vec2<TX>::ld(sx + (size_t)(r - r0) * C + c);
+            v.x = v.x * g0 + b0;
+            v.y = v.y * g1 + b1;
+            if (act) { v.x = silu_f(v.x); v.y = silu_f(v.y); }
+            Vec2<TY>::st(y + base + (size_t)r * C + c, v);
+        }
+    }
+}
+
+template <typename TX, typename TG, typename TD>
+__global__ void __launch_bounds__(kGnThreads)
+gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    double* __restrict__ ws, unsigned* __restrict__ counter, TD* __restrict__ dx, int HW, int C, int G,
+                    int act, int accumulate, int rows_per_block, int PW, int RY, int chunks) {
+    pdl_sync();
+    // shared memory caches, per element, xhat (fp32) and t = dz*gamma (fp32) of this CTA's rows
+    extern __shared__ __align__(16) unsigned char gn_smem[];
+    float* sxh = reinterpret_cast<float*>(gn_smem);
+    float* st = sxh + (size_t)rows_per_block * C;
+    __shared__ float s_1[64], s_2[64];
+    const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
+    const int cpg = C / G;
+    if (threadIdx.x < 64) { s_1[threadIdx.x] = 0.f; s_2[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const size_t base = ((size_t)n * HW) * C;
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
+        const int g = c / cpg;
+        const float m = mean[n * G + g], rs = rstd[n * G + g];
+        const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll 2
+        for (int r = r0 + ty; r < r1; r += RY) {
+            const size_t off = base + (size_t)r * C + c;
+            const float2 xv = Vec2<TX>::ld(x + off);
+            float2 d = Vec2<TG>::ld(dy + off);
+            const float xh0 = (xv.x - m) * rs, xh1 = (xv.y - m) * rs;
+            if (act) {
+                d.x *= silu_grad(xh0 * ga0 + be0);
+                d.y *= silu_grad(xh1 * ga1 + be1);
+            }
+            const float t0 = d.x * ga0, t1 = d.y * ga1;
+            const size_t so = (size_t)(r - r0) * C + c;
+            *reinterpret_cast<float2*>(sxh + so) = make_float2(xh0, xh1);
+            *reinterpret_cast<float2*>(st + so) = make_float2(t0, t1);
+            a1 += t0 + t1;
+            a2 += t0 * xh0 + t1 * xh1;
+        }
+        atomicAdd(&s_1[g], a1);
+        atomicAdd(&s_2[g], a2);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_1[threadIdx.x]);
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_2[threadIdx.x]);
+    }
+    grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        s_1[threadIdx.x] = (float)(__ldcg(&ws[((size_t)n * G + threadIdx.x) * 2]) / cnt);
+        s_2[threadIdx.x] = (float)(__ldcg(&ws[((size_t)n * G + threadIdx.x) * 2 + 1]) / cnt);
+    }
+    __syncthreads();
+    for (int j = 0; j < chunks; ++j) {
+        const int c = 2 * (tx + j * PW);
+        const int g = c / cpg;
+        const float rs = rstd[n * G + g];
+        const float m1 = s_1[g], m2 = s_2[g];
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += RY) {
+            const size_t so = (size_t)(r - r0) * C + c;
+            const float2 xh = *reinterpret_cast<const float2*>(sxh + so);
+            const float2 t = *reinterpret_cast<const float2*>(st + so);
+            float2 o;
+            o.x = rs * (t.x - m1 - xh.x * m2);
+            o.y = rs * (t.y - m1 - xh.y * m2);
+            const size_t off = base + (size_t)r * C + c;
+            if (accumulate) {
+                const float2 p = Vec2<TD>::ld(dx + off);
+                o.x += p.x;
+                o.y += p.y;
+            }
+            Vec2<TD>::st(dx + off, o);
+        }
+    }
+}
+
 // ---- LayerNorm: one warp per row ------------------------------------------------------------------------
 constexpr int kLnMaxPairsPerLane = 32;  // C <= 2048
 
@@ -381,11 +560,34 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
-    const int rpb = gn_rows_per_block(HW, N);
-    dim3 grid(ceil_div(HW, rpb), N);
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * N * G + 1), st));   // sums + the grid arrival counter
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
+    {
+        // fused single-kernel path: all CTAs co-resident (<= 1 per SM) and each CTA's rows fit in shared memory
+        const int sms = device_sm_count();
+        const int nb = sms / N;
+        const int xes = x_dtype == CB_F32 ? 4 : 2;
+        if (nb >= 1) {
+            const int rpbf = ceil_div(HW, nb);
+            const size_t smem = (size_t)rpbf * C * xes;
+            if (smem <= 200 * 1024) {
+                dim3 gridf(ceil_div(HW, rpbf), N);
+                unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * N * G);
+                CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
+                    auto kern = gn_fused_fwd_kernel<TX, TY>;
+                    static size_t max_set = 0;
+                    if (smem > max_set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); max_set = 200 * 1024; }
+                    CB_LAUNCH((kern), gridf, nthr, smem, st, (const TX*)x, (TY*)y, gamma, beta, ws, counter, mean_out, rstd_out, HW, C, G, eps, act_silu, rpbf, gs.pw, gs.ry, gs.chunks);
+                }));
+                CB_CUDA(cudaGetLastError());
+                cb::count_launches(1);
+                return 0;
+            }
+        }
+    }
+    const int rpb = gn_rows_per_block(HW, N);
+    dim3 grid(ceil_div(HW, rpb), N);
     CB_DISPATCH_2(x_dtype, TX,CB_LAUNCH((gn_stats_kernel<TX>), grid, nthr, 0, st, (const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY,
 CB_LAUNCH((gn_apply_kernel<TX, TY>), grid, nthr, 0, st, (const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
@@ -400,11 +602,36 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
-    const int rpb = gn_rows_per_block(HW, N);
-    dim3 grid(ceil_div(HW, rpb), N);
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * N * G + 1), st));
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
+    CB_REQUIRE(dx_dtype == CB_F32 || dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
+    {
+        const int sms = device_sm_count();
+        const int nb = sms / N;
+        if (nb >= 1) {
+            const int rpbf = ceil_div(HW, nb);
+            const size_t smem = (size_t)rpbf * C * 8;      // xhat + t, fp32 each
+            if (smem <= 200 * 1024) {
+                dim3 gridf(ceil_div(HW, rpbf), N);
+                unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * N * G);
+#define CB_GN_BWD_FUSED(TDX)                                                                                                      \
+                CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG, {                                                              \
+                    auto kern = gn_fused_bwd_kernel<TX, TG, TDX>;                                                                     \
+                    static bool set = false;                                                                                         \
+                    if (!set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
+                    CB_LAUNCH((kern), gridf, nthr, smem, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, counter, (TDX*)dx, HW, C, G, act_silu, accumulate, rpbf, gs.pw, gs.ry, gs.chunks); \
+                }))
+                if (dx_dtype == CB_F32) { CB_GN_BWD_FUSED(float); } else { CB_GN_BWD_FUSED(TG); }
+#undef CB_GN_BWD_FUSED
+                CB_CUDA(cudaGetLastError());
+                cb::count_launches(1);
+                return 0;
+            }
+        }
+    }
+    const int rpb = gn_rows_per_block(HW, N);
+    dim3 grid(ceil_div(HW, rpb), N);
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
 CB_LAUNCH((gn_bwd_stats_kernel<TX, TG>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, HW, C, G, act_silu, rpb, gs.pw, gs.ry, gs.chunks)));
     // dx dtype: f32 or the gradient dtype

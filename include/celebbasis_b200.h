@@ -142,7 +142,7 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------
- * Normalisation (channels-last).  ws = caller workspace of 2*N*G doubles.
+ * Normalisation (channels-last).  ws = caller workspace of 2*N*G+1 doubles (group sums + a grid arrival counter).
  * cb_groupnorm_*: ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32, eps 1e-5),
  *   ldm/modules/attention.py:76-77 and ldm/modules/diffusionmodules/model.py:38-39 (Normalize, eps 1e-6),
  *   optionally fused with the nn.SiLU that follows (openaimodel.py:201-241, model.py:33-35 nonlinearity).
