@@ -261,6 +261,29 @@ __device__ __forceinline__ void grid_arrive_and_wait(unsigned* counter, unsigned
     __syncthreads();
 }
 
+// Cross-CTA reduction without same-address atomics (which serialise in L2): every CTA publishes its per-group partial
+// sums to its own slot part[(n*nb + block)*G + g]; after the grid barrier each CTA folds the nb partials of its image.
+__device__ __forceinline__ void publish_partials(float2* __restrict__ part, const float* s_a, const float* s_b, int G) {
+    if (threadIdx.x < G)
+        part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * G + threadIdx.x] = make_float2(s_a[threadIdx.x], s_b[threadIdx.x]);
+}
+__device__ __forceinline__ void fold_partials(const float2* __restrict__ part, double* s_d0, double* s_d1, int G) {
+    if (threadIdx.x < 64) { s_d0[threadIdx.x] = 0.0; s_d1[threadIdx.x] = 0.0; }
+    __syncthreads();
+    const int g = threadIdx.x % G, slice = threadIdx.x / G, nslices = blockDim.x / G;
+    if (slice < nslices) {
+        double a = 0.0, b = 0.0;
+        for (int blk = slice; blk < (int)gridDim.x; blk += nslices) {
+            const float2 v = __ldcg(&part[((size_t)blockIdx.y * gridDim.x + blk) * G + g]);
+            a += v.x;
+            b += v.y;
+        }
+        atomicAdd(&s_d0[g], a);
+        atomicAdd(&s_d1[g], b);
+    }
+    __syncthreads();
+}
+
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(kGnThreads)
 gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
@@ -305,15 +328,15 @@ gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* _
         }
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_a[threadIdx.x]);
-        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_b[threadIdx.x]);
-    }
+    __shared__ double s_d0[64], s_d1[64];
+    float2* part = reinterpret_cast<float2*>(ws);
+    publish_partials(part, s_a, s_b, G);
     grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
+    fold_partials(part, s_d0, s_d1, G);
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
-        const double m = __ldcg(&ws[((size_t)n * G + threadIdx.x) * 2]) / cnt;
-        double var = __ldcg(&ws[((size_t)n * G + threadIdx.x) * 2 + 1]) / cnt - m * m;
+        const double m = s_d0[threadIdx.x] / cnt;
+        double var = s_d1[threadIdx.x] / cnt - m * m;
         if (var < 0) var = 0;
         const float rs = (float)(1.0 / sqrt(var + (double)eps));
         s_a[threadIdx.x] = (float)m;
@@ -389,15 +412,15 @@ gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
         atomicAdd(&s_2[g], a2);
     }
     __syncthreads();
-    if (threadIdx.x < G) {
-        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_1[threadIdx.x]);
-        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_2[threadIdx.x]);
-    }
+    __shared__ double s_d0[64], s_d1[64];
+    float2* part = reinterpret_cast<float2*>(ws);
+    publish_partials(part, s_1, s_2, G);
     grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
+    fold_partials(part, s_d0, s_d1, G);
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
-        s_1[threadIdx.x] = (float)(__ldcg(&ws[((size_t)n * G + threadIdx.x) * 2]) / cnt);
-        s_2[threadIdx.x] = (float)(__ldcg(&ws[((size_t)n * G + threadIdx.x) * 2 + 1]) / cnt);
+        s_1[threadIdx.x] = (float)(s_d0[threadIdx.x] / cnt);
+        s_2[threadIdx.x] = (float)(s_d1[threadIdx.x] / cnt);
     }
     __syncthreads();
     for (int j = 0; j < chunks; ++j) {
@@ -560,7 +583,9 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * N * G + 1), st));   // sums + the grid arrival counter
+    // ws: CB_GN_WS_BYTES; [0, 2*N*G doubles) group sums of the two-kernel path, or per-CTA partial slots of the fused
+    // path; the last 8 bytes hold the grid arrival counter
+    unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + CB_GN_WS_BYTES - 8);
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
     {
@@ -573,7 +598,8 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
             const size_t smem = (size_t)rpbf * C * xes;
             if (smem <= 200 * 1024) {
                 dim3 gridf(ceil_div(HW, rpbf), N);
-                unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * N * G);
+                CB_REQUIRE((size_t)gridf.x * N * G * 8 <= CB_GN_WS_BYTES - 8, CB_ERR_ARG, "groupnorm: workspace too small");
+                CB_CUDA(cudaMemsetAsync(counter, 0, 8, st));
                 CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
                     auto kern = gn_fused_fwd_kernel<TX, TY>;
                     static size_t max_set = 0;
@@ -586,6 +612,7 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
             }
         }
     }
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
     const int rpb = gn_rows_per_block(HW, N);
     dim3 grid(ceil_div(HW, rpb), N);
     CB_DISPATCH_2(x_dtype, TX,CB_LAUNCH((gn_stats_kernel<TX>), grid, nthr, 0, st, (const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));
@@ -602,7 +629,7 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * N * G + 1), st));
+    unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + CB_GN_WS_BYTES - 8);
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
     CB_REQUIRE(dx_dtype == CB_F32 || dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
@@ -614,7 +641,8 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
             const size_t smem = (size_t)rpbf * C * 8;      // xhat + t, fp32 each
             if (smem <= 200 * 1024) {
                 dim3 gridf(ceil_div(HW, rpbf), N);
-                unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * N * G);
+                CB_REQUIRE((size_t)gridf.x * N * G * 8 <= CB_GN_WS_BYTES - 8, CB_ERR_ARG, "groupnorm: workspace too small");
+                CB_CUDA(cudaMemsetAsync(counter, 0, 8, st));
 #define CB_GN_BWD_FUSED(TDX)                                                                                                      \
                 CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG, {                                                              \
                     auto kern = gn_fused_bwd_kernel<TX, TG, TDX>;                                                                     \
@@ -630,6 +658,7 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
             }
         }
     }
+    CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
     const int rpb = gn_rows_per_block(HW, N);
     dim3 grid(ceil_div(HW, rpb), N);
     CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,

@@ -226,6 +226,16 @@ class NormStats:
 
 
 _ws_cache = {}
+CB_GN_WS_BYTES = 131072
+
+
+def _gn_workspace(device):
+    """One GroupNorm workspace per device (calls are stream-ordered)."""
+    ws = _ws_cache.get(("gn", device))
+    if ws is None:
+        ws = torch.zeros(CB_GN_WS_BYTES // 8, dtype=torch.float64, device=device)
+        _ws_cache[("gn", device)] = ws
+    return ws
 
 
 def _gn_ws(device, n):
@@ -242,7 +252,7 @@ def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     mean = torch.empty(geo.n * groups, dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
-    ws = torch.empty(2 * geo.n * groups + 1, dtype=torch.float64, device=x.device)
+    ws = _gn_workspace(x.device)
     _lib.check(_L().cb_groupnorm_fwd(_p(x), _dt(x), _p(y), _dt(y), _p(gamma), _p(beta), geo.n, geo.hw, C, groups,
                                      eps, 1 if silu else 0, _p(mean), _p(rstd), _p(ws), _st()), "cb_groupnorm_fwd")
     return y, NormStats(mean, rstd)
@@ -254,7 +264,7 @@ def groupnorm_bwd(dy, x, geo, gamma, beta, stats, *, groups=32, silu=False, dx=N
     if dx is None:
         dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
         accumulate = False
-    ws = torch.empty(2 * geo.n * groups + 1, dtype=torch.float64, device=x.device)
+    ws = _gn_workspace(x.device)
     _lib.check(_L().cb_groupnorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(beta), _p(stats.mean),
                                      _p(stats.rstd), _p(dx), _dt(dx), geo.n, geo.hw, C, groups, 1 if silu else 0,
                                      1 if accumulate else 0, _p(ws), _st()), "cb_groupnorm_bwd")

@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 #define CB_ABI_VERSION 1
+#define CB_GN_WS_BYTES 131072
 
 /* element types */
 enum { CB_F16 = 0, CB_BF16 = 1, CB_F32 = 2 };
@@ -142,7 +143,8 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------
- * Normalisation (channels-last).  ws = caller workspace of 2*N*G+1 doubles (group sums + a grid arrival counter).
+ * Normalisation (channels-last).  ws = caller workspace of CB_GN_WS_BYTES bytes (group sums or per-CTA partial
+ * slots, plus a grid arrival counter in its last 8 bytes); calls sharing it must be stream-ordered.
  * cb_groupnorm_*: ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32, eps 1e-5),
  *   ldm/modules/attention.py:76-77 and ldm/modules/diffusionmodules/model.py:38-39 (Normalize, eps 1e-6),
  *   optionally fused with the nn.SiLU that follows (openaimodel.py:201-241, model.py:33-35 nonlinearity).
