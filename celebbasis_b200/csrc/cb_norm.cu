@@ -34,11 +34,37 @@ template <> struct Vec2<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ float silu_grad(float z) {
-    const float s = 1.0f / (1.0f + __expf(-z));
+    const float s = __fdividef(1.0f, 1.0f + __expf(-z));
     return s * (1.0f + z * (1.0f - s));
 }
 
+// Per-group accumulation into shared memory.  Float atomics on shared memory are compare-and-swap loops, so letting
+// every lane hit the (few) group addresses serialises the whole CTA: lanes of a warp that hold the same group (a
+// contiguous run, since channel pairs are lane-consecutive) first add up with shuffles and only the run's first lane
+// issues the atomic.  Must be called by all live lanes of the warp (uniform control flow).
+__device__ __forceinline__ void group_accumulate(float* s_a, float* s_b, int g, float v1, float v2) {
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, g);
+    const int lane = threadIdx.x & 31;
+    const int first = __ffs(peers) - 1, last = 31 - __clz(peers);
+    const unsigned run = peers >> first;
+    const bool contiguous = (run & (run + 1)) == 0;
+    if (__all_sync(act, contiguous)) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float t1 = __shfl_down_sync(act, v1, off);
+            const float t2 = __shfl_down_sync(act, v2, off);
+            if (lane + off <= last) { v1 += t1; v2 += t2; }
+        }
+        if (lane == first) { atomicAdd(&s_a[g], v1); atomicAdd(&s_b[g], v2); }
+    } else {
+        atomicAdd(&s_a[g], v1);
+        atomicAdd(&s_b[g], v2);
+    }
+}
+
 constexpr int kGnThreads = 256;           // upper bound; the launch uses PW*RY threads (see gn_shape)
+constexpr int kGnFusedThreads = 1024;     // fused kernels: one CTA per SM, so fill it (PW x up-to-1024/PW row lanes)
 constexpr int kGnMaxChunks = 8;           // channel-pair chunks per thread: C <= 2*PW*8
 
 // Thread mapping shared by the four GroupNorm kernels: a block is a (RY x PW) grid of threads; tx owns channel
@@ -90,8 +116,7 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C
     for (int j = 0; j < kGnMaxChunks; ++j) {
         if (j < chunks) {
             const int g = (2 * (tx + j * PW)) / cpg;
-            atomicAdd(&s_sum[g], a1[j]);
-            atomicAdd(&s_sq[g], a2[j]);
+            group_accumulate(s_sum, s_sq, g, a1[j], a2[j]);
         }
     }
     __syncthreads();
@@ -185,8 +210,7 @@ gn_bwd_stats_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
             a1 += t0 + t1;
             a2 += t0 * xh0 + t1 * xh1;
         }
-        atomicAdd(&s_1[g], a1);
-        atomicAdd(&s_2[g], a2);
+        group_accumulate(s_1, s_2, g, a1, a2);
     }
     __syncthreads();
     if (threadIdx.x < G) {
@@ -250,70 +274,113 @@ gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
 // into shared memory while accumulating the group sums, publishes them with fp64 atomics, waits on a grid-wide
 // arrival counter, then normalises straight out of shared memory.  x is read from HBM/L2 once instead of twice and
 // the statistics + apply passes are one launch.
+// counter[0] = arrivals, counter[1] = departures.  Arrival is a fire-and-forget red.add and the wait is a plain poll,
+// so the critical path after the last arrival is one L2 round trip.  Every CTA also counts its departure; the last one
+// to leave (off the critical path) clears both words, so the pair is reusable by the next call without a memset node
+// (the workspace is zeroed once by its owner).  Requires all CTAs of the grid to be co-resident.
 __device__ __forceinline__ void grid_arrive_and_wait(unsigned* counter, unsigned expected) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(counter, 1u);
-        while (*reinterpret_cast<volatile unsigned*>(counter) < expected) { __nanosleep(64); }
-        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < expected);
     }
     __syncthreads();
 }
+__device__ __forceinline__ void grid_depart(unsigned* counter, unsigned expected) {
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter + 1, 1u) == expected - 1) {
+            counter[0] = 0;
+            counter[1] = 0;
+        }
+    }
+}
 
 // Cross-CTA reduction without same-address atomics (which serialise in L2): every CTA publishes its per-group partial
-// sums to its own slot part[(n*nb + block)*G + g]; after the grid barrier each CTA folds the nb partials of its image.
+// sums to its own slot part[(n*nb + block)*G + g]; after the grid barrier each CTA folds the nb partials of its image
+// (kFoldSlices x G threads, each with a handful of independent L2 loads in flight, then one pass over shared memory).
+constexpr int kFoldSlices = 16;
 __device__ __forceinline__ void publish_partials(float2* __restrict__ part, const float* s_a, const float* s_b, int G) {
     if (threadIdx.x < G)
         part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * G + threadIdx.x] = make_float2(s_a[threadIdx.x], s_b[threadIdx.x]);
 }
-__device__ __forceinline__ void fold_partials(const float2* __restrict__ part, double* s_d0, double* s_d1, int G) {
-    if (threadIdx.x < 64) { s_d0[threadIdx.x] = 0.0; s_d1[threadIdx.x] = 0.0; }
-    __syncthreads();
-    const int g = threadIdx.x % G, slice = threadIdx.x / G, nslices = blockDim.x / G;
+__device__ __forceinline__ void fold_partials(const float2* __restrict__ part, double2 (*s_fold)[64], double* s_d0,
+                                              double* s_d1, int G) {
+    const int g = threadIdx.x % G, slice = threadIdx.x / G;
+    const int nslices = min(kFoldSlices, (int)blockDim.x / G);
+    const int nb = gridDim.x;
     if (slice < nslices) {
         double a = 0.0, b = 0.0;
-        for (int blk = slice; blk < (int)gridDim.x; blk += nslices) {
-            const float2 v = __ldcg(&part[((size_t)blockIdx.y * gridDim.x + blk) * G + g]);
-            a += v.x;
-            b += v.y;
+        const float2* pp = part + (size_t)blockIdx.y * nb * G + g;
+        for (int blk = slice; blk < nb; blk += 4 * nslices) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int bi = blk + u * nslices;
+                v[u] = bi < nb ? __ldcg(pp + (size_t)bi * G) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a += v[u].x; b += v[u].y; }
         }
-        atomicAdd(&s_d0[g], a);
-        atomicAdd(&s_d1[g], b);
+        s_fold[slice][g] = make_double2(a, b);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nslices; ++i) { a += s_fold[i][threadIdx.x].x; b += s_fold[i][threadIdx.x].y; }
+        s_d0[threadIdx.x] = a;
+        s_d1[threadIdx.x] = b;
     }
     __syncthreads();
 }
 
+// The CTA's rows are one contiguous range of the [HW][C] matrix: a single cp.async.bulk (TMA, 1-D) stages them in
+// shared memory -- the whole range is in flight at once instead of two 8-byte loads per thread.
 template <typename TX, typename TY>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnFusedThreads)
 gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
                     const float* __restrict__ beta, double* __restrict__ ws, unsigned* __restrict__ counter,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act,
                     int rows_per_block, int PW, int RY, int chunks) {
-    pdl_sync();
-    extern __shared__ __align__(16) unsigned char gn_smem[];
+    extern __shared__ __align__(128) unsigned char gn_smem[];
     TX* sx = reinterpret_cast<TX*>(gn_smem);
     __shared__ float s_a[64], s_b[64];
+    __shared__ double s_d0[64], s_d1[64];
+    __shared__ double2 s_fold[kFoldSlices][64];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
     const int cpg = C / G;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
     if (threadIdx.x < 64) { s_a[threadIdx.x] = 0.f; s_b[threadIdx.x] = 0.f; }
     __syncthreads();
+    pdl_sync();
+    if (threadIdx.x == 0 && r1 > r0) {
+        const uint32_t bytes = (uint32_t)((size_t)(r1 - r0) * C * sizeof(TX));
+        mbar_arrive_expect_tx(bar, bytes);
+        tma_bulk_g2s(smem_u32(sx), x + ((size_t)n * HW + r0) * C, bytes, bar);
+    }
+    if (r1 > r0) mbar_wait(bar, 0);
     float a1[kGnMaxChunks], a2[kGnMaxChunks];
 #pragma unroll
     for (int j = 0; j < kGnMaxChunks; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
-    const TX* xb = x + ((size_t)n * HW) * C + 2 * tx;
-#pragma unroll 2
+#pragma unroll 4
     for (int r = r0 + ty; r < r1; r += RY) {
-        const TX* xr = xb + (size_t)r * C;
-        TX* sr = sx + (size_t)(r - r0) * C + 2 * tx;
+        const TX* sr = sx + (size_t)(r - r0) * C + 2 * tx;
 #pragma unroll
         for (int j = 0; j < kGnMaxChunks; ++j) {
             if (j < chunks) {
-                const float2 v = Vec2<TX>::ld(xr + 2 * j * PW);
-                Vec2<TX>::st(sr + 2 * j * PW, v);
+                const float2 v = Vec2<TX>::ld(sr + 2 * j * PW);
                 a1[j] += v.x + v.y;
                 a2[j] += v.x * v.x + v.y * v.y;
             }
@@ -323,16 +390,15 @@ gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* _
     for (int j = 0; j < kGnMaxChunks; ++j) {
         if (j < chunks) {
             const int g = (2 * (tx + j * PW)) / cpg;
-            atomicAdd(&s_a[g], a1[j]);
-            atomicAdd(&s_b[g], a2[j]);
+            group_accumulate(s_a, s_b, g, a1[j], a2[j]);
         }
     }
     __syncthreads();
-    __shared__ double s_d0[64], s_d1[64];
     float2* part = reinterpret_cast<float2*>(ws);
     publish_partials(part, s_a, s_b, G);
     grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
-    fold_partials(part, s_d0, s_d1, G);
+    fold_partials(part, s_fold, s_d0, s_d1, G);
+    grid_depart(counter, gridDim.x * gridDim.y);
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
         const double m = s_d0[threadIdx.x] / cnt;
@@ -366,57 +432,69 @@ gn_fused_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* _
 }
 
 template <typename TX, typename TG, typename TD>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnFusedThreads)
 gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                     double* __restrict__ ws, unsigned* __restrict__ counter, TD* __restrict__ dx, int HW, int C, int G,
                     int act, int accumulate, int rows_per_block, int PW, int RY, int chunks) {
-    pdl_sync();
-    // shared memory caches, per element, xhat (fp32) and t = dz*gamma (fp32) of this CTA's rows
-    extern __shared__ __align__(16) unsigned char gn_smem[];
-    float* sxh = reinterpret_cast<float*>(gn_smem);
-    float* st = sxh + (size_t)rows_per_block * C;
+    // shared memory stages this CTA's rows of x and dy (two bulk copies); xhat / dz*gamma are recomputed from them
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    TX* sx = reinterpret_cast<TX*>(gn_smem);
+    TG* sdy = reinterpret_cast<TG*>(gn_smem + (((size_t)rows_per_block * C * sizeof(TX) + 127) & ~(size_t)127));
     __shared__ float s_1[64], s_2[64];
+    __shared__ double s_d0[64], s_d1[64];
+    __shared__ double2 s_fold[kFoldSlices][64];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int n = blockIdx.y;
     const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
     const int cpg = C / G;
-    if (threadIdx.x < 64) { s_1[threadIdx.x] = 0.f; s_2[threadIdx.x] = 0.f; }
-    __syncthreads();
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(HW, r0 + rows_per_block);
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (threadIdx.x < 64) { s_1[threadIdx.x] = 0.f; s_2[threadIdx.x] = 0.f; }
+    __syncthreads();
+    pdl_sync();
     const size_t base = ((size_t)n * HW) * C;
+    if (threadIdx.x == 0 && r1 > r0) {
+        const uint32_t bx = (uint32_t)((size_t)(r1 - r0) * C * sizeof(TX)), bd = (uint32_t)((size_t)(r1 - r0) * C * sizeof(TG));
+        mbar_arrive_expect_tx(bar, bx + bd);
+        tma_bulk_g2s(smem_u32(sx), x + base + (size_t)r0 * C, bx, bar);
+        tma_bulk_g2s(smem_u32(sdy), dy + base + (size_t)r0 * C, bd, bar);
+    }
+    if (r1 > r0) mbar_wait(bar, 0);
     for (int j = 0; j < chunks; ++j) {
         const int c = 2 * (tx + j * PW);
         const int g = c / cpg;
         const float m = mean[n * G + g], rs = rstd[n * G + g];
         const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
         float a1 = 0.f, a2 = 0.f;
-#pragma unroll 2
+#pragma unroll 4
         for (int r = r0 + ty; r < r1; r += RY) {
-            const size_t off = base + (size_t)r * C + c;
-            const float2 xv = Vec2<TX>::ld(x + off);
-            float2 d = Vec2<TG>::ld(dy + off);
+            const size_t so = (size_t)(r - r0) * C + c;
+            const float2 xv = Vec2<TX>::ld(sx + so);
+            float2 d = Vec2<TG>::ld(sdy + so);
             const float xh0 = (xv.x - m) * rs, xh1 = (xv.y - m) * rs;
             if (act) {
                 d.x *= silu_grad(xh0 * ga0 + be0);
                 d.y *= silu_grad(xh1 * ga1 + be1);
             }
             const float t0 = d.x * ga0, t1 = d.y * ga1;
-            const size_t so = (size_t)(r - r0) * C + c;
-            *reinterpret_cast<float2*>(sxh + so) = make_float2(xh0, xh1);
-            *reinterpret_cast<float2*>(st + so) = make_float2(t0, t1);
             a1 += t0 + t1;
             a2 += t0 * xh0 + t1 * xh1;
         }
-        atomicAdd(&s_1[g], a1);
-        atomicAdd(&s_2[g], a2);
+        group_accumulate(s_1, s_2, g, a1, a2);
     }
     __syncthreads();
-    __shared__ double s_d0[64], s_d1[64];
     float2* part = reinterpret_cast<float2*>(ws);
     publish_partials(part, s_1, s_2, G);
     grid_arrive_and_wait(counter, gridDim.x * gridDim.y);
-    fold_partials(part, s_d0, s_d1, G);
+    fold_partials(part, s_fold, s_d0, s_d1, G);
+    grid_depart(counter, gridDim.x * gridDim.y);
     if (threadIdx.x < G) {
         const double cnt = (double)HW * cpg;
         s_1[threadIdx.x] = (float)(s_d0[threadIdx.x] / cnt);
@@ -426,16 +504,22 @@ gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
     for (int j = 0; j < chunks; ++j) {
         const int c = 2 * (tx + j * PW);
         const int g = c / cpg;
-        const float rs = rstd[n * G + g];
+        const float m = mean[n * G + g], rs = rstd[n * G + g];
+        const float ga0 = gamma[c], ga1 = gamma[c + 1], be0 = beta[c], be1 = beta[c + 1];
         const float m1 = s_1[g], m2 = s_2[g];
 #pragma unroll 4
         for (int r = r0 + ty; r < r1; r += RY) {
             const size_t so = (size_t)(r - r0) * C + c;
-            const float2 xh = *reinterpret_cast<const float2*>(sxh + so);
-            const float2 t = *reinterpret_cast<const float2*>(st + so);
+            const float2 xv = Vec2<TX>::ld(sx + so);
+            float2 d = Vec2<TG>::ld(sdy + so);
+            const float xh0 = (xv.x - m) * rs, xh1 = (xv.y - m) * rs;
+            if (act) {
+                d.x *= silu_grad(xh0 * ga0 + be0);
+                d.y *= silu_grad(xh1 * ga1 + be1);
+            }
             float2 o;
-            o.x = rs * (t.x - m1 - xh.x * m2);
-            o.y = rs * (t.y - m1 - xh.y * m2);
+            o.x = rs * (d.x * ga0 - m1 - xh0 * m2);
+            o.y = rs * (d.y * ga1 - m1 - xh1 * m2);
             const size_t off = base + (size_t)r * C + c;
             if (accumulate) {
                 const float2 p = Vec2<TD>::ld(dx + off);
@@ -596,15 +680,15 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
         if (nb >= 1) {
             const int rpbf = ceil_div(HW, nb);
             const size_t smem = (size_t)rpbf * C * xes;
-            if (smem <= 200 * 1024) {
+            if (smem <= 200 * 1024 && ((size_t)C * xes) % 16 == 0) {
                 dim3 gridf(ceil_div(HW, rpbf), N);
                 CB_REQUIRE((size_t)gridf.x * N * G * 8 <= CB_GN_WS_BYTES - 8, CB_ERR_ARG, "groupnorm: workspace too small");
-                CB_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+                const int ryf = std::max(1, std::min(rpbf, kGnFusedThreads / gs.pw));
                 CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
                     auto kern = gn_fused_fwd_kernel<TX, TY>;
                     static size_t max_set = 0;
                     if (smem > max_set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); max_set = 200 * 1024; }
-                    CB_LAUNCH((kern), gridf, nthr, smem, st, (const TX*)x, (TY*)y, gamma, beta, ws, counter, mean_out, rstd_out, HW, C, G, eps, act_silu, rpbf, gs.pw, gs.ry, gs.chunks);
+                    CB_LAUNCH((kern), gridf, gs.pw * ryf, smem, st, (const TX*)x, (TY*)y, gamma, beta, ws, counter, mean_out, rstd_out, HW, C, G, eps, act_silu, rpbf, gs.pw, ryf, gs.chunks);
                 }));
                 CB_CUDA(cudaGetLastError());
                 cb::count_launches(1);
@@ -638,17 +722,18 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
         const int nb = sms / N;
         if (nb >= 1) {
             const int rpbf = ceil_div(HW, nb);
-            const size_t smem = (size_t)rpbf * C * 8;      // xhat + t, fp32 each
-            if (smem <= 200 * 1024) {
+            const int xes = x_dtype == CB_F32 ? 4 : 2, ges = dy_dtype == CB_F32 ? 4 : 2;
+            const size_t smem = (((size_t)rpbf * C * xes + 127) & ~(size_t)127) + (size_t)rpbf * C * ges;   // staged x + dy
+            if (smem <= 200 * 1024 && ((size_t)C * xes) % 16 == 0 && ((size_t)C * ges) % 16 == 0) {
                 dim3 gridf(ceil_div(HW, rpbf), N);
                 CB_REQUIRE((size_t)gridf.x * N * G * 8 <= CB_GN_WS_BYTES - 8, CB_ERR_ARG, "groupnorm: workspace too small");
-                CB_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+                const int ryf = std::max(1, std::min(rpbf, kGnFusedThreads / gs.pw));
 #define CB_GN_BWD_FUSED(TDX)                                                                                                      \
                 CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG, {                                                              \
                     auto kern = gn_fused_bwd_kernel<TX, TG, TDX>;                                                                     \
                     static bool set = false;                                                                                         \
                     if (!set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
-                    CB_LAUNCH((kern), gridf, nthr, smem, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, counter, (TDX*)dx, HW, C, G, act_silu, accumulate, rpbf, gs.pw, gs.ry, gs.chunks); \
+                    CB_LAUNCH((kern), gridf, gs.pw * ryf, smem, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, counter, (TDX*)dx, HW, C, G, act_silu, accumulate, rpbf, gs.pw, ryf, gs.chunks); \
                 }))
                 if (dx_dtype == CB_F32) { CB_GN_BWD_FUSED(float); } else { CB_GN_BWD_FUSED(TG); }
 #undef CB_GN_BWD_FUSED

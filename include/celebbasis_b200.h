@@ -144,7 +144,8 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Normalisation (channels-last).  ws = caller workspace of CB_GN_WS_BYTES bytes (group sums or per-CTA partial
- * slots, plus a grid arrival counter in its last 8 bytes); calls sharing it must be stream-ordered.
+ * slots, plus a self-resetting grid arrival counter in its last 8 bytes); the caller zeroes it ONCE at allocation;
+ * calls sharing it must be stream-ordered.
  * cb_groupnorm_*: ldm/modules/diffusionmodules/util.py:199-216 (GroupNorm32, eps 1e-5),
  *   ldm/modules/attention.py:76-77 and ldm/modules/diffusionmodules/model.py:38-39 (Normalize, eps 1e-6),
  *   optionally fused with the nn.SiLU that follows (openaimodel.py:201-241, model.py:33-35 nonlinearity).
