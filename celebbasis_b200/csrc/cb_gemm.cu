@@ -150,9 +150,46 @@ __device__ __forceinline__ void store_any(void* base, int dtype, long long idx, 
 
 // Epilogue for 8 consecutive columns of one output row (one thread).  Kept deliberately small: the epilogue runs once
 // per CTA, so its cost is dominated by cold instruction fetch (~300 cycles per 128 B line of straight-line code).
+// Residual values of one 32-column chunk of this thread's row, fetched as raw 16-byte words BEFORE the accumulator is
+// needed (the loads are in flight while the MMAs / the previous chunk's stores run; D may alias R, so the compiler could
+// never hoist them itself).
+struct ResidualChunk { uint4 v[8]; };
+__device__ __forceinline__ void residual_prefetch(const GemmParams& p, long long ridx, ResidualChunk& rc) {
+    if (p.r_dtype == CB_F32) {
+        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.R) + ridx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rc.v[j] = s[j];
+    } else {
+        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + ridx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rc.v[j] = s[j];
+    }
+}
+__device__ __forceinline__ void residual_unpack8(const GemmParams& p, const ResidualChunk& rc, int g, float (&r)[8]) {
+    if (p.r_dtype == CB_F32) {
+        const uint4 a = rc.v[2 * g], b = rc.v[2 * g + 1];
+        r[0] = __uint_as_float(a.x); r[1] = __uint_as_float(a.y); r[2] = __uint_as_float(a.z); r[3] = __uint_as_float(a.w);
+        r[4] = __uint_as_float(b.x); r[5] = __uint_as_float(b.y); r[6] = __uint_as_float(b.z); r[7] = __uint_as_float(b.w);
+    } else {
+        const uint4 a = rc.v[g];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 t;
+            if (p.r_dtype == CB_F16) t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            else t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            r[2 * j] = t.x; r[2 * j + 1] = t.y;
+        }
+    }
+}
+
 __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[8], long long grow, long long brow, int col,
-                                             long long d_off, long long r_off, int ncols) {
-    if (p.bias) {
+                                             long long d_off, long long r_off, int ncols, const float* rpre = nullptr,
+                                             const float* sbias = nullptr) {
+    if (sbias) {       // this tile's bias row, staged in shared memory before the accumulator was ready
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += sbias[j];
+    } else if (p.bias) {
         if (ncols == 8) {
             float b[8];
             load8<float>(p.bias + brow * p.ldbias + col, b);
@@ -167,7 +204,10 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
         for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
     }
     if (ncols == 8 && p.vec_ok && !p.d_transposed) {
-        if (p.R) {
+        if (rpre) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += rpre[j];
+        } else if (p.R) {
             float r[8];
             const long long ridx = r_off + grow * p.ldr + col;
             if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
@@ -341,10 +381,26 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
         const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
         const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
+        const int ncols_tile = min(BN, p.N - n0);
+        // bias row of this tile -> shared memory while the MMAs run (global bias loads in the store loop would each
+        // wait a full L2 round trip behind the previous chunk's stores)
+        __shared__ __align__(16) float s_bias[BN + 8];
+        const float* sb = nullptr;
+        if (p.bias) {
+            const long long tile_row0 = p.conv ? (((long long)img0 * p.out_h + oh0) * p.out_w + ow0) : (long long)m0;
+            const long long brow0 = p.bias_row_div > 0 ? tile_row0 / p.bias_row_div : 0;
+            for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = i < ncols_tile ? p.bias[brow0 * p.ldbias + n0 + i] : 0.f;
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (brow == brow0) sb = s_bias;
+        }
+        // residual fast path: whole 32-column chunks, 16-byte aligned rows
+        const bool r_fast = p.R && p.vec_ok && !p.d_transposed && row_valid;
+        const long long r_row = r_off + grow * p.ldr + n0;
+        ResidualChunk rc_cur, rc_next;
+        if (r_fast && p.splits == 1 && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);   // in flight during the MMAs
         if (p.dbg_mode != 1) mbar_wait(tmem_full_bar, 0);
         if (dbg && threadIdx.x == 64) dbg[4] = clock64();
         tc_fence_after();
-        const int ncols_tile = min(BN, p.N - n0);
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (p.dbg_mode == 1 || p.dbg_mode == 2) {
         } else if (p.splits == 1) {
@@ -352,6 +408,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c * 32 < ncols_tile; ++c) {
                 uint32_t acc[32];
                 tmem_ld_32x32(trow + c * 32, acc);      // one TMEM round trip per 32 columns
+                const bool pre = r_fast && ncols_tile - c * 32 >= 32;
+                if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
                 tmem_ld_wait();
                 if (row_valid) {
 #pragma unroll
@@ -361,10 +419,17 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
-                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc);
+                            if (pre) {
+                                float r8[8];
+                                residual_unpack8(p, rc_cur, g, r8);
+                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, r8, sb ? sb + c * 32 + g * 8 : nullptr);
+                            } else {
+                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                            }
                         }
                     }
                 }
+                rc_cur = rc_next;
             }
         } else {
             // ---- split-K: every CTA adds its fp32 partial tile into one L2-resident accumulator tile with vector
@@ -402,6 +467,8 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float4 v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + c * 32 + j * 4));   // 8 loads in flight
+                        const bool pre = r_fast && ncols_tile - c * 32 >= 32;
+                        if (pre) residual_prefetch(p, r_row + c * 32, rc_cur);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) __stcg(reinterpret_cast<float4*>(mine + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));
 #pragma unroll
@@ -410,7 +477,13 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (nc > 0) {
                                 float f[8] = {v[2 * g].x * p.alpha, v[2 * g].y * p.alpha, v[2 * g].z * p.alpha, v[2 * g].w * p.alpha,
                                               v[2 * g + 1].x * p.alpha, v[2 * g + 1].y * p.alpha, v[2 * g + 1].z * p.alpha, v[2 * g + 1].w * p.alpha};
-                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc);
+                                if (pre) {
+                                    float r8[8];
+                                    residual_unpack8(p, rc_cur, g, r8);
+                                    epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, r8, sb ? sb + c * 32 + g * 8 : nullptr);
+                                } else {
+                                    epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                                }
                             }
                         }
                     }

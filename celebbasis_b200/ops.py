@@ -36,20 +36,37 @@ GEMM_RECORD = None   # when set to a list, every cb_gemm launch appends (bytes(G
 
 SPLITK_WS_BYTES = 96 << 20
 _splitk_ws = {}
+_LANE = 0     # launches that share a workspace must be stream-ordered: a concurrent branch runs under `with lane(1)`
+
+
+class lane:
+    """Select the workspace set (split-K accumulators, GroupNorm slots) used by launches inside the block.  The two
+    independent branches of the step (VAE encode | face net -> CLIP text) run on two streams; each gets its own lane."""
+
+    def __init__(self, idx):
+        self.idx = int(idx)
+
+    def __enter__(self):
+        global _LANE
+        self.prev, _LANE = _LANE, self.idx
+
+    def __exit__(self, *exc):
+        global _LANE
+        _LANE = self.prev
 
 
 def _splitk_workspace(device):
-    """One zero-initialised split-K workspace per device; every stream-ordered cb_gemm launch may share it."""
-    ws = _splitk_ws.get(device)
+    """One zero-initialised split-K workspace per (device, lane); stream-ordered cb_gemm launches share it."""
+    ws = _splitk_ws.get((device, _LANE))
     if ws is None:
-        ws = torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
-        _splitk_ws[device] = ws
+        ws = torch.zeros(SPLITK_WS_BYTES if _LANE == 0 else SPLITK_WS_BYTES // 4, dtype=torch.uint8, device=device)
+        _splitk_ws[(device, _LANE)] = ws
     return ws
 
 
 def _gemm(d, what):
     ws = _splitk_workspace(torch.cuda.current_device())
-    d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), SPLITK_WS_BYTES
+    d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     if GEMM_DEBUG_TIMELINE is not None:
         d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
     if GEMM_RECORD is not None:
@@ -231,10 +248,10 @@ CB_GN_WS_BYTES = 131072
 
 def _gn_workspace(device):
     """One GroupNorm workspace per device (calls are stream-ordered)."""
-    ws = _ws_cache.get(("gn", device))
+    ws = _ws_cache.get(("gn", device, _LANE))
     if ws is None:
         ws = torch.zeros(CB_GN_WS_BYTES // 8, dtype=torch.float64, device=device)
-        _ws_cache[("gn", device)] = ws
+        _ws_cache[("gn", device, _LANE)] = ws
     return ws
 
 

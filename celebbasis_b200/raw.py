@@ -49,5 +49,5 @@ def gemm(A, B, D, *, M, N, K, batch=1, lda=None, ldb=None, ldd=None, a_bs=0, b_b
     d.alpha, d.act = float(alpha), int(act)
     from . import ops as _ops
     ws = _ops._splitk_workspace(torch.cuda.current_device())
-    d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), _ops.SPLITK_WS_BYTES
+    d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     _lib.check(L.cb_gemm(ctypes.byref(d), stream_ptr()), "cb_gemm")

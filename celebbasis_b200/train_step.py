@@ -9,6 +9,8 @@ This is the function LatentDiffusion.shared_step + loss.backward() + optimizer.s
 (ldm/models/diffusion/ddpm.py:921-936,1069-1116,1442-1454).  Forward and backward are launched back to back so the
 whole step can be captured in one CUDA graph; torch is used for buffers, streams and the graph only.
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -112,6 +114,8 @@ class CelebBasisStep:
         self.adam_v = torch.zeros_like(self.flat)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.lr = lr
+        self.overlap_branches = True     # VAE encode || face net + CLIP text on two streams (see run())
+        self._side = None
         self.basis = basis.detach().to(self.dev, torch.float32).contiguous()
         self.tokenizer = tokenizer
         self.placeholder_token = int(tokenizer(placeholder)["input_ids"][0, 1])
@@ -171,16 +175,35 @@ class CelebBasisStep:
         """Device side of the step: only kernel launches on the current stream (CUDA-graph capturable)."""
         B = image.shape[0]
         n_chunks = ids_person.shape[1]
-        z, _ = self.encode_first_stage(image, posterior_eps)
-        v = self.face_features(faces, n_chunks)                                  # (n_chunks*B, 512)
-        pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
-        zc = ops.celeb_basis_fwd(coef, self.basis)                               # (F, es, 768)
         T = ids_dev.shape[1]
-        tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
-        emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
-        context = self.clip.forward(emb, B, need_grad=need_grad)                 # (B*T, 768) fp32
+        # Two independent branches until the UNet: (a) face net -> celeb-basis MLP -> CLIP text (small, latency-bound
+        # launches that use few SMs) and (b) VAE encode + q_sample (large, throughput-bound convs).  They run on two
+        # streams (fork/join with events; a captured graph keeps them as parallel branches).  Branch (a) never launches
+        # a grid-barrier kernel (no GroupNorm), so the fused GroupNorm of branch (b) keeps its co-residency guarantee.
+        main = torch.cuda.current_stream()
+        if self.overlap_branches:
+            side = self._side_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            ctx_a, lane_a = torch.cuda.stream(side), ops.lane(1)
+        else:
+            ctx_a, lane_a = contextlib.nullcontext(), contextlib.nullcontext()
+        with ctx_a, lane_a:
+            v = self.face_features(faces, n_chunks)                                  # (n_chunks*B, 512)
+            pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
+            zc = ops.celeb_basis_fwd(coef, self.basis)                               # (F, es, 768)
+            tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
+            emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
+            context = self.clip.forward(emb, B, need_grad=need_grad)                 # (B*T, 768) fp32
+            if self.overlap_branches:
+                join = torch.cuda.Event()
+                join.record(side)
+        z, _ = self.encode_first_stage(image, posterior_eps)
         noise = noise.contiguous()
         x_noisy = self.q_sample(z, t, noise)
+        if self.overlap_branches:
+            main.wait_event(join)
         eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
         loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)   # (B,) per-sample losses
         loss = loss_simple if B == 1 else loss_simple.mean(0, keepdim=True)
@@ -196,6 +219,11 @@ class CelebBasisStep:
             ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, self.gW, self.gb)
             self.last.update(d_eps=d_eps, dctx=dctx, demb=demb, dz=dz, dcoef=dcoef)
         return loss
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
 
     def _ema_update(self, zc, coef, ids_person, B):
         """_momentum_update, training branch (embedding_manager.py:484-489) for the main identity of each sample."""
