@@ -361,6 +361,356 @@ CB_LAUNCH((kern), grid, kAttnThreads, Cfg::kSmemBytes, st, q, k, v, p);
     return 0;
 }
 
+
+// =================================================================================================================
+// Backward.  Two launches of one kernel template, both without atomics and without the (heads x N x N) tensors:
+//   MODE 0 (dQ)    : CTA = 128 query rows.  X1 = Q, X2 = dO stationary; per 64-key block Y1 = K_j, Y2 = V_j.
+//   MODE 1 (dK,dV) : CTA = 128 key rows.    X1 = K, X2 = V  stationary; per 64-query block Y1 = Q_j, Y2 = dO_j.
+// Every block: T1 = X1 Y1^T (scores, or their transpose) and T2 = X2 Y2^T (dP, or its transpose) into TMEM;
+// one thread per stationary row rebuilds P = exp2(T1*scale*log2e - lse*log2e) and dS = P o (T2 - delta) * scale with the
+// forward's log-sum-exp and delta = rowsum(dO o O) (indexed by row in MODE 0, by column in MODE 1) and writes them as
+// K-major SWIZZLE_128B A tiles; then  MODE 0: acc += dS Y1 (= dS K);  MODE 1: accV += P^T Y2 (= P^T dO),
+// accK += dS^T Y1 (= dS^T Q) with the streamed tiles read MN-major, exactly like V in the forward kernel.
+// MODE 0 also computes delta (it owns dO and reads O) and stores it for the MODE 1 launch that follows it in stream order.
+struct AttnBwdParams {
+    int n_stat, n_stream, heads, images;     // rows of the stationary / streamed operands (nq,nk in MODE 0; nk,nq in MODE 1)
+    int d, dpad16, dboxes, causal;
+    float scale, scale_log2e;
+    const float* lse;        // [images][heads][nq]
+    float* delta;            // [images][heads][nq]   (written by MODE 0, read by MODE 1)
+    const void* O;           // MODE 0 only: forward output, for delta
+    const void* dO;
+    long long ldo, lddo;
+    void* out1;              // MODE 0: dQ ; MODE 1: dV
+    void* out2;              // MODE 1: dK
+    long long ld1, ld2;
+    int is_bf16;
+    int nq;                  // query count (lse / delta row pitch)
+    unsigned idesc_t, idesc_acc;
+};
+
+template <int DBOX, int MODE>
+struct AttnBwdCfg {
+    static constexpr int kXBytes = DBOX * kBQ * 128;        // one stationary tile
+    static constexpr int kYBytes = DBOX * kBKV * 128;       // one streamed tile
+    static constexpr int kABytes = kBQ * 128;               // one A tile (128 rows x 64 block items)
+    static constexpr int kNumA = MODE == 0 ? 1 : 2;
+    static constexpr int kNumAcc = MODE == 0 ? 1 : 2;
+    static constexpr int kSmemBytes = 2 * kXBytes + 2 * 2 * kYBytes + kNumA * kABytes + 1024 + 256 + 1024;
+    static constexpr int kTmemNeed = 128 + kNumAcc * DBOX * 64;
+    static constexpr int kTmemCols = kTmemNeed <= 256 ? 256 : 512;
+    static constexpr int kMinBlocks = (kTmemCols <= 256 && kSmemBytes <= 110 * 1024) ? 2 : 1;
+};
+
+__device__ __forceinline__ void store_a16(uint32_t tile, int r, int key8, const float (&e)[8], bool bf16) {
+    uint4 pk;
+    if (bf16) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(e[2 * i], e[2 * i + 1]);
+    } else {
+        __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
+    }
+    const uint32_t dst = tile + r * 128 + ((key8 ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+}
+
+template <int DBOX, int MODE>
+__global__ void __launch_bounds__(kAttnThreads, AttnBwdCfg<DBOX, MODE>::kMinBlocks)
+cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                        const __grid_constant__ CUtensorMap tmY1, const __grid_constant__ CUtensorMap tmY2,
+                        const __grid_constant__ AttnBwdParams p) {
+    using Cfg = AttnBwdCfg<DBOX, MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sX1 = base, sX2 = base + Cfg::kXBytes;
+    const uint32_t sY = sX2 + Cfg::kXBytes;                       // stage s: Y1 at sY + s*2*kYBytes, Y2 right after
+    const uint32_t sA = sY + 4 * Cfg::kYBytes;                    // A tile 0 (dS in MODE 0, P^T in MODE 1), tile 1 (dS^T)
+    const uint32_t bars = sA + Cfg::kNumA * Cfg::kABytes;
+    const uint32_t bar_x = bars;
+    auto bar_y_full = [&](int s) { return bars + 8u * (1 + s); };
+    auto bar_y_empty = [&](int s) { return bars + 8u * (3 + s); };
+    const uint32_t bar_t_full = bars + 8u * 5;
+    const uint32_t bar_t_empty = bars + 8u * 6;
+    const uint32_t bar_a_full = bars + 8u * 7;
+    const uint32_t bar_a_done = bars + 8u * 8;
+    const uint32_t tmem_slot = bars + 8u * 9;
+    float* s_stat = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));    // [2 buffers][2][64] (MODE 1)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * kBQ;
+    const int head = blockIdx.y, img = blockIdx.z;
+    // streamed block range (causal: keys <= query)
+    int jbeg = 0, jend = (p.n_stream + kBKV - 1) / kBKV;
+    if (p.causal) {
+        if (MODE == 0) jend = min(jend, (min(x0 + kBQ, p.n_stat) + kBKV - 1) / kBKV);     // keys up to the last query row
+        else jbeg = x0 / kBKV;                                                            // queries from the first key row
+    }
+    const int nit = max(0, jend - jbeg);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmX2); tma_prefetch_desc(&tmY1); tma_prefetch_desc(&tmY2);
+        mbar_init(bar_x, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_y_full(s), 1); mbar_init(bar_y_empty(s), 1); }
+        mbar_init(bar_t_full, 1);
+        mbar_init(bar_t_empty, 128);
+        mbar_init(bar_a_full, 128);
+        mbar_init(bar_a_done, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+    const uint32_t tT1 = tmem, tT2 = tmem + 64, tAcc0 = tmem + 128, tAcc1 = tmem + 128 + DBOX * 64;
+    pdl_sync();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_x, 2 * Cfg::kXBytes);
+#pragma unroll
+            for (int b = 0; b < DBOX; ++b) {
+                tma_load_4d(sX1 + b * (kBQ * 128), &tmX1, bar_x, b * 64, x0, head, img);
+                tma_load_4d(sX2 + b * (kBQ * 128), &tmX2, bar_x, b * 64, x0, head, img);
+            }
+            for (int it = 0; it < nit; ++it) {
+                const int s = it & 1;
+                mbar_wait(bar_y_empty(s), ((it >> 1) & 1) ^ 1u);
+                mbar_arrive_expect_tx(bar_y_full(s), 2 * Cfg::kYBytes);
+                const uint32_t d1 = sY + s * 2 * Cfg::kYBytes, d2 = d1 + Cfg::kYBytes;
+#pragma unroll
+                for (int b = 0; b < DBOX; ++b) {
+                    tma_load_4d(d1 + b * (kBKV * 128), &tmY1, bar_y_full(s), b * 64, (jbeg + it) * kBKV, head, img);
+                    tma_load_4d(d2 + b * (kBKV * 128), &tmY2, bar_y_full(s), b * 64, (jbeg + it) * kBKV, head, img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const int ks = p.dpad16 / 16;
+            auto issue_T = [&](int it) {
+                const int s = it & 1;
+                mbar_wait(bar_y_full(s), (it >> 1) & 1);
+                mbar_wait(bar_t_empty, (it & 1) ^ 1u);
+                tc_fence_after();
+                const uint32_t y1 = sY + s * 2 * Cfg::kYBytes, y2 = y1 + Cfg::kYBytes;
+                for (int k = 0; k < ks; ++k) {
+                    const uint32_t offx = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                    const uint32_t offy = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                    umma_f16(tT1, umma_smem_desc_sw128(sX1 + offx, 16, 1024), umma_smem_desc_sw128(y1 + offy, 16, 1024),
+                             p.idesc_t, k > 0 ? 1u : 0u);
+                }
+                for (int k = 0; k < ks; ++k) {
+                    const uint32_t offx = (k >> 2) * (kBQ * 128) + (k & 3) * 32;
+                    const uint32_t offy = (k >> 2) * (kBKV * 128) + (k & 3) * 32;
+                    umma_f16(tT2, umma_smem_desc_sw128(sX2 + offx, 16, 1024), umma_smem_desc_sw128(y2 + offy, 16, 1024),
+                             p.idesc_t, k > 0 ? 1u : 0u);
+                }
+                umma_commit(bar_t_full);
+            };
+            mbar_wait(bar_x, 0);
+            if (nit > 0) issue_T(0);
+            for (int it = 0; it < nit; ++it) {
+                if (it + 1 < nit) issue_T(it + 1);
+                const int s = it & 1;
+                mbar_wait(bar_a_full, it & 1);
+                tc_fence_after();
+                const uint32_t y1 = sY + s * 2 * Cfg::kYBytes, y2 = y1 + Cfg::kYBytes;
+                for (int k = 0; k < kBKV / 16; ++k) {
+                    const uint64_t a0 = umma_smem_desc_sw128(sA + k * 32, 16, 1024);
+                    if (MODE == 0) {
+                        umma_f16(tAcc0, a0, umma_smem_desc_sw128(y1 + k * 2048, kBKV * 128, 1024), p.idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+                        const uint64_t a1 = umma_smem_desc_sw128(sA + Cfg::kABytes + k * 32, 16, 1024);
+                        umma_f16(tAcc0, a0, umma_smem_desc_sw128(y2 + k * 2048, kBKV * 128, 1024), p.idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_f16(tAcc1, a1, umma_smem_desc_sw128(y1 + k * 2048, kBKV * 128, 1024), p.idesc_acc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(bar_y_empty(s));
+                umma_commit(bar_a_done);
+            }
+        }
+    } else {
+        // ====================== one thread per stationary row ======================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int xrow = x0 + r;
+        const bool row_ok = xrow < p.n_stat;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const int et = threadIdx.x - 64;
+        const long long stat_base = (static_cast<long long>(img) * p.heads + head) * p.nq;
+        const float kLog2e = 1.4426950408889634f;
+        float lse_r = 0.f, delta_r = 0.f;          // MODE 0: this query row's statistics
+        float nlse = 0.f, ndelta = 0.f;            // MODE 1: prefetched column statistics of the next block (threads et < 64)
+        if (MODE == 0) {
+            if (row_ok) {
+                lse_r = p.lse[stat_base + xrow] * kLog2e;
+                const uint16_t* orow = reinterpret_cast<const uint16_t*>(p.O) + (static_cast<long long>(img) * p.n_stat + xrow) * p.ldo + static_cast<long long>(head) * p.d;
+                const uint16_t* grow = reinterpret_cast<const uint16_t*>(p.dO) + (static_cast<long long>(img) * p.n_stat + xrow) * p.lddo + static_cast<long long>(head) * p.d;
+                float acc = 0.f;
+                for (int c = 0; c < p.d; c += 8) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(orow + c), b = *reinterpret_cast<const uint4*>(grow + c);
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float2 fa, fb;
+                        if (p.is_bf16) {
+                            fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+                            fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+                        } else {
+                            fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[i]));
+                            fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[i]));
+                        }
+                        acc += fa.x * fb.x + fa.y * fb.y;
+                    }
+                }
+                delta_r = acc;
+                p.delta[stat_base + xrow] = acc;
+            }
+        } else if (et < 64 && nit > 0) {
+            const int qc = jbeg * kBKV + et;
+            if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc]; }
+        }
+        for (int it = 0; it < nit; ++it) {
+            const int j = jbeg + it;
+            const int cbase = j * kBKV;
+            float* st_l = s_stat + (it & 1) * 128;
+            float* st_d = st_l + 64;
+            if (MODE == 1) {
+                if (et < 64) { st_l[et] = nlse; st_d[et] = ndelta; }
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+                if (et < 64 && it + 1 < nit) {
+                    const int qc = (j + 1) * kBKV + et;
+                    nlse = 0.f; ndelta = 0.f;
+                    if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc]; }
+                }
+            }
+            // valid streamed items of this block for this row
+            int cvalid = min(kBKV, p.n_stream - cbase);      // columns past the end of the streamed operand
+            int cfirst = 0;
+            if (p.causal) {
+                if (MODE == 0) cvalid = min(cvalid, xrow - cbase + 1);      // keys <= this query
+                else cfirst = max(0, xrow - cbase);                         // queries >= this key
+            }
+            if (!row_ok && MODE == 0) cvalid = 0;
+            mbar_wait(bar_t_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t t1[32], t2[32];
+                tmem_ld_32x32(tT1 + lane_off + half * 32, t1);
+                tmem_ld_32x32(tT2 + lane_off + half * 32, t2);
+                tmem_ld_wait();
+                if (half == 1) {
+                    tc_fence_before();
+                    mbar_arrive(bar_t_empty);           // T1/T2 may be overwritten by the next block's MMAs
+                } else if (it > 0) {
+                    mbar_wait(bar_a_done, (it - 1) & 1);    // the previous block's accumulation MMAs have read the A tiles
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float pe[8], ds[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = half * 32 + g * 8 + i;
+                        const float l2 = MODE == 0 ? lse_r : st_l[c];
+                        const float dl = MODE == 0 ? delta_r : st_d[c];
+                        const bool ok = c < cvalid && c >= cfirst;
+                        const float pv = ok ? fast_exp2(__uint_as_float(t1[g * 8 + i]) * p.scale_log2e - l2) : 0.f;
+                        pe[i] = pv;
+                        ds[i] = pv * (__uint_as_float(t2[g * 8 + i]) - dl) * p.scale;
+                    }
+                    const int key8 = half * 4 + g;
+                    if (MODE == 0) {
+                        store_a16(sA, r, key8, ds, p.is_bf16 != 0);
+                    } else {
+                        store_a16(sA, r, key8, pe, p.is_bf16 != 0);
+                        store_a16(sA + Cfg::kABytes, r, key8, ds, p.is_bf16 != 0);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_a_full);
+        }
+        // ---- epilogue: accumulators -> HBM ----
+        if (nit > 0) mbar_wait(bar_a_done, (nit - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int a = 0; a < Cfg::kNumAcc; ++a) {
+            const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
+            uint16_t* outp = reinterpret_cast<uint16_t*>(a == 0 ? p.out1 : p.out2);
+            const long long ldout = a == 0 ? p.ld1 : p.ld2;
+            for (int c = 0; c * 32 < DBOX * 64; ++c) {
+                if (c * 32 >= p.d) break;
+                uint32_t o[32];
+                if (nit > 0) {
+                    tmem_ld_32x32(tacc + lane_off + c * 32, o);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = 0u;
+                }
+                if (row_ok) {
+                    const long long orow = (static_cast<long long>(img) * p.n_stat + xrow) * ldout + static_cast<long long>(head) * p.d;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = c * 32 + g * 8;
+                        if (col < p.d) {
+                            uint4 pk;
+                            if (p.is_bf16) {
+                                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * i]), __uint_as_float(o[g * 8 + 2 * i + 1]));
+                            } else {
+                                __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(__uint_as_float(o[g * 8 + 2 * i]), __uint_as_float(o[g * 8 + 2 * i + 1]));
+                            }
+                            *reinterpret_cast<uint4*>(outp + orow + col) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem);
+}
+
+template <int DBOX, int MODE>
+static int launch_attn_bwd(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& y1, const CUtensorMap& y2,
+                           const AttnBwdParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = AttnBwdCfg<DBOX, MODE>;
+    static bool done = false;
+    auto kern = cb_attention_bwd_kernel<DBOX, MODE>;
+    if (!done) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        done = true;
+    }
+    CB_LAUNCH((kern), grid, kAttnThreads, Cfg::kSmemBytes, st, x1, x2, y1, y2, p);
+    CB_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+static int attn_tmap(CUtensorMap* out, int dtype, const void* ptr, long long ld, int rows, int d, int heads, int images, int box_rows) {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)rows, (uint64_t)heads, (uint64_t)images};
+    uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)d * 2, (uint64_t)rows * ld * 2};
+    uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+    uint32_t estr[4] = {1, 1, 1, 1};
+    return make_tmap(out, dtype, 4, ptr, dims, str, box, estr);
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -410,4 +760,52 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (p.dboxes == 1) return launch_attn<1>(tq, tk, tv, p, grid, st);
     return launch_attn<2>(tq, tk, tv, p, grid, st);
+}
+
+extern "C" int cb_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                                const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
+                                void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, int dtype,
+                                int images, int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
+    CB_REQUIRE(dtype == CB_F16 || dtype == CB_BF16, CB_ERR_ARG, "attention_bwd: dtype must be f16/bf16");
+    CB_REQUIRE(Q && K && V && O && dO && lse && delta && dQ && dK && dV && images > 0 && heads > 0 && nq > 0 && nk > 0,
+               CB_ERR_ARG, "attention_bwd: bad args");
+    CB_REQUIRE(d >= 8 && d <= 128 && d % 8 == 0, CB_ERR_ARG, "attention_bwd: head dim %d unsupported (8..128, multiple of 8)", d);
+    const void* ptrs[8] = {Q, K, V, O, dO, dQ, dK, dV};
+    const long long lds[8] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv};
+    for (int i = 0; i < 8; ++i)
+        CB_REQUIRE((lds[i] * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15u) == 0, CB_ERR_ALIGN,
+                   "attention_bwd: operand %d must be 16-byte aligned with a 16-byte multiple row pitch", i);
+    AttnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.heads = heads; p.images = images; p.d = d; p.dpad16 = (d + 15) / 16 * 16; p.dboxes = d <= 64 ? 1 : 2;
+    p.causal = causal; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+    p.lse = lse; p.delta = delta; p.O = O; p.dO = dO; p.ldo = ldo; p.lddo = lddo;
+    p.is_bf16 = dtype == CB_BF16; p.nq = nq;
+    p.idesc_t = umma_idesc_f16(128, kBKV, dtype == CB_BF16, false, false);
+    p.idesc_acc = umma_idesc_f16(128, p.dboxes * 64, dtype == CB_BF16, false, true);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap x1, x2, y1, y2;
+    int rc;
+    // ---- MODE 0: dQ (+ delta) ----
+    if ((rc = attn_tmap(&x1, dtype, Q, ldq, nq, d, heads, images, kBQ))) return rc;
+    if ((rc = attn_tmap(&x2, dtype, dO, lddo, nq, d, heads, images, kBQ))) return rc;
+    if ((rc = attn_tmap(&y1, dtype, K, ldk, nk, d, heads, images, kBKV))) return rc;
+    if ((rc = attn_tmap(&y2, dtype, V, ldv, nk, d, heads, images, kBKV))) return rc;
+    p.n_stat = nq; p.n_stream = nk; p.out1 = dQ; p.ld1 = lddq; p.out2 = nullptr; p.ld2 = 0;
+    {
+        dim3 grid((unsigned)ceil_div(nq, kBQ), (unsigned)heads, (unsigned)images);
+        rc = p.dboxes == 1 ? launch_attn_bwd<1, 0>(x1, x2, y1, y2, p, grid, st) : launch_attn_bwd<2, 0>(x1, x2, y1, y2, p, grid, st);
+        if (rc) return rc;
+    }
+    // ---- MODE 1: dK, dV ----
+    if ((rc = attn_tmap(&x1, dtype, K, ldk, nk, d, heads, images, kBQ))) return rc;
+    if ((rc = attn_tmap(&x2, dtype, V, ldv, nk, d, heads, images, kBQ))) return rc;
+    if ((rc = attn_tmap(&y1, dtype, Q, ldq, nq, d, heads, images, kBKV))) return rc;
+    if ((rc = attn_tmap(&y2, dtype, dO, lddo, nq, d, heads, images, kBKV))) return rc;
+    p.n_stat = nk; p.n_stream = nq; p.out1 = dV; p.ld1 = lddv; p.out2 = dK; p.ld2 = lddk;
+    {
+        dim3 grid((unsigned)ceil_div(nk, kBQ), (unsigned)heads, (unsigned)images);
+        rc = p.dboxes == 1 ? launch_attn_bwd<1, 1>(x1, x2, y1, y2, p, grid, st) : launch_attn_bwd<2, 1>(x1, x2, y1, y2, p, grid, st);
+    }
+    return rc;
 }

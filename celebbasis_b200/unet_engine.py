@@ -28,14 +28,22 @@ def _round_up(a, b):
 
 
 class _Attn:
-    """softmax(q k^T * scale) v for (image, head) batches; probabilities are kept for backward."""
+    """softmax(q k^T * scale) v for (image, head) batches.  What is kept for the backward pass is either the
+    log-sum-exp + output (flash backward, nothing quadratic in HBM) or the probabilities (materialised path)."""
 
-    FLASH = True   # fused tcgen05 flash kernel for head dims <= 128 (set False to force the materialised path)
+    FLASH = True       # fused tcgen05 flash kernel for head dims <= 128 (set False to force the materialised path)
+    FLASH_BWD = True   # recompute-in-TMEM backward (cb_attention_bwd) instead of P / dP / dS round trips through HBM
+    FLASH_BWD_MIN_NK = 256   # short key sequences (cross attention on 77 tokens): the materialised path has more CTAs
 
     @staticmethod
     def fwd(q, k, v, *, images, heads, dh, nq, nk, scale, out, causal=False, need_p=True):
-        """Returns the probabilities [images*heads*nq][round_up(nk,8)] when need_p (kept for the backward pass)."""
+        """Returns the state the backward pass needs: ("lse", lse, out) or the probabilities
+        [images*heads*nq][round_up(nk,8)] (None when not need_p)."""
         if _Attn.FLASH and dh <= 128 and dh % 8 == 0:
+            if need_p and _Attn.FLASH_BWD and nk >= _Attn.FLASH_BWD_MIN_NK:
+                _, lse = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
+                                           causal=causal, want_lse=True)
+                return ("lse", lse, out, causal)
             P, _ = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
                                      causal=causal, want_p=need_p)
             return P
@@ -52,6 +60,11 @@ class _Attn:
 
     @staticmethod
     def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv):
+        if isinstance(P, tuple):
+            _, lse, out, causal = P
+            ops.attention_bwd(q, k, v, out, dO, lse, dq, dk, dv, images=images, heads=heads, dh=dh, nq=nq, nk=nk,
+                              scale=scale, causal=causal)
+            return
         ldp = P.shape[1]
         dP = torch.empty_like(P)
         # dP = dO V^T

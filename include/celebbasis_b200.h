@@ -276,6 +276,19 @@ int cb_attention_fwd(const void* Q, long long ldq, const void* K, long long ldk,
                      long long ldo, float* lse, void* P, long long ldp, int dtype, int images, int heads, int nq,
                      int nk, int d, float scale, int causal, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * cb_attention_bwd -- flash-style backward of the same attention (the gradient torch.autograd derives for
+ * ldm/modules/attention.py:178-191): dQ, dK, dV from Q, K, V, O, dO and the forward's lse, recomputing the
+ * probabilities tile by tile in TMEM; no (heads x N x N) tensor and no atomics.  Two launches: query-stationary
+ * (dQ, also writes delta = rowsum(dO o O)) then key-stationary (dK, dV).
+ *   layouts as cb_attention_fwd; dQ/dK/dV use the layouts of Q/K/V with their own row pitches;
+ *   delta: caller workspace [images][heads][nq] fp32.
+ * ------------------------------------------------------------------------------------------- */
+int cb_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                     const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
+                     void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, int dtype, int images,
+                     int heads, int nq, int nk, int d, float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

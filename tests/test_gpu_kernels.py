@@ -282,6 +282,40 @@ def test_face_warp_resize(dev):
 
 
 @pytest.mark.parametrize("nq,nk,dh,heads,images,causal", [(4096, 4096, 40, 8, 1, False), (1024, 1024, 80, 8, 1, False),
+                                                          (1024, 77, 80, 8, 2, False), (77, 77, 64, 12, 2, True),
+                                                          (300, 200, 128, 2, 1, False), (64, 64, 40, 8, 1, False),
+                                                          (200, 330, 40, 2, 2, True)])
+def test_flash_attention_bwd(dev, nq, nk, dh, heads, images, causal):
+    """cb_attention_bwd (P, dP, dS rebuilt tile by tile in TMEM from the forward's log-sum-exp; dQ then dK/dV, no
+    atomics) vs torch.autograd of softmax(QK^T*scale)V in fp32 on the same fp16 inputs."""
+    from celebbasis_b200 import ops
+    C = heads * dh
+    scale = dh ** -0.5
+    # q/k/v and the gradients live in wider fused buffers (as the engines keep them): exercises the row pitches
+    qkv = rnd(images * max(nq, nk), 3 * C + 8)
+    q, k, v = qkv[:images * nq, :C], qkv[:images * nk, C:2 * C], qkv[:images * nk, 2 * C:3 * C]
+    dO = rnd(images * nq, C)
+    o = torch.empty(images * nq, C, dtype=torch.float16, device="cuda")
+    _, lse = ops.attention_fwd(q, k, v, o, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale, causal=causal,
+                               want_lse=True)
+    dqkv = torch.full((images * max(nq, nk), 3 * C), float("nan"), dtype=torch.float16, device="cuda")
+    dq, dk, dv = dqkv[:images * nq, :C], dqkv[:images * nk, C:2 * C], dqkv[:images * nk, 2 * C:]
+    ops.attention_bwd(q, k, v, o, dO, lse, dq, dk, dv, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
+                      causal=causal)
+    sp = lambda t, n: t.float().reshape(images, n, heads, dh).permute(0, 2, 1, 3)
+    qf, kf, vf = (sp(q, nq).requires_grad_(), sp(k, nk).requires_grad_(), sp(v, nk).requires_grad_())
+    sc = qf @ kf.transpose(-1, -2) * scale
+    if causal:
+        sc = sc + torch.full((nq, nk), float("-inf"), device="cuda").triu_(1)
+    ref_o = torch.softmax(sc, -1) @ vf
+    ref_o.backward(sp(dO, nq))
+    back = lambda t, n: t.permute(0, 2, 1, 3).reshape(images * n, C)
+    for name, got, ref in (("dq", dq, back(qf.grad, nq)), ("dk", dk, back(kf.grad, nk)), ("dv", dv, back(vf.grad, nk))):
+        assert torch.isfinite(got.float()).all(), name
+        assert rel(got, ref) < 6e-3, (name, rel(got, ref))
+
+
+@pytest.mark.parametrize("nq,nk,dh,heads,images,causal", [(4096, 4096, 40, 8, 1, False), (1024, 1024, 80, 8, 1, False),
                                                           (1024, 77, 80, 8, 2, False), (4096, 77, 40, 8, 1, False),
                                                           (77, 77, 64, 12, 2, True), (300, 200, 128, 2, 1, False),
                                                           (64, 64, 40, 8, 1, False)])

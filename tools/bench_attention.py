@@ -39,3 +39,21 @@ for (nq, nk, dh, H) in [(4096, 4096, 40, 8), (1024, 1024, 80, 8), (4096, 77, 40,
         res[mode + "_us"] = round(us, 1)
         res[mode + "_tflops"] = round(flops / us / 1e6, 1)
     print(json.dumps(res), flush=True)
+
+# ---- backward: flash (cb_attention_bwd, 2 launches) vs materialised (dP GEMM + softmax_bwd + 3 GEMMs) ----
+_Attn.FLASH = True
+for (nq, nk, dh, H) in [(4096, 4096, 40, 8), (1024, 1024, 80, 8), (4096, 77, 40, 8), (1024, 77, 80, 8)]:
+    C = H * dh
+    q, k, v, dO = rnd(nq, C), rnd(nk, C), rnd(nk, C), rnd(nq, C)
+    o = torch.empty_like(q)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    res = {"case": f"attn_bwd_nq{nq}_nk{nk}_d{dh}"}
+    for mode in ("flash", "materialised"):
+        _Attn.FLASH_BWD = mode == "flash"
+        _Attn.FLASH_BWD_MIN_NK = 0
+        saved = _Attn.fwd(q, k, v, images=1, heads=H, dh=dh, nq=nq, nk=nk, scale=dh ** -0.5, out=o)
+        fn = lambda: _Attn.bwd(dO, q, k, v, saved, images=1, heads=H, dh=dh, nq=nq, nk=nk, scale=dh ** -0.5, dq=dq, dk=dk, dv=dv)
+        us = timeit(fn)
+        res[mode + "_us"] = round(us, 1)
+        res[mode + "_tflops"] = round(10.0 * nq * nk * C / us / 1e6, 1)
+    print(json.dumps(res), flush=True)
