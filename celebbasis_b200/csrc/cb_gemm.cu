@@ -595,6 +595,10 @@ static int pick_bn(const cb_gemm_desc& d, int m_tiles, int kiters) {
         cands[nc++] = 128;
         cands[nc++] = 64;
     }
+    static const int env_bn = getenv("CB_GEMM_BN") ? atoi(getenv("CB_GEMM_BN")) : 0;   // tuning aid
+    const int force_bn = d.tile_n > 0 ? d.tile_n : env_bn;
+    for (int i = 0; i < nc; ++i)
+        if (cands[i] == force_bn) return force_bn;
     int best = cands[0];
     double best_t = 1e30;
     for (int i = 0; i < nc; ++i) {
@@ -770,17 +774,21 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         // (L2 reductions serialise per address, so split-K only pays when the output tile is small: <= 512 rows)
         const long long counters_bytes = 65536;
         const long long avail = d.splitk_ws_bytes - counters_bytes;
-        if (d.splitk_ws != nullptr && tiles < sms && kiters >= 8 && tiles <= counters_bytes / 4 &&
-            tiles * (long long)(BM * BN * 4) <= avail) {
+        const bool ws_ok = d.splitk_ws != nullptr && tiles <= counters_bytes / 4 && tiles * (long long)(BM * BN * 4) <= avail;
+        if (ws_ok && (d.splits > 0 || (tiles < sms && kiters >= 8))) {
             const double out_elems = (double)p.M * d.batch * d.N;
             double best_t = tile_time_us(BN, tiles, kiters, sms);
             int best_sp = 1;
-            const int max_sp = (int)(sms / tiles) < 64 ? (int)(sms / tiles) : 64;
-            for (int sp = 2; sp <= max_sp; ++sp) {
-                const int per = ceil_div(kiters, sp);
-                if (per < 4) break;
-                const double t = per * ((128.0 + BN) * 128.0 / 80e3) + out_elems * sp / 150e3 + 3.0;
-                if (t < best_t) { best_t = t; best_sp = sp; }
+            if (d.splits > 0) {
+                best_sp = d.splits < kiters ? d.splits : kiters;       // caller-tuned
+            } else {
+                const int max_sp = (int)(sms / tiles) < 64 ? (int)(sms / tiles) : 64;
+                for (int sp = 2; sp <= max_sp; ++sp) {
+                    const int per = ceil_div(kiters, sp);
+                    if (per < 4) break;
+                    const double t = per * ((128.0 + BN) * 128.0 / 80e3) + out_elems * sp / 150e3 + 3.0;
+                    if (t < best_t) { best_t = t; best_sp = sp; }
+                }
             }
             if (best_sp > 1) {
                 const int per = ceil_div(kiters, best_sp);

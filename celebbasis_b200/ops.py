@@ -4,6 +4,7 @@ Layout conventions (see include/celebbasis_b200.h): activations are 2-D channels
 [rows][C] (rows = N*H*W pixels in raster order, or tokens).  All math happens inside the .so.
 """
 import ctypes
+import os
 
 import torch
 
@@ -64,11 +65,114 @@ def _splitk_workspace(device):
     return ws
 
 
+# ---- per-shape tile autotuner --------------------------------------------------------------------------------
+# cb_gemm picks its tile width and split-K factor from a cost model; at bs=1 most launches are latency / L2-fabric
+# bound and the model is off by up to 1.5x on some shapes, so the first (eager, un-captured) launch of every distinct
+# shape times the candidates on the device (CUDA-graph replay of 8 launches each, output redirected to scratch) and
+# later launches -- including the ones captured into the step graph -- pass the winner in desc.tile_n / desc.splits.
+AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
+_TUNE = {}
+_tune_scratch = {}
+_tune_stream = {}
+TUNE_LOG = None     # set to a list to collect (key, table of candidate times)
+
+
+def _tune_key(d):
+    return (d.M, d.N, d.K, d.batch, d.batch_inner, d.ab_dtype, d.a_major, d.b_major, d.conv, d.img_n, d.img_h, d.img_w,
+            d.out_h, d.out_w, d.kh, d.kw, d.stride, d.flip_taps, d.d_dtype, d.d_transposed, 1 if d.R else 0, d.r_dtype,
+            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd)
+
+
+def _autotune(d, key):
+    dev = torch.cuda.current_device()
+    M = d.img_n * d.out_h * d.out_w if d.conv else d.M
+    taps = d.kh * d.kw if d.conv else 1
+    kiters = taps * ((d.K + 63) // 64)
+    bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
+    cands = [(0, 0)]
+    for bn in bns:
+        tiles = ((d.N + bn - 1) // bn) * ((M + 127) // 128) * d.batch
+        cands.append((bn, 1))
+        if tiles < 148:
+            for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
+                if tiles * sp <= 320 and kiters // sp >= 2:
+                    cands.append((bn, sp))
+    t = GemmDesc.from_buffer_copy(bytes(d))
+    # scratch output large enough for any addressing the descriptor can produce
+    inner = d.batch_inner if d.batch_inner > 0 else d.batch
+    outer = max(1, d.batch // max(1, inner))
+    span = (d.ldd * (d.N if d.d_transposed else M) + abs(d.d_batch_stride) * (inner - 1) +
+            abs(d.d_batch_stride2) * (outer - 1) + max(M, d.N) + 64)
+    nbytes = int(span) * (4 if d.d_dtype == CB_F32 else 2)
+    sc = _tune_scratch.get(dev)
+    if sc is None or sc.numel() < nbytes:
+        sc = None
+        _tune_scratch.pop(dev, None)
+        sc = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device="cuda")
+        _tune_scratch[dev] = sc
+    t.D, t.R = sc.data_ptr(), None
+    L = _L()
+    times = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
+    side = _tune_stream.get(dev)
+    if side is None:
+        side = _tune_stream[dev] = torch.cuda.Stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        sp_ = ctypes.c_void_p(side.cuda_stream)
+        for bn, sp in cands:
+            t.tile_n, t.splits = bn, sp
+            if L.cb_gemm(ctypes.byref(t), sp_) != 0:
+                continue
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin()
+            ok = True
+            for _ in range(8):
+                ok = ok and L.cb_gemm(ctypes.byref(t), sp_) == 0
+            g.capture_end()
+            if not ok:
+                continue
+            g.replay()
+            best = 1e9
+            for _ in range(3):
+                e0.record(side)
+                g.replay()
+                e1.record(side)
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1) * 125.0)     # us per launch
+            times[(bn, sp)] = best
+            del g
+    cur.wait_stream(side)
+    base = times.get((0, 0), 1e9)
+    win = min(times, key=times.get) if times else (0, 0)
+    if times.get(win, 1e9) > 0.97 * base:     # keep the library's own choice unless the gain is real
+        win = (0, 0)
+    _TUNE[key] = win
+    if TUNE_LOG is not None:
+        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}": round(v, 2) for k, v in times.items()}, win))
+    log_path = os.environ.get("CB_GEMM_TUNE_LOG")
+    if log_path:
+        import json
+        with open(log_path, "a") as f:
+            f.write(json.dumps({"M": M, "N": d.N, "K": d.K, "batch": d.batch, "conv": d.conv, "kh": d.kh, "b_major": d.b_major,
+                                "a_major": d.a_major, "d_dtype": d.d_dtype, "win": list(win),
+                                "us": {f"{k[0]}x{k[1]}": round(v, 2) for k, v in times.items()}}) + "\n")
+    return win
+
+
 def _gemm(d, what):
     ws = _splitk_workspace(torch.cuda.current_device())
     d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     if GEMM_DEBUG_TIMELINE is not None:
         d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
+    if AUTOTUNE and d.tile_n == 0 and d.splits == 0:
+        key = _tune_key(d)
+        win = _TUNE.get(key)
+        if win is None and not torch.cuda.is_current_stream_capturing():
+            win = _autotune(d, key)
+        if win is not None:
+            d.tile_n, d.splits = win
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M

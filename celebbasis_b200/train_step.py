@@ -116,6 +116,7 @@ class CelebBasisStep:
         self.lr = lr
         self.overlap_branches = True     # VAE encode || face net + CLIP text on two streams (see run())
         self._side = None
+        self._warm = False
         self.basis = basis.detach().to(self.dev, torch.float32).contiguous()
         self.tokenizer = tokenizer
         self.placeholder_token = int(tokenizer(placeholder)["input_ids"][0, 1])
@@ -181,7 +182,9 @@ class CelebBasisStep:
         # streams (fork/join with events; a captured graph keeps them as parallel branches).  Branch (a) never launches
         # a grid-barrier kernel (no GroupNorm), so the fused GroupNorm of branch (b) keeps its co-residency guarantee.
         main = torch.cuda.current_stream()
-        if self.overlap_branches:
+        overlap = self.overlap_branches and self._warm      # first call: sequential, so the GEMM autotuner times alone
+        self._warm = True
+        if overlap:
             side = self._side_stream()
             fork = torch.cuda.Event()
             fork.record(main)
@@ -196,13 +199,13 @@ class CelebBasisStep:
             tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
             emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
             context = self.clip.forward(emb, B, need_grad=need_grad)                 # (B*T, 768) fp32
-            if self.overlap_branches:
+            if overlap:
                 join = torch.cuda.Event()
                 join.record(side)
         z, _ = self.encode_first_stage(image, posterior_eps)
         noise = noise.contiguous()
         x_noisy = self.q_sample(z, t, noise)
-        if self.overlap_branches:
+        if overlap:
             main.wait_event(join)
         eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
         loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)   # (B,) per-sample losses

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 1
+#define CB_ABI_VERSION 2
 #define CB_GN_WS_BYTES 131072
 
 /* element types */
@@ -137,6 +137,12 @@ typedef struct cb_gemm_desc {
     /* profiling aid, NULL in production: device buffer of 8 x uint64 per CTA receiving %globaltimer stamps
      * {start, setup done, first stage full, last MMA issued, accumulator ready, exit, 4th stage full, -}. */
     void* debug_timeline;
+
+    /* tuning overrides, 0 = the library's cost model: tile width (64 / 128 / 160; 160 only with K-major B) and the
+     * number of split-K slices (1 = no split; ignored when the workspace cannot hold it).  The host autotuner
+     * (celebbasis_b200/ops.py) times the candidates once per shape and passes the winner here. */
+    int32_t tile_n;
+    int32_t splits;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
