@@ -38,6 +38,7 @@ struct GemmParams {
     int batch_inner;
     int d_transposed;
     int vec_ok;
+    int vec32_ok;     // D (and R) rows are 32-byte aligned: 256-bit LDG/STG (sm_100) in the epilogue
     const float* bias;
     int bias_row_div;
     long long ldbias;
@@ -154,15 +155,35 @@ __device__ __forceinline__ void store_any(void* base, int dtype, long long idx, 
 // needed (the loads are in flight while the MMAs / the previous chunk's stores run; D may alias R, so the compiler could
 // never hoist them itself).
 struct ResidualChunk { uint4 v[8]; };
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
 __device__ __forceinline__ void residual_prefetch(const GemmParams& p, long long ridx, ResidualChunk& rc) {
     if (p.r_dtype == CB_F32) {
-        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.R) + ridx);
+        const float* s = reinterpret_cast<const float*>(p.R) + ridx;
+        if (p.vec32_ok) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rc.v[j] = s[j];
+            for (int j = 0; j < 4; ++j) ldg256(s + 8 * j, rc.v[2 * j], rc.v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rc.v[j] = reinterpret_cast<const uint4*>(s)[j];
+        }
     } else {
-        const uint4* s = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.R) + ridx);
+        const __half* s = reinterpret_cast<const __half*>(p.R) + ridx;
+        if (p.vec32_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rc.v[j] = s[j];
+            for (int j = 0; j < 2; ++j) ldg256(s + 16 * j, rc.v[2 * j], rc.v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rc.v[j] = reinterpret_cast<const uint4*>(s)[j];
+        }
     }
 }
 __device__ __forceinline__ void residual_unpack8(const GemmParams& p, const ResidualChunk& rc, int g, float (&r)[8]) {
@@ -227,6 +248,70 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             const long long didx = p.d_transposed ? (d_off + (long long)(col + j) * p.ldd + grow)
                                                   : (d_off + grow * p.ldd + col + j);
             store_any(p.D, p.d_dtype, didx, v);
+        }
+    }
+}
+
+// Full 32-column chunk of one output row on the aligned fast path: bias / activation / residual on registers, then
+// 256-bit stores (one full 32-byte sector per lane and instruction) when the rows are 32-byte aligned.
+__device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const float (&fin)[32], long long grow, long long brow,
+                                                 int col, long long d_off, long long r_off, const ResidualChunk* rc,
+                                                 const float* sbias) {
+    const long long didx = d_off + grow * p.ldd + col;
+    uint4 pk[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fin[g * 8 + j];
+        if (sbias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += sbias[g * 8 + j];
+        } else if (p.bias) {
+            float b[8];
+            load8<float>(p.bias + brow * p.ldbias + col + g * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += b[j];
+        }
+        if (p.act != CB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (rc) {
+            float r[8];
+            residual_unpack8(p, *rc, g, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        } else if (p.R) {
+            float r[8];
+            const long long ridx = r_off + grow * p.ldr + col + g * 8;
+            if (p.r_dtype == CB_F32) load8<float>(reinterpret_cast<const float*>(p.R) + ridx, r);
+            else if (p.r_dtype == CB_F16) load8<__half>(reinterpret_cast<const __half*>(p.R) + ridx, r);
+            else load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(p.R) + ridx, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        if (p.d_dtype == CB_F32) {
+            float* dst = reinterpret_cast<float*>(p.D) + didx + g * 8;
+            const uint4 a = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+            const uint4 b = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+            if (p.vec32_ok) stg256(dst, a, b);
+            else { reinterpret_cast<uint4*>(dst)[0] = a; reinterpret_cast<uint4*>(dst)[1] = b; }
+        } else {
+            if (p.d_dtype == CB_F16) {
+                __half2* h = reinterpret_cast<__half2*>(&pk[g]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            } else {
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[g]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            }
+            if (g & 1) {
+                uint16_t* dst = reinterpret_cast<uint16_t*>(p.D) + didx + (g - 1) * 8;
+                if (p.vec32_ok) stg256(dst, pk[g - 1], pk[g]);
+                else { reinterpret_cast<uint4*>(dst)[0] = pk[g - 1]; reinterpret_cast<uint4*>(dst)[1] = pk[g]; }
+            }
         }
     }
 }
@@ -411,7 +496,12 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const bool pre = r_fast && ncols_tile - c * 32 >= 32;
                 if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
                 tmem_ld_wait();
-                if (row_valid) {
+                if (row_valid && p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
+                    epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                } else if (row_valid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int nc = min(8, ncols_tile - c * 32 - g * 8);
@@ -419,13 +509,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
-                            if (pre) {
-                                float r8[8];
-                                residual_unpack8(p, rc_cur, g, r8);
-                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, r8, sb ? sb + c * 32 + g * 8 : nullptr);
-                            } else {
-                                epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
-                            }
+                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
                         }
                     }
                 }
@@ -471,17 +555,22 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (pre) residual_prefetch(p, r_row + c * 32, rc_cur);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) __stcg(reinterpret_cast<float4*>(mine + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));
+                        if (p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
+                            float f[32];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int nc = min(8, ncols_tile - c * 32 - g * 8);
-                            if (nc > 0) {
-                                float f[8] = {v[2 * g].x * p.alpha, v[2 * g].y * p.alpha, v[2 * g].z * p.alpha, v[2 * g].w * p.alpha,
-                                              v[2 * g + 1].x * p.alpha, v[2 * g + 1].y * p.alpha, v[2 * g + 1].z * p.alpha, v[2 * g + 1].w * p.alpha};
-                                if (pre) {
-                                    float r8[8];
-                                    residual_unpack8(p, rc_cur, g, r8);
-                                    epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, r8, sb ? sb + c * 32 + g * 8 : nullptr);
-                                } else {
+                            for (int j = 0; j < 8; ++j) {
+                                f[4 * j] = v[j].x * p.alpha; f[4 * j + 1] = v[j].y * p.alpha;
+                                f[4 * j + 2] = v[j].z * p.alpha; f[4 * j + 3] = v[j].w * p.alpha;
+                            }
+                            epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                                if (nc > 0) {
+                                    const float4 lo = v[2 * g], hi = v[2 * g + 1];
+                                    float f[8] = {lo.x * p.alpha, lo.y * p.alpha, lo.z * p.alpha, lo.w * p.alpha,
+                                                  hi.x * p.alpha, hi.y * p.alpha, hi.z * p.alpha, hi.w * p.alpha};
                                     epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
                                 }
                             }
@@ -762,6 +851,14 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         }
         if (d.bias) ok = ok && ((reinterpret_cast<uintptr_t>(d.bias) & 15u) == 0) && ((d.ldbias * 4) % 16 == 0);
         p.vec_ok = ok ? 1 : 0;
+        bool ok32 = ok && ((reinterpret_cast<uintptr_t>(d.D) & 31u) == 0) && ((d.ldd * des) % 32 == 0) &&
+                    ((d.d_batch_stride * des) % 32 == 0) && ((d.d_batch_stride2 * des) % 32 == 0);
+        if (d.R) {
+            const int res = d.r_dtype == CB_F32 ? 4 : 2;
+            ok32 = ok32 && ((reinterpret_cast<uintptr_t>(d.R) & 31u) == 0) && ((d.ldr * res) % 32 == 0) &&
+                   ((d.r_batch_stride * res) % 32 == 0) && ((d.r_batch_stride2 * res) % 32 == 0);
+        }
+        p.vec32_ok = ok32 ? 1 : 0;
     }
 
     // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----
