@@ -30,6 +30,19 @@ METRIC = "celeb-basis training steps/sec (SD-v1 UNet 512^2, bs=1/GPU)"
 WORKLOAD = "configs[1]: single identity per GPU, 512x512, bs=1, SD-v1 UNet + CLIP text fwd/bwd + VAE encode + CosFace R100, AdamW on the 525,312 MLP weights"
 
 
+def _ncu_traffic():
+    """DRAM bytes per cb_gemm launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches)
+    from the newest committed ncu pass under profiles/ (written by the command in its "source" field), or None."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic_*.json"))):
+        try:
+            best = json.load(open(f))
+        except Exception:
+            pass
+    return None if best is None else best.get("traffic_bytes_per_launch")
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -290,7 +303,7 @@ def run_ours(args):
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "cb_gemm_kernel (tcgen05 GEMM / implicit-GEMM conv, all instantiations)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": _ncu_traffic(),
                 "peak_source": src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": len(descs), "avg_launch_us": gemm_ms * 1e3 / len(descs),
                 "algorithmic_gflop_per_step": flops / 1e9, "gemm_ms_per_step": gemm_ms,
