@@ -17,6 +17,8 @@
 // K extent, so TMA zero-fills the rest of each 64-column box and the MMAs run on 16-column multiples.
 #include <string.h>
 
+#include <type_traits>
+
 #include "cb_common.cuh"
 
 namespace cb {
@@ -213,15 +215,25 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const int kbase = j * kBKV;
             int kvalid = min(kBKV, p.nk - kbase);
             if (p.causal) kvalid = min(kvalid, qrow - kbase + 1);
+            // row max on the raw scores (scale > 0 commutes with max); masked blocks overwrite the invalid tail with
+            // -inf first, so the exp loop below is the same for both: e = ex2(fma(s, scale*log2e, -m))
             float mx = -INFINITY;
+            if (kvalid >= kBKV) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float v = (c * 32 + i < kvalid) ? __uint_as_float(sc[c][i]) * p.scale_log2e : -INFINITY;
-                    sc[c][i] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
-                }
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sc[c][i]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float v = (c * 32 + i < kvalid) ? __uint_as_float(sc[c][i]) : -INFINITY;
+                        sc[c][i] = __float_as_uint(v);
+                        mx = fmaxf(mx, v);
+                    }
+            }
+            mx *= p.scale_log2e;
             const bool online = !(p.two_pass && full);      // running max / sum still being built
             float m_use = m;
             if (online) {
@@ -256,7 +268,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) rs += fast_exp2(__uint_as_float(sc[c][i]) - m_use);
+                    for (int i = 0; i < 32; ++i) rs += fast_exp2(fmaf(__uint_as_float(sc[c][i]), p.scale_log2e, -m_use));
                 l += rs;
                 if (vj == nstat - 1) inv_l = l > 0.f ? 1.f / l : 0.f;
                 continue;
@@ -268,6 +280,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                                        ((static_cast<long long>(img) * p.heads + head) * p.nq + qrow) * p.ldp + kbase
                                  : nullptr;
             const float pscale = p.two_pass ? inv_l : 1.f;
+            auto write_p = [&](auto scaled) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -275,7 +288,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     float e[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        e[i] = fast_exp2(__uint_as_float(sc[c][g * 8 + i]) - m_use) * pscale;
+                        e[i] = fast_exp2(fmaf(__uint_as_float(sc[c][g * 8 + i]), p.scale_log2e, -m_use));
+                        if (decltype(scaled)::value) e[i] *= pscale;
                         rs += e[i];
                     }
                     uint4 pk;
@@ -296,6 +310,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     if (prow && kbase + key8 * 8 < p.ldp) *reinterpret_cast<uint4*>(prow + key8 * 8) = pk;
                 }
             }
+            };
+            if (p.two_pass) write_p(std::true_type{}); else write_p(std::false_type{});
             if (online) l += rs;
             fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
@@ -570,25 +586,24 @@ cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_c
                         acc += fa.x * fb.x + fa.y * fb.y;
                     }
                 }
-                delta_r = acc;
+                delta_r = acc * p.scale;            // used as fma(T2, scale, -delta*scale)
                 p.delta[stat_base + xrow] = acc;
             }
         } else if (et < 64 && nit > 0) {
             const int qc = jbeg * kBKV + et;
-            if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc]; }
+            if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc] * p.scale; }
         }
         for (int it = 0; it < nit; ++it) {
             const int j = jbeg + it;
             const int cbase = j * kBKV;
-            float* st_l = s_stat + (it & 1) * 128;
-            float* st_d = st_l + 64;
+            float2* st_ld = reinterpret_cast<float2*>(s_stat) + (it & 1) * 64;     // (lse*log2e, delta*scale) per streamed query
             if (MODE == 1) {
-                if (et < 64) { st_l[et] = nlse; st_d[et] = ndelta; }
+                if (et < 64) st_ld[et] = make_float2(nlse, ndelta);
                 asm volatile("bar.sync 3, 128;" ::: "memory");
                 if (et < 64 && it + 1 < nit) {
                     const int qc = (j + 1) * kBKV + et;
                     nlse = 0.f; ndelta = 0.f;
-                    if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc]; }
+                    if (qc < p.n_stream) { nlse = p.lse[stat_base + qc] * kLog2e; ndelta = p.delta[stat_base + qc] * p.scale; }
                 }
             }
             // valid streamed items of this block for this row
@@ -614,18 +629,22 @@ cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_c
                     mbar_wait(bar_a_done, (it - 1) & 1);    // the previous block's accumulation MMAs have read the A tiles
                     tc_fence_after();
                 }
+                // P = ex2(fma(T1, scale*log2e, -lse*log2e)); dS = P * fma(T2, scale, -delta*scale).  Unmasked blocks (all
+                // but the ragged tail / the causal diagonal) skip the per-element predicates.
+                const bool masked = cvalid < kBKV || cfirst > 0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float pe[8], ds[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int c = half * 32 + g * 8 + i;
-                        const float l2 = MODE == 0 ? lse_r : st_l[c];
-                        const float dl = MODE == 0 ? delta_r : st_d[c];
-                        const bool ok = c < cvalid && c >= cfirst;
-                        const float pv = ok ? fast_exp2(__uint_as_float(t1[g * 8 + i]) * p.scale_log2e - l2) : 0.f;
+                        float l2, dl;
+                        if (MODE == 0) { l2 = lse_r; dl = delta_r; }
+                        else { const float2 sd = st_ld[c]; l2 = sd.x; dl = sd.y; }
+                        float pv = fast_exp2(fmaf(__uint_as_float(t1[g * 8 + i]), p.scale_log2e, -l2));
+                        if (masked) pv = (c < cvalid && c >= cfirst) ? pv : 0.f;
                         pe[i] = pv;
-                        ds[i] = pv * (__uint_as_float(t2[g * 8 + i]) - dl) * p.scale;
+                        ds[i] = pv * fmaf(__uint_as_float(t2[g * 8 + i]), p.scale, -dl);
                     }
                     const int key8 = half * 4 + g;
                     if (MODE == 0) {
@@ -719,7 +738,7 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
                                 void* O, long long ldo, float* lse, void* P, long long ldp, int dtype, int images,
                                 int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
     CB_REQUIRE(dtype == CB_F16 || dtype == CB_BF16, CB_ERR_ARG, "attention_fwd: dtype must be f16/bf16");
-    CB_REQUIRE(Q && K && V && O && images > 0 && heads > 0 && nq > 0 && nk > 0, CB_ERR_ARG, "attention_fwd: bad args");
+    CB_REQUIRE(Q && K && V && O && images > 0 && heads > 0 && nq > 0 && nk > 0 && scale > 0.f, CB_ERR_ARG, "attention_fwd: bad args");
     CB_REQUIRE(d >= 8 && d <= 128 && d % 8 == 0, CB_ERR_ARG, "attention_fwd: head dim %d unsupported (8..128, multiple of 8)", d);
     CB_REQUIRE((ldo * 2) % 16 == 0 && ((long long)d * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(O) & 15u) == 0,
                CB_ERR_ALIGN, "attention_fwd: O alignment");

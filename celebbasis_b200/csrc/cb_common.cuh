@@ -130,12 +130,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (context error -> host sees it) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    // the poll loop shares issue slots with the compute warps: keep it to try_wait + branch (no clock reads)
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) {  // ~4 s at 2 GHz
-            __trap();
-        }
+        if (++spins > (1u << 26)) __trap();     // seconds of polling: protocol bug
     }
 }
 
