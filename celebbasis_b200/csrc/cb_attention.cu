@@ -42,6 +42,7 @@ struct AttnParams {
     long long ldp;
     int p_is_bf16;
     unsigned idesc_s, idesc_o;
+    unsigned long long* dbg;      // profiling aid (tools/attn_timeline.py): per-CTA accumulated cycles of the softmax phases
 };
 
 template <int DBOX>  // number of 64-column boxes of the head dim (1: d <= 64, 2: d <= 128)
@@ -50,8 +51,10 @@ struct AttnCfg {
     static constexpr int kKBytes = DBOX * kBKV * 128;
     static constexpr int kVBytes = DBOX * kBKV * 128;
     static constexpr int kPBytes = kBQ * 128;              // 64 keys = one 128-byte chunk per query row
-    static constexpr int kStages = 2;
-    static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBytes + 1024 + 256;
+    // K/V ring depth: a stage is re-requested only when the P.V of its previous block has retired, so with 2 stages the
+    // TMA round trip (~1.5 us under load) was exposed once per block; 4 stages keep ~3 blocks of K/V in flight.
+    static constexpr int kStages = 3;
+    static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024 + 256;   // two P buffers
     static constexpr int kTmemCols = DBOX == 1 ? 128 : 256;   // S [0,64)  O [64, 64 + DBOX*64)
     static constexpr int kMinBlocks = 2;
 };
@@ -84,16 +87,19 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t sQ = base;
     const uint32_t sKV = sQ + Cfg::kQBytes;                                 // stage s: K at sKV + s*(K+V), V after K
     const uint32_t sP = sKV + Cfg::kStages * (Cfg::kKBytes + Cfg::kVBytes);
-    const uint32_t bars = sP + Cfg::kPBytes;
+    const uint32_t bars = sP + 2 * Cfg::kPBytes;
     // barriers: q_full, kv_full[2], kv_empty[2], s_full[2], s_empty[2], p_full, pv_done ; then the TMEM slot
     const uint32_t bar_q = bars;
+    constexpr int kSt = Cfg::kStages;
     auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
-    auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
-    const uint32_t bar_s_full = bars + 8u * 5;
-    const uint32_t bar_s_empty = bars + 8u * 7;
-    const uint32_t bar_p_full = bars + 8u * 9;
-    const uint32_t bar_pv_done = bars + 8u * 10;
-    const uint32_t tmem_slot = bars + 8u * 11;
+    auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + kSt + s); };
+    const uint32_t bar_s_full = bars + 8u * (1 + 2 * kSt);
+    const uint32_t bar_s_empty = bars + 8u * (2 + 2 * kSt);
+    // P is double-buffered (block j uses buffer j&1), each buffer with its own full / done barrier: the softmax of block
+    // j only waits for P.V of block j-2 (buffer reuse); it waits for block j-1 only when it must rescale the output tile.
+    auto bar_p_full = [&](int b) { return bars + 8u * (3 + 2 * kSt + b); };
+    auto bar_pv_done = [&](int b) { return bars + 8u * (5 + 2 * kSt + b); };
+    const uint32_t tmem_slot = bars + 8u * (7 + 2 * kSt);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ;
@@ -108,14 +114,16 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         mbar_init(bar_q, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kSt; ++s) {
             mbar_init(bar_kv_full(s), 1);
             mbar_init(bar_kv_empty(s), 1);
         }
         mbar_init(bar_s_full, 1);
         mbar_init(bar_s_empty, 128);
-        mbar_init(bar_p_full, 128);
-        mbar_init(bar_pv_done, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_p_full(b), 128);
+            mbar_init(bar_pv_done(b), 1);
+        }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
@@ -136,8 +144,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
             for (int b = 0; b < DBOX; ++b) tma_load_4d(sQ + b * (kBQ * 128), &tmQ, bar_q, b * 64, q0, head, img);
             for (int vj = 0; vj < nv; ++vj) {
-                const int s = vj & 1;
-                const uint32_t ph = (vj >> 1) & 1;
+                const int s = vj % kSt;
+                const uint32_t ph = (vj / kSt) & 1;
                 const bool full = vj >= nstat;
                 const int j = full ? vj - nstat : vj;
                 mbar_wait(bar_kv_empty(s), ph ^ 1u);
@@ -155,8 +163,8 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             // ============================ MMA issuer ============================
             const int ks_qk = p.dpad16 / 16;
             auto issue_S = [&](int vj) {
-                const int s = vj & 1;
-                mbar_wait(bar_kv_full(s), (vj >> 1) & 1);
+                const int s = vj % kSt;
+                mbar_wait(bar_kv_full(s), (vj / kSt) & 1);
                 mbar_wait(bar_s_empty, (vj & 1) ^ 1u);      // softmax has copied the previous scores to registers
                 tc_fence_after();
                 const uint32_t aK = sKV + s * (Cfg::kKBytes + Cfg::kVBytes);
@@ -175,19 +183,19 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 if (vj + 1 < nv) issue_S(vj + 1);          // next block's scores overlap this block's softmax
                 if (vj < nstat) continue;
                 const int fj = vj - nstat;
-                const int s = vj & 1;
-                mbar_wait(bar_p_full, fj & 1);
+                const int s = vj % kSt;
+                mbar_wait(bar_p_full(fj & 1), (fj >> 1) & 1);
                 tc_fence_after();
                 const uint32_t aV = sKV + s * (Cfg::kKBytes + Cfg::kVBytes) + Cfg::kKBytes;
                 for (int k = 0; k < kBKV / 16; ++k) {
                     // A = P [128 rows][64 keys] K-major: 16-key step k
-                    const uint64_t ad = umma_smem_desc_sw128(sP + k * 32, 16, 1024);
+                    const uint64_t ad = umma_smem_desc_sw128(sP + (fj & 1) * Cfg::kPBytes + k * 32, 16, 1024);
                     // B = V [128 keys][d] read MN-major: 16 keys = 2 groups of 8 rows (SBO 1024), 64-col chunks at LBO
                     const uint64_t bd = umma_smem_desc_sw128(aV + k * 2048, kBKV * 128, 1024);
                     umma_f16(tO, ad, bd, p.idesc_o, (fj > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(bar_kv_empty(s));   // K_j / V_j stage reusable
-                umma_commit(bar_pv_done);       // P buffer reusable, O stable
+                umma_commit(bar_pv_done(fj & 1));       // this P buffer reusable, O stable up to block fj
             }
         }
     } else {
@@ -201,17 +209,23 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int et = threadIdx.x - 64;
         const int ocols = DBOX * 64;
         float inv_l = 1.f;
+        unsigned tph[6] = {0, 0, 0, 0, 0, 0};
+        const bool prof = p.dbg != nullptr && et == 0;
         for (int vj = 0; vj < nv; ++vj) {
             const bool full = vj >= nstat;
             const int j = full ? vj - nstat : vj;
+            unsigned tc0 = 0, tc1;
+            if (prof) tc0 = (unsigned)clock64();
             mbar_wait(bar_s_full, vj & 1);
             tc_fence_after();
+            if (prof) { tc1 = (unsigned)clock64(); tph[0] += tc1 - tc0; tc0 = tc1; }
             uint32_t sc[2][32];
 #pragma unroll
             for (int c = 0; c < 2; ++c) tmem_ld_32x32(tS0 + lane_off + c * 32, sc[c]);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(bar_s_empty);                       // the score tile may be overwritten by S_{vj+1}
+            if (prof) { tc1 = (unsigned)clock64(); tph[1] += tc1 - tc0; tc0 = tc1; }
             const int kbase = j * kBKV;
             int kvalid = min(kBKV, p.nk - kbase);
             if (p.causal) kvalid = min(kvalid, qrow - kbase + 1);
@@ -219,10 +233,13 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             // -inf first, so the exp loop below is the same for both: e = ex2(fma(s, scale*log2e, -m))
             float mx = -INFINITY;
             if (kvalid >= kBKV) {
+                // four independent chains: a single running max is a 64-deep dependent FMNMX chain per block
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sc[c][i]));
+                    for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sc[c][i]));
+                mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             } else {
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
@@ -234,19 +251,28 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     }
             }
             mx *= p.scale_log2e;
+            if (prof) { tc1 = (unsigned)clock64(); tph[2] += tc1 - tc0; tc0 = tc1; }
             const bool online = !(p.two_pass && full);      // running max / sum still being built
             float m_use = m;
+            // wait until P.V of block jj has retired (barrier of its P buffer, phase jj>>1)
+            auto wait_pv = [&](int jj) { mbar_wait(bar_pv_done(jj & 1), (jj >> 1) & 1); tc_fence_after(); };
             if (online) {
+                // Lazy rescale: the reference maximum only moves when the block maximum exceeds it by more than 2^8
+                // (probabilities stay <= 256, exact in fp16/fp32), so the TMEM output tile is rescaled -- and the previous
+                // P.V waited for -- a handful of times per row instead of nearly every block.
                 const float m_new = fmaxf(m, mx);
-                m_use = (m_new == -INFINITY) ? 0.f : m_new;
-                const float corr = fast_exp2(m - m_use);    // 0 on the first block (m = -inf)
+                float corr = 1.f;
+                if (m == -INFINITY) {
+                    m = m_new;                               // first block: nothing accumulated yet (l = 0, O untouched)
+                } else if (m_new > m + 8.f) {
+                    corr = fast_exp2(m - m_new);
+                    m = m_new;
+                }
                 l *= corr;
                 if (full) {
-                    // one-pass mode: the previous P.V must be complete, then the TMEM output tile is rescaled
-                    if (j > 0) mbar_wait(bar_pv_done, (j - 1) & 1);
-                    tc_fence_after();
                     const bool need = __any_sync(0xffffffffu, j > 0 && corr != 1.f);   // tcgen05.ld/st are warp-collective
                     if (need) {
+                        wait_pv(j - 1);                     // the previous P.V must be complete before O is rescaled
                         for (int c = 0; c * 32 < ocols; ++c) {
                             uint32_t o[32];
                             tmem_ld_32x32(tO + lane_off + c * 32, o);
@@ -256,13 +282,13 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                             tmem_st_32x32(tO + lane_off + c * 32, o);
                         }
                         tmem_st_wait();
+                        tc_fence_before();
                     }
                 }
-                m = m_use;
-            } else if (j > 0) {
-                mbar_wait(bar_pv_done, (j - 1) & 1);        // two-pass mode: only the P buffer hand-over
-                tc_fence_after();
             }
+            m_use = (m == -INFINITY) ? 0.f : m;             // (fully masked so far: the exponent argument stays -inf)
+            if (full && j > 1) wait_pv(j - 2);              // P buffer j&1 was last read by the P.V of block j-2
+            if (prof) { tc1 = (unsigned)clock64(); tph[3] += tc1 - tc0; tc0 = tc1; }
             if (!full) {                                    // statistics pass: accumulate the row sum only
                 float rs = 0.f;
 #pragma unroll
@@ -274,7 +300,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 continue;
             }
             // P = exp2(s - m) (normalised by 1/l in two-pass mode): swizzled K-major A tile in smem (+ optional HBM copy)
-            float rs = 0.f;
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};      // independent partial row sums (no 64-deep FADD chain)
             uint16_t* prow = (p.P && row_ok)
                                  ? reinterpret_cast<uint16_t*>(p.P) +
                                        ((static_cast<long long>(img) * p.heads + head) * p.nq + qrow) * p.ldp + kbase
@@ -290,7 +316,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     for (int i = 0; i < 8; ++i) {
                         e[i] = fast_exp2(fmaf(__uint_as_float(sc[c][g * 8 + i]), p.scale_log2e, -m_use));
                         if (decltype(scaled)::value) e[i] *= pscale;
-                        rs += e[i];
+                        rs4[i & 3] += e[i];
                     }
                     uint4 pk;
                     if (p.p_is_bf16) {
@@ -303,7 +329,7 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(e[2 * i], e[2 * i + 1]);
                     }
                     const int key8 = c * 4 + g;                               // 8-key group 0..7
-                    const uint32_t dst = sP + r * 128 + ((key8 ^ (r & 7)) << 4);
+                    const uint32_t dst = sP + (j & 1) * Cfg::kPBytes + r * 128 + ((key8 ^ (r & 7)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z),
                                  "r"(pk.w)
                                  : "memory");
@@ -312,13 +338,22 @@ cb_attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
             };
             if (p.two_pass) write_p(std::true_type{}); else write_p(std::false_type{});
-            if (online) l += rs;
+            if (online) l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            if (prof) { tc1 = (unsigned)clock64(); tph[4] += tc1 - tc0; tc0 = tc1; }
             fence_proxy_async_smem();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
-            mbar_arrive(bar_p_full);
+            mbar_arrive(bar_p_full(j & 1));
+            if (prof) { tc1 = (unsigned)clock64(); tph[5] += tc1 - tc0; }
+        }
+        if (prof) {
+            unsigned long long* d = p.dbg + 8ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) d[i] = tph[i];
+            d[6] = nv;
         }
         // ---- epilogue: O / l, logsumexp ----
-        if (nblk > 0) mbar_wait(bar_pv_done, (nblk - 1) & 1);
+        if (nblk > 1) mbar_wait(bar_pv_done((nblk - 2) & 1), ((nblk - 2) >> 1) & 1);
+        if (nblk > 0) mbar_wait(bar_pv_done((nblk - 1) & 1), ((nblk - 1) >> 1) & 1);
         tc_fence_after();
         const float inv = p.two_pass ? 1.f : (l > 0.f ? 1.f / l : 0.f);
         if (row_ok && p.lse && et >= 0)
@@ -734,6 +769,10 @@ static int attn_tmap(CUtensorMap* out, int dtype, const void* ptr, long long ld,
 
 using namespace cb;
 
+static unsigned long long* g_attn_dbg = nullptr;
+// profiling hook (not part of the public header): device buffer of 8 x uint64 per CTA, or NULL to disable
+extern "C" void cb_debug_attention_timeline(void* buf) { g_attn_dbg = reinterpret_cast<unsigned long long*>(buf); }
+
 extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
                                 void* O, long long ldo, float* lse, void* P, long long ldp, int dtype, int images,
                                 int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
@@ -752,6 +791,7 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
     p.O = O; p.o_dtype = dtype; p.ldo = ldo; p.lse = lse;
     p.P = P; p.ldp = ldp; p.p_is_bf16 = dtype == CB_BF16;
     p.two_pass = P != nullptr ? 1 : 0;
+    p.dbg = g_attn_dbg;
     if (P) CB_REQUIRE(ldp >= nk && ldp % 8 == 0 && (reinterpret_cast<uintptr_t>(P) & 15u) == 0, CB_ERR_ALIGN, "attention_fwd: P row pitch must be a multiple of 8 elements >= nk");
     // S = Q K^T : M=128, N=128 keys, both K-major.  O = P V : M=128, N=dpad16, A K-major, B (V) MN-major.
     p.idesc_s = umma_idesc_f16(128, kBKV, dtype == CB_BF16, false, false);
