@@ -62,6 +62,8 @@ class _Attn:
     def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv):
         if isinstance(P, tuple):
             _, lse, out, causal = P
+            if dq is None:
+                dq = torch.empty_like(q)
             ops.attention_bwd(q, k, v, out, dO, lse, dq, dk, dv, images=images, heads=heads, dh=dh, nq=nq, nk=nk,
                               scale=scale, causal=causal)
             return
@@ -76,14 +78,16 @@ class _Attn:
                 ldd=dv.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * dO.stride(0),
                 d_is=nk * dv.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
         ops.softmax_bwd_(dP, P, images * heads * nq, nk, ldp)  # dP <- dS
-        # dQ = scale * dS K
-        ops.bmm(dP, k, dq, M=nq, N=dh, K=nk, heads=heads, images=images, lda=ldp, ldb=k.stride(0),
-                ldd=dq.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nk * k.stride(0),
-                d_is=nq * dq.stride(0), b_major=CB_MAJOR_MN, alpha=scale)
         # dK = scale * dS^T Q
         ops.bmm(dP, q, dk, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=q.stride(0),
                 ldd=dk.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * q.stride(0),
                 d_is=nk * dk.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN, alpha=scale)
+        if dq is None:
+            return
+        # dQ = scale * dS K
+        ops.bmm(dP, k, dq, M=nq, N=dh, K=nk, heads=heads, images=images, lda=ldp, ldb=k.stride(0),
+                ldd=dq.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nk * k.stride(0),
+                d_is=nq * dq.stride(0), b_major=CB_MAJOR_MN, alpha=scale)
 
 
 class UNetEngine:
@@ -274,7 +278,10 @@ class UNetEngine:
             tape.append(("xf", w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk))
         return out
 
-    def _xf_bwd(self, rec, dout, dctx):
+    def _xf_bwd(self, rec, dout, dctx, to_input=True):
+        """to_input=False: this is the first transformer block of the network -- only the context gradient is wanted, so
+        the chain stops after the cross-attention K/V gradients (what autograd prunes in the reference: x_noisy, the
+        timestep embedding and every weight before this point do not require grad)."""
         _, w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk = rec
         c, dh, H = w["c"], w["dh"], self.heads
         B, nq = geo.n, geo.hw
@@ -288,11 +295,13 @@ class UNetEngine:
         ops.layernorm_bwd(dl3, h2, w["ln3g"], s3, dx=dr, accumulate=True)
         # cross attention
         dO = ops.linear_dgrad(ops.cast(dr, self.dt), w["wo2"])
-        dq2 = torch.empty_like(q2)
+        dq2 = torch.empty_like(q2) if to_input else None
         dkv2 = torch.empty_like(kv2)
         _Attn.bwd(dO, q2, kv2[:, :c], kv2[:, c:], P2, images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale,
                   dq=dq2, dk=dkv2[:, :c], dv=dkv2[:, c:])
         ops.linear_dgrad(dkv2, w["wkv2"], out=dctx, residual=dctx)
+        if not to_input:
+            return None
         dl2 = ops.linear_dgrad(dq2, w["wq2"])
         ops.layernorm_bwd(dl2, h1, w["ln2g"], s2, dx=dr, accumulate=True)
         # self attention
@@ -401,12 +410,19 @@ class UNetEngine:
         da16, _ = ops.conv2d_dgrad(dy16, geo, self.out_w, self.mc, cout_rows=self.out_pad)
         dh = ops.groupnorm_bwd(da16, h_head, geo, self.out_g, self.out_b, sto, silu=True, dx_dtype=torch.float32)
         dskips = []
+        first_xf = next((i for i, r in enumerate(tape) if r[0] == "xf"), -1)
         while tape:
             rec = tape.pop()
             k = rec[0]
             if k == "res":
                 dh = self._res_bwd(rec, dh)
             elif k == "xf":
+                if len(tape) == first_xf:
+                    # first transformer block in forward order: nothing before it (stem, ResBlock, its own self-attention)
+                    # depends on the context, so the backward pass ends with its cross-attention K/V gradients
+                    self._xf_bwd(rec, dh, dctx, to_input=False)
+                    tape.clear()
+                    break
                 dh = self._xf_bwd(rec, dh, dctx)
             elif k == "down":
                 dh = self._down_bwd(rec, dh)
