@@ -85,16 +85,17 @@ class CLIPTextEngine:
         scale = dh ** -0.5
         dys = ops.axpby(dctx, S)
         dh_ = ops.layernorm_bwd(dys, h_last, self.fg, sf, dx_dtype=torch.float32)
+        dh16 = ops.cast(dh_, self.dt)     # 16-bit copy of the running gradient; the LayerNorm-backward kernels keep it current
         while tape:
             L, h, s1, qkv, P, h1, s2, f = tape.pop()
-            da = ops.linear_dgrad(ops.cast(dh_, self.dt), L["w2"])
+            da = ops.linear_dgrad(dh16, L["w2"])
             df = ops.act_bwd(da, f, CB_ACT_QUICK_GELU)
             dl2 = ops.linear_dgrad(df, L["w1"])
-            ops.layernorm_bwd(dl2, h1, L["ln2g"], s2, dx=dh_, accumulate=True)
-            dO = ops.linear_dgrad(ops.cast(dh_, self.dt), L["wo"])
+            ops.layernorm_bwd(dl2, h1, L["ln2g"], s2, dx=dh_, accumulate=True, dx_lp=dh16)
+            dO = ops.linear_dgrad(dh16, L["wo"])
             dqkv = torch.empty_like(qkv)
             _Attn.bwd(dO, qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], P, images=batch, heads=H, dh=dh, nq=T, nk=T,
                       scale=scale, dq=dqkv[:, :c], dk=dqkv[:, c:2 * c], dv=dqkv[:, 2 * c:])
             dl1 = ops.linear_dgrad(dqkv, L["wqkv"])
-            ops.layernorm_bwd(dl1, h, L["ln1g"], s1, dx=dh_, accumulate=True)
+            ops.layernorm_bwd(dl1, h, L["ln1g"], s1, dx=dh_, accumulate=True, dx_lp=dh16)
         return ops.axpby(dh_, 1.0 / S)

@@ -38,6 +38,7 @@ struct GemmParams {
     int batch_inner;
     int d_transposed;
     int vec_ok;
+    int force_stages;  // 0 auto / 3 / 6 (cb_gemm_desc.stages)
     int vec32_ok;     // D (and R) rows are 32-byte aligned: 256-bit LDG/STG (sm_100) in the epilogue
     const float* bias;
     int bias_row_div;
@@ -653,7 +654,8 @@ CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    static const int force = getenv("CB_GEMM_STAGES") ? atoi(getenv("CB_GEMM_STAGES")) : 0;   // tuning aid
+    static const int env_force = getenv("CB_GEMM_STAGES") ? atoi(getenv("CB_GEMM_STAGES")) : 0;   // tuning aid
+    const int force = p.force_stages ? p.force_stages : env_force;
     if (force == 3) return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
     if (force == 6 || ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
     return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
@@ -862,6 +864,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     }
 
     // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----
+    p.force_stages = (d.stages == 3 || d.stages == 6) ? d.stages : 0;
     p.splits = 1;
     p.kiters_per_split = p.taps * p.kchunks;
     {

@@ -587,8 +587,8 @@ ln_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restr
 template <typename TX, typename TG, typename TD>
 __global__ void __launch_bounds__(128)
 ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
-              const float* __restrict__ mean, const float* __restrict__ rstd, TD* __restrict__ dx, int M, int C,
-              int accumulate) {
+              const float* __restrict__ mean, const float* __restrict__ rstd, TD* __restrict__ dx, TG* __restrict__ dx_lp,
+              int M, int C, int accumulate) {
     pdl_sync();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -631,6 +631,7 @@ ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* 
                 o.y += p.y;
             }
             Vec2<TD>::st(or_ + c, o);
+            if (dx_lp) Vec2<TG>::st(dx_lp + (size_t)row * C + c, o);     // 16-bit copy for the GEMM that consumes dx next
         }
     }
 }
@@ -775,18 +776,18 @@ CB_LAUNCH((ln_fwd_kernel<TX, TY>), grid, 128, 0, st, (const TX*)x, (TY*)y, gamma
 }
 
 extern "C" int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
-                                const float* mean, const float* rstd, void* dx, int dx_dtype, int M, int C,
+                                const float* mean, const float* rstd, void* dx, int dx_dtype, void* dx_lp, int M, int C,
                                 int accumulate, void* stream) {
     CB_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && C <= 64 * kLnMaxPairsPerLane, CB_ERR_ARG, "layernorm_bwd: bad shape M=%d C=%d", M, C);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(ceil_div(M, 4));
     if (dx_dtype == CB_F32) {
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-CB_LAUNCH((ln_bwd_kernel<TX, TG, float>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (float*)dx, M, C, accumulate)));
+CB_LAUNCH((ln_bwd_kernel<TX, TG, float>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (float*)dx, (TG*)dx_lp, M, C, accumulate)));
     } else {
         CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "layernorm_bwd: dx dtype must be f32 or equal dy dtype");
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-CB_LAUNCH((ln_bwd_kernel<TX, TG, TG>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, M, C, accumulate)));
+CB_LAUNCH((ln_bwd_kernel<TX, TG, TG>), grid, 128, 0, st, (const TG*)dy, (const TX*)x, gamma, mean, rstd, (TG*)dx, (TG*)dx_lp, M, C, accumulate)));
     }
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);

@@ -89,14 +89,18 @@ def _autotune(d, key):
     taps = d.kh * d.kw if d.conv else 1
     kiters = taps * ((d.K + 63) // 64)
     bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
-    cands = [(0, 0)]
+    cands = [(0, 0, 0)]
     for bn in bns:
         tiles = ((d.N + bn - 1) // bn) * ((M + 127) // 128) * d.batch
-        cands.append((bn, 1))
+        cands.append((bn, 1, 0))
+        if tiles <= 148:
+            cands.append((bn, 1, 3))          # 3-stage ring: leaves room for the next kernel's CTAs on the SM
         if tiles < 148:
             for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
                 if tiles * sp <= 320 and kiters // sp >= 2:
-                    cands.append((bn, sp))
+                    cands.append((bn, sp, 0))
+                    if tiles * sp <= 148:
+                        cands.append((bn, sp, 3))
     t = GemmDesc.from_buffer_copy(bytes(d))
     # scratch output large enough for any addressing the descriptor can produce
     inner = d.batch_inner if d.batch_inner > 0 else d.batch
@@ -121,8 +125,8 @@ def _autotune(d, key):
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         sp_ = ctypes.c_void_p(side.cuda_stream)
-        for bn, sp in cands:
-            t.tile_n, t.splits = bn, sp
+        for bn, sp, stg in cands:
+            t.tile_n, t.splits, t.stages = bn, sp, stg
             if L.cb_gemm(ctypes.byref(t), sp_) != 0:
                 continue
             g = torch.cuda.CUDAGraph()
@@ -141,23 +145,23 @@ def _autotune(d, key):
                 e1.record(side)
                 e1.synchronize()
                 best = min(best, e0.elapsed_time(e1) * 125.0)     # us per launch
-            times[(bn, sp)] = best
+            times[(bn, sp, stg)] = best
             del g
     cur.wait_stream(side)
-    base = times.get((0, 0), 1e9)
-    win = min(times, key=times.get) if times else (0, 0)
+    base = times.get((0, 0, 0), 1e9)
+    win = min(times, key=times.get) if times else (0, 0, 0)
     if times.get(win, 1e9) > 0.97 * base:     # keep the library's own choice unless the gain is real
-        win = (0, 0)
+        win = (0, 0, 0)
     _TUNE[key] = win
     if TUNE_LOG is not None:
-        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}": round(v, 2) for k, v in times.items()}, win))
+        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}": round(v, 2) for k, v in times.items()}, win))
     log_path = os.environ.get("CB_GEMM_TUNE_LOG")
     if log_path:
         import json
         with open(log_path, "a") as f:
             f.write(json.dumps({"M": M, "N": d.N, "K": d.K, "batch": d.batch, "conv": d.conv, "kh": d.kh, "b_major": d.b_major,
                                 "a_major": d.a_major, "d_dtype": d.d_dtype, "win": list(win),
-                                "us": {f"{k[0]}x{k[1]}": round(v, 2) for k, v in times.items()}}) + "\n")
+                                "us": {f"{k[0]}x{k[1]}s{k[2]}": round(v, 2) for k, v in times.items()}}) + "\n")
     return win
 
 
@@ -166,13 +170,13 @@ def _gemm(d, what):
     d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     if GEMM_DEBUG_TIMELINE is not None:
         d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
-    if AUTOTUNE and d.tile_n == 0 and d.splits == 0:
+    if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0:
         key = _tune_key(d)
         win = _TUNE.get(key)
         if win is None and not torch.cuda.is_current_stream_capturing():
             win = _autotune(d, key)
         if win is not None:
-            d.tile_n, d.splits = win
+            d.tile_n, d.splits, d.stages = win
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M
@@ -402,13 +406,13 @@ def layernorm(x, gamma, beta, *, eps=1e-5, out_dtype=torch.float16):
     return y, NormStats(mean, rstd)
 
 
-def layernorm_bwd(dy, x, gamma, stats, *, dx=None, accumulate=False, dx_dtype=torch.float32):
+def layernorm_bwd(dy, x, gamma, stats, *, dx=None, accumulate=False, dx_dtype=torch.float32, dx_lp=None):
     M, C = x.shape
     if dx is None:
         dx = torch.empty(M, C, dtype=dx_dtype, device=x.device)
         accumulate = False
     _lib.check(_L().cb_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(stats.mean), _p(stats.rstd),
-                                     _p(dx), _dt(dx), M, C, 1 if accumulate else 0, _st()), "cb_layernorm_bwd")
+                                     _p(dx), _dt(dx), _p(dx_lp), M, C, 1 if accumulate else 0, _st()), "cb_layernorm_bwd")
     return dx
 
 

@@ -292,9 +292,10 @@ class UNetEngine:
         du = ops.linear_dgrad(ops.cast(dr, self.dt), w["wff2"])
         dg = ops.geglu_bwd(du, g16)
         dl3 = ops.linear_dgrad(dg, w["wff1"])
-        ops.layernorm_bwd(dl3, h2, w["ln3g"], s3, dx=dr, accumulate=True)
+        dr16 = torch.empty(dr.shape, dtype=self.dt, device=self.dev)      # 16-bit copy of the running gradient, written
+        ops.layernorm_bwd(dl3, h2, w["ln3g"], s3, dx=dr, accumulate=True, dx_lp=dr16)   # by the kernel that updates it
         # cross attention
-        dO = ops.linear_dgrad(ops.cast(dr, self.dt), w["wo2"])
+        dO = ops.linear_dgrad(dr16, w["wo2"])
         dq2 = torch.empty_like(q2) if to_input else None
         dkv2 = torch.empty_like(kv2)
         _Attn.bwd(dO, q2, kv2[:, :c], kv2[:, c:], P2, images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale,
@@ -303,16 +304,16 @@ class UNetEngine:
         if not to_input:
             return None
         dl2 = ops.linear_dgrad(dq2, w["wq2"])
-        ops.layernorm_bwd(dl2, h1, w["ln2g"], s2, dx=dr, accumulate=True)
+        ops.layernorm_bwd(dl2, h1, w["ln2g"], s2, dx=dr, accumulate=True, dx_lp=dr16)
         # self attention
-        dO = ops.linear_dgrad(ops.cast(dr, self.dt), w["wo1"])
+        dO = ops.linear_dgrad(dr16, w["wo1"])
         dqkv = torch.empty_like(qkv)
         _Attn.bwd(dO, qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], P1, images=B, heads=H, dh=dh, nq=nq, nk=nq,
                   scale=scale, dq=dqkv[:, :c], dk=dqkv[:, c:2 * c], dv=dqkv[:, 2 * c:])
         dl1 = ops.linear_dgrad(dqkv, w["wqkv"])
-        ops.layernorm_bwd(dl1, h0, w["ln1g"], s1, dx=dr, accumulate=True)
+        ops.layernorm_bwd(dl1, h0, w["ln1g"], s1, dx=dr, accumulate=True, dx_lp=dr16)
         # proj_in + group norm
-        dn = ops.linear_dgrad(ops.cast(dr, self.dt), w["wpi"])
+        dn = ops.linear_dgrad(dr16, w["wpi"])
         ops.groupnorm_bwd(dn, x, geo, w["gn"], w["bn"], stn, silu=False, dx=dx, accumulate=True)
         return dx
 

@@ -143,6 +143,8 @@ typedef struct cb_gemm_desc {
      * (celebbasis_b200/ops.py) times the candidates once per shape and passes the winner here. */
     int32_t tile_n;
     int32_t splits;
+    int32_t stages;      /* 0 = auto, 3 = 3-stage ring / 2 CTAs per SM, 6 = 6-stage ring / 1 CTA per SM */
+    int32_t reserved0;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
@@ -167,8 +169,10 @@ int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      int C, int G, int act_silu, int accumulate, double* ws, void* stream);
 int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, int M,
                      int C, float eps, float* mean_out, float* rstd_out, void* stream);
+/* dx_lp (optional): a second copy of the final dx in dy's 16-bit dtype, for the GEMM that consumes it next */
 int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
-                     const float* rstd, void* dx, int dx_dtype, int M, int C, int accumulate, void* stream);
+                     const float* rstd, void* dx, int dx_dtype, void* dx_lp, int M, int C, int accumulate,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pointwise / row-wise kernels.

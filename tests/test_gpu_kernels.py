@@ -159,6 +159,11 @@ def test_layernorm_fwd_bwd(dev, m, c):
     yr = F.layer_norm(xr, (c,), g, b, 1e-5)
     yr.backward(dy.float())
     assert rel(y, yr) < 1e-3 and rel(dx, xr.grad) < 1e-3
+    # accumulate into a running fp32 gradient and emit its 16-bit copy in the same launch
+    acc = torch.ones_like(dx)
+    lp = torch.full((m, c), float("nan"), dtype=torch.float16, device="cuda")
+    ops.layernorm_bwd(dy, x, g, st, dx=acc, accumulate=True, dx_lp=lp)
+    assert rel(acc, dx + 1) < 1e-5 and rel(lp, acc) < 1e-3
 
 
 # ---------------------------------------------------------------------------------------------------- pointwise
