@@ -437,6 +437,8 @@ struct AttnBwdParams {
     long long ld1, ld2;
     int is_bf16;
     int nq;                  // query count (lse / delta row pitch)
+    void* dS;                // MODE 0, optional: dS = P o (dP - delta) * scale exported as [images*heads][nq][ldds] (16-bit)
+    long long ldds;
     unsigned idesc_t, idesc_acc;
 };
 
@@ -453,7 +455,7 @@ struct AttnBwdCfg {
     static constexpr int kMinBlocks = (kTmemCols <= 256 && kSmemBytes <= 110 * 1024) ? 2 : 1;
 };
 
-__device__ __forceinline__ void store_a16(uint32_t tile, int r, int key8, const float (&e)[8], bool bf16) {
+__device__ __forceinline__ uint4 store_a16(uint32_t tile, int r, int key8, const float (&e)[8], bool bf16) {
     uint4 pk;
     if (bf16) {
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
@@ -466,6 +468,7 @@ __device__ __forceinline__ void store_a16(uint32_t tile, int r, int key8, const 
     }
     const uint32_t dst = tile + r * 128 + ((key8 ^ (r & 7)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+    return pk;
 }
 
 template <int DBOX, int MODE>
@@ -683,7 +686,9 @@ cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_c
                     }
                     const int key8 = half * 4 + g;
                     if (MODE == 0) {
-                        store_a16(sA, r, key8, ds, p.is_bf16 != 0);
+                        const uint4 pk = store_a16(sA, r, key8, ds, p.is_bf16 != 0);
+                        if (p.dS && row_ok && cbase + key8 * 8 < p.ldds)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dS) + (stat_base + xrow) * p.ldds + cbase + key8 * 8) = pk;
                     } else {
                         store_a16(sA, r, key8, pe, p.is_bf16 != 0);
                         store_a16(sA + Cfg::kABytes, r, key8, ds, p.is_bf16 != 0);
@@ -694,6 +699,14 @@ cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_c
             tc_fence_before();
             mbar_arrive(bar_a_full);
         }
+        if (MODE == 0 && p.dS && row_ok) {
+            // causal: key blocks past this tile's last query were never visited -- their dS is zero
+            const int nblk_all = (p.n_stream + kBKV - 1) / kBKV;
+            uint16_t* dsrow = reinterpret_cast<uint16_t*>(p.dS) + (stat_base + xrow) * p.ldds;
+            for (int j = jend; j < nblk_all; ++j)
+                for (int key8 = 0; key8 < 8; ++key8)
+                    if (j * kBKV + key8 * 8 < p.ldds) *reinterpret_cast<uint4*>(dsrow + j * kBKV + key8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
         // ---- epilogue: accumulators -> HBM ----
         if (nit > 0) mbar_wait(bar_a_done, (nit - 1) & 1);
         tc_fence_after();
@@ -701,6 +714,7 @@ cb_attention_bwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_c
         for (int a = 0; a < Cfg::kNumAcc; ++a) {
             const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
             uint16_t* outp = reinterpret_cast<uint16_t*>(a == 0 ? p.out1 : p.out2);
+            if (outp == nullptr) continue;
             const long long ldout = a == 0 ? p.ld1 : p.ld2;
             for (int c = 0; c * 32 < DBOX * 64; ++c) {
                 if (c * 32 >= p.d) break;
@@ -821,19 +835,22 @@ extern "C" int cb_attention_fwd(const void* Q, long long ldq, const void* K, lon
     return launch_attn<2>(tq, tk, tv, p, grid, st);
 }
 
-extern "C" int cb_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
-                                const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
-                                void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, int dtype,
-                                int images, int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
+static int attention_bwd_impl(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                              const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
+                              void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, void* dS,
+                              long long ldds, bool run_dq, bool run_dkdv, int dtype, int images, int heads, int nq, int nk,
+                              int d, float scale, int causal, void* stream) {
     CB_REQUIRE(dtype == CB_F16 || dtype == CB_BF16, CB_ERR_ARG, "attention_bwd: dtype must be f16/bf16");
-    CB_REQUIRE(Q && K && V && O && dO && lse && delta && dQ && dK && dV && images > 0 && heads > 0 && nq > 0 && nk > 0,
+    CB_REQUIRE(Q && K && V && O && dO && lse && delta && images > 0 && heads > 0 && nq > 0 && nk > 0 && scale > 0.f,
                CB_ERR_ARG, "attention_bwd: bad args");
+    CB_REQUIRE(!run_dkdv || (dK && dV), CB_ERR_ARG, "attention_bwd: dK/dV required");
     CB_REQUIRE(d >= 8 && d <= 128 && d % 8 == 0, CB_ERR_ARG, "attention_bwd: head dim %d unsupported (8..128, multiple of 8)", d);
     const void* ptrs[8] = {Q, K, V, O, dO, dQ, dK, dV};
     const long long lds[8] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv};
     for (int i = 0; i < 8; ++i)
-        CB_REQUIRE((lds[i] * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15u) == 0, CB_ERR_ALIGN,
+        CB_REQUIRE(ptrs[i] == nullptr || ((lds[i] * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15u) == 0), CB_ERR_ALIGN,
                    "attention_bwd: operand %d must be 16-byte aligned with a 16-byte multiple row pitch", i);
+    if (dS) CB_REQUIRE(ldds >= nk && ldds % 8 == 0 && (reinterpret_cast<uintptr_t>(dS) & 15u) == 0, CB_ERR_ALIGN, "attention_bwd: dS row pitch must be a multiple of 8 elements >= nk");
     AttnBwdParams p;
     memset(&p, 0, sizeof(p));
     p.heads = heads; p.images = images; p.d = d; p.dpad16 = (d + 15) / 16 * 16; p.dboxes = d <= 64 ? 1 : 2;
@@ -844,27 +861,45 @@ extern "C" int cb_attention_bwd(const void* Q, long long ldq, const void* K, lon
     p.idesc_acc = umma_idesc_f16(128, p.dboxes * 64, dtype == CB_BF16, false, true);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap x1, x2, y1, y2;
-    int rc;
-    // ---- MODE 0: dQ (+ delta) ----
-    if ((rc = attn_tmap(&x1, dtype, Q, ldq, nq, d, heads, images, kBQ))) return rc;
-    if ((rc = attn_tmap(&x2, dtype, dO, lddo, nq, d, heads, images, kBQ))) return rc;
-    if ((rc = attn_tmap(&y1, dtype, K, ldk, nk, d, heads, images, kBKV))) return rc;
-    if ((rc = attn_tmap(&y2, dtype, V, ldv, nk, d, heads, images, kBKV))) return rc;
-    p.n_stat = nq; p.n_stream = nk; p.out1 = dQ; p.ld1 = lddq; p.out2 = nullptr; p.ld2 = 0;
-    {
+    int rc = 0;
+    if (run_dq) {
+        // ---- MODE 0: dQ (+ delta, + optional dS export) ----
+        if ((rc = attn_tmap(&x1, dtype, Q, ldq, nq, d, heads, images, kBQ))) return rc;
+        if ((rc = attn_tmap(&x2, dtype, dO, lddo, nq, d, heads, images, kBQ))) return rc;
+        if ((rc = attn_tmap(&y1, dtype, K, ldk, nk, d, heads, images, kBKV))) return rc;
+        if ((rc = attn_tmap(&y2, dtype, V, ldv, nk, d, heads, images, kBKV))) return rc;
+        p.n_stat = nq; p.n_stream = nk; p.out1 = dQ; p.ld1 = lddq; p.out2 = nullptr; p.ld2 = 0; p.dS = dS; p.ldds = ldds;
         dim3 grid((unsigned)ceil_div(nq, kBQ), (unsigned)heads, (unsigned)images);
         rc = p.dboxes == 1 ? launch_attn_bwd<1, 0>(x1, x2, y1, y2, p, grid, st) : launch_attn_bwd<2, 0>(x1, x2, y1, y2, p, grid, st);
         if (rc) return rc;
     }
-    // ---- MODE 1: dK, dV ----
-    if ((rc = attn_tmap(&x1, dtype, K, ldk, nk, d, heads, images, kBQ))) return rc;
-    if ((rc = attn_tmap(&x2, dtype, V, ldv, nk, d, heads, images, kBQ))) return rc;
-    if ((rc = attn_tmap(&y1, dtype, Q, ldq, nq, d, heads, images, kBKV))) return rc;
-    if ((rc = attn_tmap(&y2, dtype, dO, lddo, nq, d, heads, images, kBKV))) return rc;
-    p.n_stat = nk; p.n_stream = nq; p.out1 = dV; p.ld1 = lddv; p.out2 = dK; p.ld2 = lddk;
-    {
+    if (run_dkdv) {
+        // ---- MODE 1: dK, dV ----
+        if ((rc = attn_tmap(&x1, dtype, K, ldk, nk, d, heads, images, kBQ))) return rc;
+        if ((rc = attn_tmap(&x2, dtype, V, ldv, nk, d, heads, images, kBQ))) return rc;
+        if ((rc = attn_tmap(&y1, dtype, Q, ldq, nq, d, heads, images, kBKV))) return rc;
+        if ((rc = attn_tmap(&y2, dtype, dO, lddo, nq, d, heads, images, kBKV))) return rc;
+        p.n_stat = nk; p.n_stream = nq; p.out1 = dV; p.ld1 = lddv; p.out2 = dK; p.ld2 = lddk; p.dS = nullptr; p.ldds = 0;
         dim3 grid((unsigned)ceil_div(nk, kBQ), (unsigned)heads, (unsigned)images);
         rc = p.dboxes == 1 ? launch_attn_bwd<1, 1>(x1, x2, y1, y2, p, grid, st) : launch_attn_bwd<2, 1>(x1, x2, y1, y2, p, grid, st);
     }
     return rc;
+}
+
+extern "C" int cb_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                                const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
+                                void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, int dtype,
+                                int images, int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
+    CB_REQUIRE(dQ != nullptr, CB_ERR_ARG, "attention_bwd: dQ required");
+    return attention_bwd_impl(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, dK, lddk, dV, lddv, nullptr, 0,
+                              true, true, dtype, images, heads, nq, nk, d, scale, causal, stream);
+}
+
+extern "C" int cb_attention_bwd_dq(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                                   const void* O, long long ldo, const void* dO, long long lddo, const float* lse,
+                                   float* delta, void* dQ, long long lddq, void* dS, long long ldds, int dtype, int images,
+                                   int heads, int nq, int nk, int d, float scale, int causal, void* stream) {
+    CB_REQUIRE(dQ != nullptr || dS != nullptr, CB_ERR_ARG, "attention_bwd_dq: nothing to compute");
+    return attention_bwd_impl(Q, ldq, K, ldk, V, ldv, O, ldo, dO, lddo, lse, delta, dQ, lddq, nullptr, 0, nullptr, 0, dS, ldds,
+                              true, false, dtype, images, heads, nq, nk, d, scale, causal, stream);
 }

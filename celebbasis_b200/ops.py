@@ -663,6 +663,16 @@ def attention_fwd(q, k, v, out, *, images, heads, dh, nq, nk, scale, causal=Fals
     return P, lse
 
 
+def attention_bwd_dq(q, k, v, o, dO, lse, dq, dS, *, images, heads, dh, nq, nk, scale, causal=False):
+    """Query-stationary half of the flash backward (cb_attention_bwd_dq): dq (or None) and, optionally, the scaled score
+    gradient dS [images*heads*nq][ldds] for GEMM-based dK / dV (short key sequences)."""
+    delta = torch.empty(images * heads * nq, dtype=torch.float32, device=q.device)
+    _lib.check(_L().cb_attention_bwd_dq(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0),
+                                        _p(dO), dO.stride(0), _p(lse), _p(delta), _p(dq), dq.stride(0) if dq is not None else 0,
+                                        _p(dS), dS.shape[1] if dS is not None else 0, _dt(q), images, heads, nq, nk, dh,
+                                        scale, 1 if causal else 0, _st()), "cb_attention_bwd_dq")
+
+
 def attention_bwd(q, k, v, o, dO, lse, dq, dk, dv, *, images, heads, dh, nq, nk, scale, causal=False):
     """Flash attention backward (cb_attention_bwd): dq/dk/dv from q, k, v, the forward output o, its gradient dO and the
     forward log-sum-exp; all operands are row-strided 2-D views with head h in columns [h*dh, (h+1)*dh)."""

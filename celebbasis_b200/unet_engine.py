@@ -44,6 +44,12 @@ class _Attn:
                 _, lse = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
                                            causal=causal, want_lse=True)
                 return ("lse", lse, out, causal)
+            if need_p and _Attn.FLASH_BWD:
+                # short key sequence (cross attention): keep P and lse; the backward rebuilds dS in TMEM (dQ kernel) and
+                # exports it, dK / dV are two small GEMMs over P and dS
+                P, lse = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
+                                           causal=causal, want_p=True, want_lse=True)
+                return ("p+lse", P, lse, out, causal)
             P, _ = ops.attention_fwd(q, k, v, out, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
                                      causal=causal, want_p=need_p)
             return P
@@ -60,6 +66,20 @@ class _Attn:
 
     @staticmethod
     def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv):
+        if isinstance(P, tuple) and P[0] == "p+lse":
+            _, Pm, lse, out, causal = P
+            ldp = Pm.shape[1]
+            dS = torch.empty_like(Pm)
+            ops.attention_bwd_dq(q, k, v, out, dO, lse, dq, dS, images=images, heads=heads, dh=dh, nq=nq, nk=nk,
+                                 scale=scale, causal=causal)
+            # dV = P^T dO ; dK = dS^T Q (dS already carries the softmax scale)
+            ops.bmm(Pm, dO, dv, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=dO.stride(0),
+                    ldd=dv.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * dO.stride(0),
+                    d_is=nk * dv.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+            ops.bmm(dS, q, dk, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=q.stride(0),
+                    ldd=dk.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * q.stride(0),
+                    d_is=nk * dk.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+            return
         if isinstance(P, tuple):
             _, lse, out, causal = P
             if dq is None:

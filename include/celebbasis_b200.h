@@ -299,6 +299,15 @@ int cb_attention_bwd(const void* Q, long long ldq, const void* K, long long ldk,
                      void* dQ, long long lddq, void* dK, long long lddk, void* dV, long long lddv, int dtype, int images,
                      int heads, int nq, int nk, int d, float scale, int causal, void* stream);
 
+/* Query-stationary half only: dQ (optional) and, optionally, dS = P o (dP - delta) * scale exported as
+ * [images*heads][nq][ldds] (16-bit, ldds a multiple of 8 >= nk) -- for short key sequences (cross attention on the 77
+ * prompt tokens, attention.py:170-193 with context=cond), where dK = dS^T Q and dV = P^T dO are better done as two small
+ * cb_gemm launches over the exported dS and the forward's P than by 8 key-stationary CTAs. */
+int cb_attention_bwd_dq(const void* Q, long long ldq, const void* K, long long ldk, const void* V, long long ldv,
+                        const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
+                        void* dQ, long long lddq, void* dS, long long ldds, int dtype, int images, int heads, int nq,
+                        int nk, int d, float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,6 +318,18 @@ def test_flash_attention_bwd(dev, nq, nk, dh, heads, images, causal):
     for name, got, ref in (("dq", dq, back(qf.grad, nq)), ("dk", dk, back(kf.grad, nk)), ("dv", dv, back(vf.grad, nk))):
         assert torch.isfinite(got.float()).all(), name
         assert rel(got, ref) < 6e-3, (name, rel(got, ref))
+    # query-stationary half alone, exporting dS = P o (dP - delta) * scale (the cross-attention backward's GEMM operand)
+    ldds = (nk + 7) // 8 * 8
+    dS = torch.full((images * heads * nq, ldds), float("nan"), dtype=torch.float16, device="cuda")
+    dq2 = torch.empty(images * nq, C, dtype=torch.float16, device="cuda")
+    ops.attention_bwd_dq(q, k, v, o, dO, lse, dq2, dS, images=images, heads=heads, dh=dh, nq=nq, nk=nk, scale=scale,
+                         causal=causal)
+    att = torch.softmax(sc.detach(), -1)
+    dP = sp(dO, nq) @ sp(v, nk).transpose(-1, -2)
+    dS_ref = att * (dP - (dP * att).sum(-1, keepdim=True)) * scale
+    assert rel(dq2, back(qf.grad, nq)) < 6e-3
+    assert rel(dS.view(images, heads, nq, ldds)[..., :nk], dS_ref) < 8e-3
+    assert float(dS.view(images, heads, nq, ldds)[..., nk:].abs().max() if ldds > nk else 0) == 0
 
 
 @pytest.mark.parametrize("nq,nk,dh,heads,images,causal", [(4096, 4096, 40, 8, 1, False), (1024, 1024, 80, 8, 1, False),
