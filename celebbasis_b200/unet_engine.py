@@ -147,6 +147,8 @@ class UNetEngine:
 
         emb_ws, emb_bs = [], []
         self._emb_off = 0
+        kvw = []              # cross-attention to_k / to_v of every transformer block: ONE [sum 2C][768] GEMM per step
+        self._kv_off = 0
 
         def res(prefix, cin, cout):
             w = {"kind": "res", "cin": cin, "cout": cout}
@@ -177,7 +179,9 @@ class UNetEngine:
                                              g(tb + "attn1.to_v.weight")], 0))
             w["wo1"], w["bo1"] = self._w16(g(tb + "attn1.to_out.0.weight")), self._f32(g(tb + "attn1.to_out.0.bias"))
             w["wq2"] = self._w16(g(tb + "attn2.to_q.weight"))
-            w["wkv2"] = self._w16(torch.cat([g(tb + "attn2.to_k.weight"), g(tb + "attn2.to_v.weight")], 0))
+            kvw.append(torch.cat([g(tb + "attn2.to_k.weight"), g(tb + "attn2.to_v.weight")], 0))
+            w["kv_off"] = self._kv_off          # this block's [K | V] columns in the batched context projection
+            self._kv_off += 2 * c
             w["wo2"], w["bo2"] = self._w16(g(tb + "attn2.to_out.0.weight")), self._f32(g(tb + "attn2.to_out.0.bias"))
             w["wff1"], w["bff1"] = self._w16(g(tb + "ff.net.0.proj.weight")), self._f32(g(tb + "ff.net.0.proj.bias"))
             w["wff2"], w["bff2"] = self._w16(g(tb + "ff.net.2.weight")), self._f32(g(tb + "ff.net.2.bias"))
@@ -225,6 +229,8 @@ class UNetEngine:
                     ds //= 2
                 self.output_blocks.append(layers)
                 idx += 1
+        self.wkv_all = self._w16(torch.cat(kvw, 0)) if kvw else None
+        del kvw
         # head
         self.out_g, self.out_b = self._f32(g("out.0.weight")), self._f32(g("out.0.bias"))
         self.out_w = ops.pack_conv_weight(g("out.2.weight").to(self.dev), self.dt, cout_pad=self.out_pad)
@@ -268,9 +274,9 @@ class UNetEngine:
         ops.groupnorm_bwd(da16, x, geo, w["g1"], w["b1"], st1, silu=True, dx=dx, accumulate=True)
         return dx
 
-    def _xf_fwd(self, w, x, geo, ctx16, tape):
+    def _xf_fwd(self, w, x, geo, kv_all, tape):
         c, dh, H = w["c"], w["dh"], self.heads
-        B, nq, nk = geo.n, geo.hw, ctx16.shape[0] // geo.n
+        B, nq, nk = geo.n, geo.hw, kv_all.shape[0] // geo.n
         scale = dh ** -0.5
         n16, stn = ops.groupnorm(x, geo, w["gn"], w["bn"], eps=1e-6, silu=False, out_dtype=self.dt)
         h0 = ops.linear(n16, w["wpi"], w["bpi"], out_dtype=torch.float32)
@@ -284,7 +290,7 @@ class UNetEngine:
         # cross attention
         l2, s2 = ops.layernorm(h1, w["ln2g"], w["ln2b"], out_dtype=self.dt)
         q2 = ops.linear(l2, w["wq2"])
-        kv2 = ops.linear(ctx16, w["wkv2"])
+        kv2 = kv_all[:, w["kv_off"]:w["kv_off"] + 2 * c]       # K | V of this block (projected once for all blocks)
         o2 = torch.empty(geo.rows, c, dtype=self.dt, device=self.dev)
         P2 = _Attn.fwd(q2, kv2[:, :c], kv2[:, c:], images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale, out=o2)
         h2 = ops.linear(o2, w["wo2"], w["bo2"], out_dtype=torch.float32, residual=h1)
@@ -298,7 +304,7 @@ class UNetEngine:
             tape.append(("xf", w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk))
         return out
 
-    def _xf_bwd(self, rec, dout, dctx, to_input=True):
+    def _xf_bwd(self, rec, dout, dkv_all, to_input=True):
         """to_input=False: this is the first transformer block of the network -- only the context gradient is wanted, so
         the chain stops after the cross-attention K/V gradients (what autograd prunes in the reference: x_noisy, the
         timestep embedding and every weight before this point do not require grad)."""
@@ -317,10 +323,9 @@ class UNetEngine:
         # cross attention
         dO = ops.linear_dgrad(dr16, w["wo2"])
         dq2 = torch.empty_like(q2) if to_input else None
-        dkv2 = torch.empty_like(kv2)
+        dkv2 = dkv_all[:, w["kv_off"]:w["kv_off"] + 2 * c]     # gradient slice of the batched context projection
         _Attn.bwd(dO, q2, kv2[:, :c], kv2[:, c:], P2, images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale,
                   dq=dq2, dk=dkv2[:, :c], dv=dkv2[:, c:])
-        ops.linear_dgrad(dkv2, w["wkv2"], out=dctx, residual=dctx)
         if not to_input:
             return None
         dl2 = ops.linear_dgrad(dq2, w["wq2"])
@@ -362,13 +367,13 @@ class UNetEngine:
         du, _ = ops.conv2d_dgrad(ops.cast(dout, self.dt), ugeo, w["w"], w["c"])
         return ops.upsample2x_bwd(du, geo, dx_dtype=torch.float32)
 
-    def _run_layers(self, layers, h, geo, emb_all, ctx16, tape):
+    def _run_layers(self, layers, h, geo, emb_all, kv_all, tape):
         for w in layers:
             k = w["kind"]
             if k == "res":
                 h = self._res_fwd(w, h, geo, emb_all, tape)
             elif k == "xf":
-                h = self._xf_fwd(w, h, geo, ctx16, tape)
+                h = self._xf_fwd(w, h, geo, kv_all, tape)
             elif k == "down":
                 h, geo = self._down_fwd(w, h, geo, tape)
             else:
@@ -387,15 +392,17 @@ class UNetEngine:
         e2 = ops.linear(e1, self.te2_w, self.te2_b, act=CB_ACT_SILU)
         emb_all = ops.linear(e2, self.emb_w, self.emb_b, out_dtype=torch.float32)
         ctx16 = ops.cast(context.reshape(-1, self.ctx_dim), self.dt)
+        # the context is the same for all 16 transformer blocks: project it to every block's K and V in one GEMM
+        kv_all = ops.linear(ctx16, self.wkv_all) if self.wkv_all is not None else None
         x16, geo = ops.nchw_to_nhwc(x.contiguous(), self.in_pad, self.dt)
         h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32)
         hs = [(h, geo)]
         for layers in self.input_blocks:
-            h, geo = self._run_layers(layers, h, geo, emb_all, ctx16, tape)
+            h, geo = self._run_layers(layers, h, geo, emb_all, kv_all, tape)
             if tape is not None:
                 tape.append(("push",))
             hs.append((h, geo))
-        h, geo = self._run_layers(self.middle, h, geo, emb_all, ctx16, tape)
+        h, geo = self._run_layers(self.middle, h, geo, emb_all, kv_all, tape)
         for layers in self.output_blocks:
             skip, _ = hs.pop()
             c1, c2 = h.shape[1], skip.shape[1]
@@ -404,7 +411,7 @@ class UNetEngine:
             ops.axpby(skip, 1.0, out=cat[:, c1:])
             if tape is not None:
                 tape.append(("cat", c1, c2))
-            h, geo = self._run_layers(layers, cat, geo, emb_all, ctx16, tape)
+            h, geo = self._run_layers(layers, cat, geo, emb_all, kv_all, tape)
         a16, sto = ops.groupnorm(h, geo, self.out_g, self.out_b, eps=1e-5, silu=True, out_dtype=self.dt)
         y, _ = ops.conv2d(a16, geo, self.out_w, self.out_ch, bias=self.out_bias, out_dtype=torch.float32,
                           cout_rows=self.out_pad)
@@ -423,7 +430,7 @@ class UNetEngine:
         tape, ctx_shape = self.tape
         self.tape = None
         S = self.loss_scale
-        dctx = torch.zeros(ctx_shape[0] * ctx_shape[1], ctx_shape[2], dtype=torch.float32, device=self.dev)
+        dkv_all = torch.empty(ctx_shape[0] * ctx_shape[1], self._kv_off, dtype=self.dt, device=self.dev)
         rec = tape.pop()
         _, geo, h_head, sto = rec
         d32, _ = ops.nchw_to_nhwc(d_eps.contiguous(), self.out_pad, torch.float32)
@@ -441,10 +448,10 @@ class UNetEngine:
                 if len(tape) == first_xf:
                     # first transformer block in forward order: nothing before it (stem, ResBlock, its own self-attention)
                     # depends on the context, so the backward pass ends with its cross-attention K/V gradients
-                    self._xf_bwd(rec, dh, dctx, to_input=False)
+                    self._xf_bwd(rec, dh, dkv_all, to_input=False)
                     tape.clear()
                     break
-                dh = self._xf_bwd(rec, dh, dctx)
+                dh = self._xf_bwd(rec, dh, dkv_all)
             elif k == "down":
                 dh = self._down_bwd(rec, dh)
             elif k == "up":
@@ -457,5 +464,7 @@ class UNetEngine:
                 # this activation also fed a skip connection: add that branch's gradient
                 dsk = dskips.pop()
                 ops.axpby(dh, 1.0, dsk, 1.0, out=dh)
+        # d(context) = [dK | dV of every block] . [W_k ; W_v of every block]: one GEMM with K = sum 2C
+        dctx = ops.linear_dgrad(dkv_all, self.wkv_all, out_dtype=torch.float32)
         out = ops.axpby(dctx, 1.0 / S)
         return out.view(ctx_shape)
