@@ -100,7 +100,7 @@ gn_stats_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C
 #pragma unroll
     for (int j = 0; j < kGnMaxChunks; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
     const TX* xb = x + ((size_t)n * HW) * C + 2 * tx;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = r0 + ty; r < r1; r += RY) {
         const TX* xr = xb + (size_t)r * C;
 #pragma unroll
@@ -161,7 +161,7 @@ gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __res
         const float m = s_mean[g], rs = s_rstd[g];
         const float g0 = gamma[c] * rs, g1 = gamma[c + 1] * rs;
         const float b0 = beta[c] - m * g0, b1 = beta[c + 1] - m * g1;
-#pragma unroll 4
+#pragma unroll 8
         for (int r = r0 + ty; r < r1; r += RY) {
             const size_t off = base + (size_t)r * C + c;
             float2 v = Vec2<TX>::ld(x + off);
@@ -171,6 +171,159 @@ gn_apply_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __res
             Vec2<TY>::st(y + off, v);
         }
     }
+}
+
+// ---- large tensors (VAE 512^2 / 256^2 maps: too big for the fused kernel's shared memory): the same two passes, but the
+// rows stream through a 3-stage ring of 32 KiB cp.async.bulk (TMA 1-D) chunks, so every CTA keeps ~64-96 KiB in flight
+// instead of a few 8-byte loads per thread.
+constexpr int kGnTmaStages = 3;
+constexpr int kGnTmaChunkBytes = 32768;
+
+template <typename TX, typename F>
+__device__ __forceinline__ void gn_tma_row_stream(const TX* __restrict__ xrows, int nrows, int C, int rows_per_chunk,
+                                                  unsigned char* smem, unsigned long long* bars, F&& consume) {
+    const int nchunks = (nrows + rows_per_chunk - 1) / rows_per_chunk;
+    auto issue = [&](int ci) {
+        const int rows = min(rows_per_chunk, nrows - ci * rows_per_chunk);
+        const uint32_t bytes = (uint32_t)((size_t)rows * C * sizeof(TX));
+        const int stg = ci % kGnTmaStages;
+        const uint32_t bar = smem_u32(&bars[stg]);
+        mbar_arrive_expect_tx(bar, bytes);
+        tma_bulk_g2s(smem_u32(smem + (size_t)stg * kGnTmaChunkBytes), xrows + (size_t)ci * rows_per_chunk * C, bytes, bar);
+    };
+    if (threadIdx.x == 0)
+        for (int ci = 0; ci < min(kGnTmaStages, nchunks); ++ci) issue(ci);
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int stg = ci % kGnTmaStages;
+        mbar_wait(smem_u32(&bars[stg]), (ci / kGnTmaStages) & 1);
+        const int rows = min(rows_per_chunk, nrows - ci * rows_per_chunk);
+        consume(reinterpret_cast<const TX*>(smem + (size_t)stg * kGnTmaChunkBytes), ci * rows_per_chunk, rows);
+        __syncthreads();                                   // every thread is done with this stage
+        if (threadIdx.x == 0 && ci + kGnTmaStages < nchunks) issue(ci + kGnTmaStages);
+    }
+}
+
+template <typename TX>
+__global__ void __launch_bounds__(kGnThreads)
+gn_stats_tma_kernel(const TX* __restrict__ x, double* __restrict__ ws, int HW, int C, int G, int rows_per_block,
+                    int rows_per_chunk, int PW, int RY, int chunks) {
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    __shared__ float s_sum[64], s_sq[64];
+    __shared__ __align__(8) unsigned long long s_bars[kGnTmaStages];
+    const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    const int cpg = C / G;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGnTmaStages; ++i) mbar_init(smem_u32(&s_bars[i]), 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    pdl_sync();
+    float a1[kGnMaxChunks], a2[kGnMaxChunks];
+#pragma unroll
+    for (int j = 0; j < kGnMaxChunks; ++j) { a1[j] = 0.f; a2[j] = 0.f; }
+    if (r1 > r0) {
+        gn_tma_row_stream<TX>(x + ((size_t)n * HW + r0) * C, r1 - r0, C, rows_per_chunk, gn_smem, s_bars,
+                              [&](const TX* sx, int, int rows) {
+#pragma unroll 4
+            for (int r = ty; r < rows; r += RY) {
+                const TX* sr = sx + (size_t)r * C + 2 * tx;
+#pragma unroll
+                for (int j = 0; j < kGnMaxChunks; ++j) {
+                    if (j < chunks) {
+                        const float2 v = Vec2<TX>::ld(sr + 2 * j * PW);
+                        a1[j] += v.x + v.y;
+                        a2[j] += v.x * v.x + v.y * v.y;
+                    }
+                }
+            }
+        });
+    }
+#pragma unroll
+    for (int j = 0; j < kGnMaxChunks; ++j) {
+        if (j < chunks) {
+            const int g = (2 * (tx + j * PW)) / cpg;
+            group_accumulate(s_sum, s_sq, g, a1[j], a2[j]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+        atomicAdd(&ws[((size_t)n * G + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+    }
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_tma_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const double* __restrict__ ws, float* __restrict__ mean_out,
+                    float* __restrict__ rstd_out, int HW, int C, int G, float eps, int act, int rows_per_block,
+                    int rows_per_chunk, int PW, int RY, int chunks) {
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    __shared__ float s_mean[64], s_rstd[64];
+    __shared__ __align__(8) unsigned long long s_bars[kGnTmaStages];
+    const int n = blockIdx.y;
+    const int tx = threadIdx.x % PW, ty = threadIdx.x / PW;
+    const int cpg = C / G;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGnTmaStages; ++i) mbar_init(smem_u32(&s_bars[i]), 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    pdl_sync();
+    if (threadIdx.x < G) {
+        const double cnt = (double)HW * cpg;
+        const double m = ws[((size_t)n * G + threadIdx.x) * 2] / cnt;
+        double var = ws[((size_t)n * G + threadIdx.x) * 2 + 1] / cnt - m * m;
+        if (var < 0) var = 0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[threadIdx.x] = (float)m;
+        s_rstd[threadIdx.x] = rs;
+        if (blockIdx.x == 0) {
+            mean_out[n * G + threadIdx.x] = (float)m;
+            rstd_out[n * G + threadIdx.x] = rs;
+        }
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(HW, r0 + rows_per_block);
+    if (r1 <= r0) return;
+    // per-thread affine of its channel pairs: y = x * ga + be
+    float ga0[kGnMaxChunks], ga1[kGnMaxChunks], be0[kGnMaxChunks], be1[kGnMaxChunks];
+#pragma unroll
+    for (int j = 0; j < kGnMaxChunks; ++j) {
+        if (j < chunks) {
+            const int c = 2 * (tx + j * PW);
+            const int g = c / cpg;
+            const float m = s_mean[g], rs = s_rstd[g];
+            ga0[j] = gamma[c] * rs; ga1[j] = gamma[c + 1] * rs;
+            be0[j] = beta[c] - m * ga0[j]; be1[j] = beta[c + 1] - m * ga1[j];
+        }
+    }
+    TY* yb = y + ((size_t)n * HW + r0) * C + 2 * tx;
+    gn_tma_row_stream<TX>(x + ((size_t)n * HW + r0) * C, r1 - r0, C, rows_per_chunk, gn_smem, s_bars,
+                          [&](const TX* sx, int row_base, int rows) {
+#pragma unroll 4
+        for (int r = ty; r < rows; r += RY) {
+            const TX* sr = sx + (size_t)r * C + 2 * tx;
+            TY* yr = yb + (size_t)(row_base + r) * C;
+#pragma unroll
+            for (int j = 0; j < kGnMaxChunks; ++j) {
+                if (j < chunks) {
+                    float2 v = Vec2<TX>::ld(sr + 2 * j * PW);
+                    v.x = v.x * ga0[j] + be0[j];
+                    v.y = v.y * ga1[j] + be1[j];
+                    if (act) { v.x = silu_f(v.x); v.y = silu_f(v.y); }
+                    Vec2<TY>::st(yr + 2 * j * PW, v);
+                }
+            }
+        }
+    });
 }
 
 // ---- GroupNorm backward statistics: ws += {sum dz*gamma, sum dz*gamma*xhat} ---------------------------
@@ -637,7 +790,7 @@ ln_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* 
 }
 
 static inline int gn_rows_per_block(int HW, int N) {
-    const int target_blocks = 4 * device_sm_count();
+    const int target_blocks = 8 * device_sm_count();     // 256-thread blocks: 8 per SM keep 2048 threads x 8 loads in flight
     int per_img = ceil_div(target_blocks, N);
     if (per_img < 1) per_img = 1;
     int rpb = ceil_div(HW, per_img);
@@ -698,6 +851,33 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
         }
     }
     CB_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st));
+    {
+        // streaming (TMA-staged) variant: rows are 16-byte multiples and a chunk of them fits one 32 KiB stage
+        const int xes = x_dtype == CB_F32 ? 4 : 2;
+        const size_t row_bytes = (size_t)C * xes;
+        const int rpc = (int)(kGnTmaChunkBytes / row_bytes);
+        if (row_bytes % 16 == 0 && rpc >= 1) {
+            const int nb = std::max(1, 2 * device_sm_count() / N);
+            const int rpbt = ceil_div(HW, nb);
+            dim3 gridt(ceil_div(HW, rpbt), N);
+            const size_t smem = (size_t)kGnTmaStages * kGnTmaChunkBytes;
+            CB_DISPATCH_2(x_dtype, TX, {
+                auto kern = gn_stats_tma_kernel<TX>;
+                static bool set = false;
+                if (!set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+                CB_LAUNCH((kern), gridt, nthr, smem, st, (const TX*)x, ws, HW, C, G, rpbt, rpc, gs.pw, gs.ry, gs.chunks);
+            });
+            CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
+                auto kern = gn_apply_tma_kernel<TX, TY>;
+                static bool set = false;
+                if (!set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+                CB_LAUNCH((kern), gridt, nthr, smem, st, (const TX*)x, (TY*)y, gamma, beta, ws, mean_out, rstd_out, HW, C, G, eps, act_silu, rpbt, rpc, gs.pw, gs.ry, gs.chunks);
+            }));
+            CB_CUDA(cudaGetLastError());
+            cb::count_launches(2);
+            return 0;
+        }
+    }
     const int rpb = gn_rows_per_block(HW, N);
     dim3 grid(ceil_div(HW, rpb), N);
     CB_DISPATCH_2(x_dtype, TX,CB_LAUNCH((gn_stats_kernel<TX>), grid, nthr, 0, st, (const TX*)x, ws, HW, C, G, rpb, gs.pw, gs.ry, gs.chunks));

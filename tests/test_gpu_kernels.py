@@ -127,7 +127,9 @@ def test_attention_fwd_bwd(dev, nq, nk, dh, heads, images):
 # ---------------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("n,hw,c,silu,eps,xdt", [(1, 4096, 320, True, 1e-5, torch.float32), (2, 64, 1280, True, 1e-5, torch.float32),
                                                  (1, 1024, 960, False, 1e-6, torch.float32), (1, 4096, 128, True, 1e-6, torch.float16),
-                                                 (1, 1, 256, True, 1e-5, torch.float32)])
+                                                 (1, 1, 256, True, 1e-5, torch.float32),
+                                                 # larger than the SMs' shared memory: TMA-streamed two-kernel path (VAE maps)
+                                                 (1, 65536, 128, True, 1e-6, torch.float32), (2, 20001, 256, False, 1e-6, torch.float16)])
 def test_groupnorm_fwd_bwd(dev, n, hw, c, silu, eps, xdt):
     from celebbasis_b200 import ops
     x = rnd(n * hw, c, dtype=xdt, scale=2.0) + 0.5

@@ -31,3 +31,8 @@ for (hw, c) in ((64, 320), (64, 640), (32, 640), (32, 1280), (16, 1280), (16, 25
     y, stt = ops.groupnorm(xs, ops.Geo(1, hw, hw), g2, b2, silu=True)
     dy = torch.randn(hw * hw, c, device=dev).half()
     per_node(f"groupnorm_bwd      {hw}x{hw}x{c}", lambda: ops.groupnorm_bwd(dy, xs, ops.Geo(1, hw, hw), g2, b2, stt, silu=True))
+
+# VAE-size tensors (two-kernel path: statistics + apply)
+for (hw, c, dt) in ((512, 128, torch.float32), (256, 256, torch.float32), (256, 128, torch.float32), (128, 512, torch.float32), (128, 256, torch.float32)):
+    xs = torch.randn(hw * hw, c, device=dev).to(dt); g2 = torch.ones(c, device=dev); b2 = torch.zeros(c, device=dev)
+    per_node(f"groupnorm+silu 2-kernel {hw}x{hw}x{c} {str(dt)[6:]}", lambda: ops.groupnorm(xs, ops.Geo(1, hw, hw), g2, b2, silu=True), n=10)
