@@ -127,3 +127,25 @@ def test_data_parallel_gloo_world2(tmp_path):
     expect = torch.arange(1, 11).float().view(10, 1, 1, 1).expand(10, 2, 1, 4)
     assert torch.equal(r0["full"], expect) and torch.equal(r1["full"], expect)
     assert abs(r0["lr"] - 2 * 5e-3) < 1e-12
+
+
+def test_gemm_autotune_key_and_lanes():
+    """Host plumbing of the tile autotuner and of the per-branch workspace lanes (no GPU needed)."""
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import GemmDesc
+    a, b = GemmDesc(), GemmDesc()
+    for d in (a, b):
+        d.M, d.N, d.K, d.batch, d.lda, d.ldb, d.ldd = 4096, 320, 320, 1, 320, 320, 320
+    assert ops._tune_key(a) == ops._tune_key(b)
+    b.conv, b.kh, b.kw = 1, 3, 3
+    assert ops._tune_key(a) != ops._tune_key(b)
+    b = GemmDesc.from_buffer_copy(bytes(a))
+    b.tile_n, b.splits, b.stages = 128, 3, 3          # tuning overrides are not part of the shape key
+    assert ops._tune_key(a) == ops._tune_key(b)
+    assert ops._LANE == 0
+    with ops.lane(1):
+        assert ops._LANE == 1
+        with ops.lane(0):
+            assert ops._LANE == 0
+        assert ops._LANE == 1
+    assert ops._LANE == 0
