@@ -8,6 +8,7 @@ is DDP's gradient averaging.  At save time the per-identity EMA coefficients, wh
 therefore loses for ranks > 0 (ddpm.py:1519-1528), are all-gathered.
 """
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -25,7 +26,21 @@ def init(backend=None):
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # NCCL prints its version banner to stdout when the communicator is created (first collective); callers such as
+        # bench.py own stdout (one JSON line), so create the communicator here with fd 1 pointed at stderr.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            if backend == "nccl":
+                t = torch.zeros(1, device="cuda")
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return world, rank, local
 
 
