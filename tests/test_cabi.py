@@ -59,3 +59,9 @@ def test_no_cpu_fallback_without_device():
     from ldm.modules.attention import CrossAttention
     with pytest.raises(RuntimeError):
         CrossAttention(64, heads=2, dim_head=32)(torch.zeros(1, 4, 64))
+
+
+def test_graft_entry_build():
+    """The driver's build hook: compiles (cached) every CUDA source for sm_100a, loads the library, checks the ABI."""
+    import __graft_entry__ as g
+    g.build()
