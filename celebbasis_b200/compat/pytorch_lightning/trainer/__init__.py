@@ -1,0 +1,213 @@
+"""`Trainer` stand-in: the optimisation loop Lightning 1.5 runs for the reference (main_id_embed.py:748,812), one
+process per GPU.  Supported: fit() over train_dataloader with max_steps / max_epochs, accumulate_grad_batches, callbacks,
+ModelCheckpoint cadence, save_checkpoint (same keys the reference reads back: "state_dict", "global_step", plus the
+module's on_save_checkpoint additions), data-parallel gradient averaging over the trainable parameters through
+celebbasis_b200.dist (torchrun environment).  Validation / test loops are no-ops (the reference runs with
+--no-test and a dummy validation set)."""
+import argparse
+import os
+
+import torch
+
+
+class _Profiler:
+    def summary(self):
+        return ""
+
+
+class _Plugin:
+    def __init__(self, trainer):
+        self.trainer = trainer
+
+    def reduce(self, value, *args, **kwargs):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.as_tensor(float(value), device=self.trainer.device)
+            dist.all_reduce(t)
+            return (t / dist.get_world_size()).item()
+        return value
+
+
+_ARGS = {  # name -> (type, default): the flags the reference passes or compares (nondefault_trainer_args)
+    "gpus": (str, None), "max_steps": (int, -1), "max_epochs": (int, None), "accumulate_grad_batches": (int, 1),
+    "accelerator": (str, None), "resume_from_checkpoint": (str, None), "benchmark": (bool, False),
+    "num_sanity_val_steps": (int, 2), "check_val_every_n_epoch": (int, 1), "val_check_interval": (float, 1.0),
+    "log_every_n_steps": (int, 50), "precision": (int, 32), "num_nodes": (int, 1), "limit_val_batches": (float, 1.0),
+    "default_root_dir": (str, None), "gradient_clip_val": (float, 0.0), "deterministic": (bool, False),
+    "profiler": (str, None), "fast_dev_run": (bool, False), "find_unused_parameters": (bool, False),
+}
+
+
+def _move(obj, device):
+    if torch.is_tensor(obj):
+        return obj.to(device, non_blocking=True)
+    if isinstance(obj, dict):
+        return {k: _move(v, device) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_move(v, device) for v in obj)
+    return obj
+
+
+class Trainer:
+    def __init__(self, gpus=None, max_steps=-1, max_epochs=None, accumulate_grad_batches=1, callbacks=None, logger=None,
+                 default_root_dir=None, gradient_clip_val=0.0, resume_from_checkpoint=None, **kwargs):
+        self.gpus = gpus
+        self.max_steps = -1 if max_steps is None else int(max_steps)
+        self.max_epochs = max_epochs
+        self.accumulate_grad_batches = int(accumulate_grad_batches or 1)
+        self.callbacks = list(callbacks or [])
+        self.logger = logger
+        self.default_root_dir = default_root_dir or os.getcwd()
+        self.gradient_clip_val = float(gradient_clip_val or 0.0)
+        self.resume_from_checkpoint = resume_from_checkpoint
+        self.extra = kwargs
+        self.global_step = 0
+        self.current_epoch = 0
+        self.optimizers = []
+        self.lr_schedulers = []
+        self.logged_metrics = {}
+        self.interrupted = False
+        self.profiler = _Profiler()
+        self.training_type_plugin = _Plugin(self)
+        self.lightning_module = None
+        self.datamodule = None
+        self.logdir = None
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.global_rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        use_gpu = gpus not in (None, 0, "0", "") and torch.cuda.is_available()
+        self.root_gpu = self.local_rank if use_gpu else None
+        self.device = torch.device("cuda", self.local_rank) if use_gpu else torch.device("cpu")
+
+    # ---- argparse plumbing (main_id_embed.py:183,540,748) -------------------------------------------------------
+    @classmethod
+    def add_argparse_args(cls, parser):
+        for name, (typ, default) in _ARGS.items():
+            if typ is bool:
+                parser.add_argument(f"--{name}", type=lambda s: str(s).lower() in ("1", "true", "yes"), nargs="?",
+                                    const=True, default=default)
+            else:
+                parser.add_argument(f"--{name}", type=typ, default=default)
+        return parser
+
+    @classmethod
+    def from_argparse_args(cls, args, **kwargs):
+        params = vars(args) if isinstance(args, argparse.Namespace) else dict(args)
+        params = {k: v for k, v in params.items()}
+        params.update(kwargs)
+        return cls(**params)
+
+    # ---- hooks ------------------------------------------------------------------------------------------------------
+    def _call(self, hook, *args):
+        for cb in self.callbacks:
+            fn = getattr(cb, hook, None)
+            if fn is not None:
+                fn(self, self.lightning_module, *args)
+
+    # ---- checkpointing ------------------------------------------------------------------------------------------------
+    def save_checkpoint(self, filepath, weights_only=False):
+        model = self.lightning_module
+        ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+                "global_step": self.global_step, "epoch": self.current_epoch,
+                "pytorch-lightning_version": "1.5.9"}
+        if not weights_only:
+            ckpt["optimizer_states"] = [o.state_dict() for o in self.optimizers]
+        model.on_save_checkpoint(ckpt)
+        self._call("on_save_checkpoint", ckpt)
+        if self.global_rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(filepath)), exist_ok=True)
+            torch.save(ckpt, filepath)
+        return ckpt
+
+    # ---- optimisation loop ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _unpack_optimizers(conf):
+        if isinstance(conf, dict):
+            return [conf["optimizer"]], [conf["lr_scheduler"]] if "lr_scheduler" in conf else []
+        if isinstance(conf, (list, tuple)):
+            if len(conf) == 2 and isinstance(conf[0], (list, tuple)):
+                return list(conf[0]), list(conf[1])
+            return list(conf), []
+        return [conf], []
+
+    def _sync_grads(self, model):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        grads = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1).float() for g in grads])
+        dist.all_reduce(flat)
+        flat /= dist.get_world_size()
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+
+    def fit(self, model, datamodule=None, train_dataloaders=None):
+        self.lightning_module = model
+        model.trainer = self
+        self.datamodule = datamodule
+        if self.world_size > 1:
+            from celebbasis_b200 import dist as cbd
+            cbd.init()
+        model.to(self.device)
+        if datamodule is not None:
+            datamodule.trainer = self
+            if not hasattr(datamodule, "datasets"):
+                datamodule.prepare_data()
+                datamodule.setup("fit")
+            loader = datamodule.train_dataloader()
+        else:
+            loader = train_dataloaders
+        self.optimizers, self.lr_schedulers = self._unpack_optimizers(model.configure_optimizers())
+        self._call("setup", "fit")
+        self._call("on_pretrain_routine_start")
+        model.train()
+        self._call("on_train_start")
+        done = False
+        try:
+            while not done:
+                self._call("on_train_epoch_start")
+                for batch_idx, batch in enumerate(loader):
+                    batch = _move(batch, self.device)
+                    self._call("on_train_batch_start", batch, batch_idx, 0)
+                    model.on_train_batch_start(batch, batch_idx, 0)
+                    out = model.training_step(batch, batch_idx)
+                    loss = out["loss"] if isinstance(out, dict) else out
+                    (loss / self.accumulate_grad_batches).backward()
+                    if (batch_idx + 1) % self.accumulate_grad_batches == 0:
+                        self._sync_grads(model)
+                        if self.gradient_clip_val > 0:
+                            torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.grad is not None],
+                                                           self.gradient_clip_val)
+                        for opt in self.optimizers:
+                            opt.step()
+                            opt.zero_grad(set_to_none=True)
+                        for sch in self.lr_schedulers:
+                            (sch["scheduler"] if isinstance(sch, dict) else sch).step()
+                        self.global_step += 1
+                    outputs = {"loss": loss.detach()}
+                    model.on_train_batch_end(outputs, batch, batch_idx, 0)
+                    self._call("on_train_batch_end", outputs, batch, batch_idx, 0)
+                    if self.max_steps is not None and 0 <= self.max_steps <= self.global_step:
+                        done = True
+                        break
+                self._call("on_train_epoch_end")
+                self.current_epoch += 1
+                if self.max_epochs is not None and self.current_epoch >= self.max_epochs:
+                    done = True
+                if self.max_steps in (None, -1) and self.max_epochs is None and self.current_epoch >= 1000:
+                    done = True      # Lightning's default max_epochs
+        except KeyboardInterrupt:
+            self.interrupted = True
+            self._call("on_keyboard_interrupt")
+        self._call("on_train_end")
+
+    def validate(self, *args, **kwargs):
+        return []
+
+    def test(self, *args, **kwargs):
+        return []
