@@ -56,6 +56,9 @@ class Trainer:
         self.max_epochs = max_epochs
         self.accumulate_grad_batches = int(accumulate_grad_batches or 1)
         self.callbacks = list(callbacks or [])
+        from ..callbacks import ModelCheckpoint
+        self.checkpoint_callbacks = [c for c in self.callbacks if isinstance(c, ModelCheckpoint)]
+        self.checkpoint_callback = self.checkpoint_callbacks[0] if self.checkpoint_callbacks else None
         self.logger = logger
         self.default_root_dir = default_root_dir or os.getcwd()
         self.gradient_clip_val = float(gradient_clip_val or 0.0)
@@ -98,6 +101,17 @@ class Trainer:
         return cls(**params)
 
     # ---- hooks ------------------------------------------------------------------------------------------------------
+    def _module_hook(self, name, *args):
+        fn = getattr(self.lightning_module, name, None)        # modules built on another LightningModule stand-in may lack it
+        return fn(*args) if callable(fn) else None
+
+    def _publish_progress(self):
+        for name, val in (("global_step", self.global_step), ("current_epoch", self.current_epoch)):
+            try:
+                setattr(self.lightning_module, name, val)
+            except AttributeError:                              # read-only property that already reads the trainer
+                pass
+
     def _call(self, hook, *args):
         for cb in self.callbacks:
             fn = getattr(cb, hook, None)
@@ -112,7 +126,7 @@ class Trainer:
                 "pytorch-lightning_version": "1.5.9"}
         if not weights_only:
             ckpt["optimizer_states"] = [o.state_dict() for o in self.optimizers]
-        model.on_save_checkpoint(ckpt)
+        self._module_hook("on_save_checkpoint", ckpt)
         self._call("on_save_checkpoint", ckpt)
         if self.global_rank == 0:
             os.makedirs(os.path.dirname(os.path.abspath(filepath)), exist_ok=True)
@@ -174,7 +188,7 @@ class Trainer:
                 for batch_idx, batch in enumerate(loader):
                     batch = _move(batch, self.device)
                     self._call("on_train_batch_start", batch, batch_idx, 0)
-                    model.on_train_batch_start(batch, batch_idx, 0)
+                    self._module_hook("on_train_batch_start", batch, batch_idx, 0)
                     out = model.training_step(batch, batch_idx)
                     loss = out["loss"] if isinstance(out, dict) else out
                     (loss / self.accumulate_grad_batches).backward()
@@ -189,14 +203,16 @@ class Trainer:
                         for sch in self.lr_schedulers:
                             (sch["scheduler"] if isinstance(sch, dict) else sch).step()
                         self.global_step += 1
+                        self._publish_progress()
                     outputs = {"loss": loss.detach()}
-                    model.on_train_batch_end(outputs, batch, batch_idx, 0)
+                    self._module_hook("on_train_batch_end", outputs, batch, batch_idx, 0)
                     self._call("on_train_batch_end", outputs, batch, batch_idx, 0)
                     if self.max_steps is not None and 0 <= self.max_steps <= self.global_step:
                         done = True
                         break
                 self._call("on_train_epoch_end")
                 self.current_epoch += 1
+                self._publish_progress()
                 if self.max_epochs is not None and self.current_epoch >= self.max_epochs:
                     done = True
                 if self.max_steps in (None, -1) and self.max_epochs is None and self.current_epoch >= 1000:
