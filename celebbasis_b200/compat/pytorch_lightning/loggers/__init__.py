@@ -1,7 +1,4 @@
 """Logger stand-ins (main_id_embed.py:640-652, ImageLogger's `pl.loggers.TestTubeLogger` key at :353)."""
-import os
-
-
 class _NullExperiment:
     def __getattr__(self, name):
         return lambda *a, **k: None

@@ -14,13 +14,10 @@ but runs it as an explicit tape of kernel launches:
     (SURVEY.md §8 a29): activation gradients down to d(context); no weight gradients, no d(emb).
     Gradients are carried fp16 with a static loss scale; residual-stream gradients are fp32.
 """
-import math
-
 import torch
 
 from . import ops
-from .lib import CB_ACT_NONE, CB_ACT_SILU, CB_MAJOR_K, CB_MAJOR_MN
-from .ops import Geo
+from .lib import CB_ACT_SILU, CB_MAJOR_MN
 
 
 def _round_up(a, b):
