@@ -149,3 +149,22 @@ def test_gemm_autotune_key_and_lanes():
             assert ops._LANE == 0
         assert ops._LANE == 1
     assert ops._LANE == 0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours): the oracle port of the reference step on the host
+    cores, one JSON line with the contract's keys (no GPU involved)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["unit"] == "steps/s" and out["value"] > 0 and out["higher_is_better"] is True
+    assert out["metric"].startswith("celeb-basis training steps/sec") and out["n_gpus"] == 1
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0 and out["e2e"]["value"] == out["value"]
