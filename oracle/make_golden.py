@@ -2,6 +2,7 @@
 
     python oracle/make_golden.py tiny        # seconds
     python oracle/make_golden.py full        # ~1-2 min, needs ~12 GB host RAM
+    python oracle/make_golden.py infer       # DDIM txt2img + VAE decode on the tiny configuration
 
 Fixtures hold the inputs' seeds (the inputs themselves are re-derivable from celebbasis_b200.workload +
 celebbasis_b200.synth) and the reference's outputs: latent z, context, eps prediction, loss, and the gradient
@@ -93,6 +94,45 @@ def run(kind):
     print(f"[{kind}] graded params: {graded}; |gW|={W.grad.norm().item():.6e}")
 
 
+def run_infer(kind="tiny", steps=4, scale=5.0):
+    """scripts/stable_txt2img.py semantics on the UNMODIFIED reference (CPU): eval-mode conditioning from stored identity
+    coefficients (embedding_manager.py eval branch), DDIMSampler.sample with classifier-free guidance, eta = 0
+    (ddim.py:57-204), decode_first_stage (ddpm.py:761-819).  Pins oracle/torch_ref.py's ddim_sample / AutoencoderKLDecode /
+    eval-branch inject."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    basis = synth.synth_celeb_basis(seed=0)
+    model = ref_shim.build_reference(workload.model_params(kind), seed=0, clip_layers=workload.clip_layers(kind),
+                                     celeb_basis=basis)
+    model.eval()
+    from ldm.models.diffusion.ddim import DDIMSampler
+
+    def register_buffer(self, name, attr):            # ddim.py:19-23 hard-codes .to("cuda"); same values on the CPU
+        setattr(self, name, attr)
+    DDIMSampler.register_buffer = register_buffer
+    g = torch.Generator().manual_seed(3)
+    coefs = [F.normalize(torch.randn(2, 1, 512, generator=g), dim=-1) for _ in range(10)]
+    model.embedding_manager.id_coefficients = [c.clone() for c in coefs]
+    prompts = ["a photo of sks person"]
+    image_ori = {"faces": None, "ids": torch.tensor([[3, 3]]), "num_ids": torch.ones(1, dtype=torch.long)}
+    hw = workload.model_params(kind)["image_size"]
+    with torch.no_grad():
+        uc = model.get_learned_conditioning([""])
+        c = model.get_learned_conditioning(prompts, image_ori=image_ori)
+        x_T = torch.randn(1, 4, hw, hw, generator=g)
+        sampler = DDIMSampler(model)
+        samples, _ = sampler.sample(S=steps, conditioning=c, batch_size=1, shape=[4, hw, hw], verbose=False,
+                                    unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T)
+        img = model.decode_first_stage(samples)
+    out = {"kind": kind, "steps": steps, "scale": scale, "coef_seed": 3, "prompts": prompts, "person_id": 3,
+           "uc": uc.clone(), "c": c.clone(), "x_T": x_T.clone(), "samples": samples.clone(), "img": img.clone(),
+           "ddim_timesteps": torch.as_tensor(np.asarray(sampler.ddim_timesteps).copy())}
+    os.makedirs(GOLD, exist_ok=True)
+    torch.save(out, os.path.join(GOLD, f"infer_{kind}.pt"))
+    print(f"[infer/{kind}] samples |x|={samples.norm().item():.6f} img |x|={img.norm().item():.6f} "
+          f"timesteps={out['ddim_timesteps'].tolist()}")
+
+
 def helpers_kat():
     """helpers.py:44-54 toy case, computed by the reference's own functions."""
     ref_shim.install_stubs()
@@ -126,5 +166,7 @@ if __name__ == "__main__":
     for w in which:
         if w == "helpers":
             helpers_kat()
+        elif w == "infer":
+            run_infer("tiny")
         else:
             run(w)

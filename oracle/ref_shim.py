@@ -55,6 +55,15 @@ def install_stubs(clip_layers=12):
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     sys.dont_write_bytecode = True
+    if "ldm" not in sys.modules:
+        # The reference's `ldm` directory has no __init__.py (namespace package), so any regular package named `ldm` on
+        # sys.path -- this repository's drop-in mirror -- would win regardless of order: bind the name to the reference
+        # tree explicitly.
+        import importlib.machinery
+        import importlib.util
+        spec = importlib.machinery.ModuleSpec("ldm", None, is_package=True)
+        spec.submodule_search_locations = [os.path.join(REF_ROOT, "ldm")]
+        sys.modules["ldm"] = importlib.util.module_from_spec(spec)
 
     def mod(name):
         m = types.ModuleType(name)

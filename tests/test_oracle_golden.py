@@ -65,3 +65,40 @@ def test_tiny_step_matches_reference(golden_dir):
                               "embedding_manager.meta_id_net.stylegan_mlp.net.0.bias"]
     # placeholder lands at positions 7,8 of "a photo of a face of sks person"
     assert [f.tolist() for f in out["positions"][0]] == [[[7, 8]]]
+
+
+def test_tiny_inference_matches_reference(golden_dir):
+    """DDIM txt2img + VAE decode (scripts/stable_txt2img.py semantics: eval-mode conditioning from stored coefficients,
+    DDIMSampler.sample with CFG and eta 0, decode_first_stage): the restatement == the UNMODIFIED reference (fixture from
+    `python oracle/make_golden.py infer`)."""
+    import torch.nn.functional as F
+    gold = torch.load(os.path.join(golden_dir, "infer_tiny.pt"))
+    params = workload.model_params("tiny")
+    om = torch_ref.OracleModel(params, clip_layers=workload.clip_layers("tiny"))
+    sd = synth.synth_state_dict(om, seed=0)
+    om.load_state_dict(sd, strict=True)
+    om.eval()
+    basis = synth.synth_celeb_basis(seed=0)
+    g = torch.Generator().manual_seed(gold["coef_seed"])
+    coefs = [F.normalize(torch.randn(2, 1, 512, generator=g), dim=-1) for _ in range(10)]
+    x_T = torch.randn(1, 4, params["image_size"], params["image_size"], generator=g)
+    assert torch.equal(x_T, gold["x_T"])                                   # same draw order as the fixture generator
+    tok = SyntheticCLIPTokenizer()
+    tm = om.cond_stage_model.transformer.text_model
+    with torch.no_grad():
+        uc = tm.forward_embeds(tm.embed_tokens(tok([""])["input_ids"]))
+        ids = tok(gold["prompts"])["input_ids"]
+        z = torch_ref.celeb_basis(coefs[gold["person_id"]].view(1, 2, 1, 512), basis)
+        emb, pos = torch_ref.inject_embeddings(ids, tm.embed_tokens(ids), z, tok.word_id("sks"), 2)
+        c = tm.forward_embeds(emb)
+        x = torch_ref.ddim_sample(om.model.diffusion_model, om.sched, c, uc, x_T, gold["steps"], gold["scale"])
+        fs = params["first_stage_config"]["params"]
+        dec = torch_ref.AutoencoderKLDecode(fs["ddconfig"], fs["embed_dim"])
+        # decoder / post_quant_conv weights: the same deterministic function of (seed, reference key, shape) the
+        # reference model was loaded with (keys first_stage_model.decoder.*, first_stage_model.post_quant_conv.*)
+        dec.load_state_dict(synth.synth_state_dict(dec, seed=0, prefix="first_stage_model."), strict=True)
+        img = dec(x / 0.18215)
+    assert _rel(uc, gold["uc"]) < 1e-5 and _rel(c, gold["c"]) < 1e-5
+    assert _rel(x, gold["samples"]) < 1e-4
+    assert img.shape == gold["img"].shape and _rel(img, gold["img"]) < 1e-4
+
