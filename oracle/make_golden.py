@@ -124,7 +124,13 @@ def run_infer(kind="tiny", steps=4, scale=5.0):
         samples, _ = sampler.sample(S=steps, conditioning=c, batch_size=1, shape=[4, hw, hw], verbose=False,
                                     unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T)
         img = model.decode_first_stage(samples)
-    out = {"kind": kind, "steps": steps, "scale": scale, "coef_seed": 3, "prompts": prompts, "person_id": 3,
+        # two / three persons in one prompt (embedding_manager.py:323-345,362-392): conditioning only
+        multi = []
+        for prompt, pid in (("a photo of sks person and ks person", [3, 5]),
+                            ("sks person , ks person and ata person", [1, 2, 7])):
+            io = {"faces": None, "ids": torch.tensor([pid]), "num_ids": torch.tensor([len(pid)])}
+            multi.append({"prompt": prompt, "ids": pid, "c": model.get_learned_conditioning([prompt], image_ori=io).clone()})
+    out = {"kind": kind, "multi": multi, "steps": steps, "scale": scale, "coef_seed": 3, "prompts": prompts, "person_id": 3,
            "uc": uc.clone(), "c": c.clone(), "x_T": x_T.clone(), "samples": samples.clone(), "img": img.clone(),
            "ddim_timesteps": torch.as_tensor(np.asarray(sampler.ddim_timesteps).copy())}
     os.makedirs(GOLD, exist_ok=True)

@@ -102,3 +102,36 @@ def test_tiny_inference_matches_reference(golden_dir):
     assert _rel(x, gold["samples"]) < 1e-4
     assert img.shape == gold["img"].shape and _rel(img, gold["img"]) < 1e-4
 
+
+
+def test_multi_identity_conditioning_matches_reference(golden_dir):
+    """Two / three persons in one prompt (embedding_manager.py:323-345,362-392, eval branch): the host row map
+    (train_step.build_inject_map_multi: integer, bit-exact placeholder arithmetic) applied to the restatement's token
+    embeddings, through the CLIP restatement == the UNMODIFIED reference's get_learned_conditioning."""
+    import torch.nn.functional as F
+    from celebbasis_b200.train_step import build_inject_map_multi
+    gold = torch.load(os.path.join(golden_dir, "infer_tiny.pt"))
+    params = workload.model_params("tiny")
+    om = torch_ref.OracleModel(params, clip_layers=workload.clip_layers("tiny"))
+    om.load_state_dict(synth.synth_state_dict(om, seed=0), strict=True)
+    om.eval()
+    basis = synth.synth_celeb_basis(seed=0)
+    g = torch.Generator().manual_seed(gold["coef_seed"])
+    coefs = [F.normalize(torch.randn(2, 1, 512, generator=g), dim=-1) for _ in range(10)]
+    tok = SyntheticCLIPTokenizer()
+    tm = om.cond_stage_model.transformer.text_model
+    words = params["personalization_config"]["params"]["placeholder_strings"]
+    es = params["personalization_config"]["params"]["num_embeds_per_token"]
+    assert len(gold["multi"]) == 2
+    for case in gold["multi"]:
+        pid = case["ids"]
+        ids = tok([case["prompt"]])["input_ids"]
+        ph = [tok.word_id(words[k]) for k in range(len(pid))]
+        with torch.no_grad():
+            z = torch.cat([torch_ref.celeb_basis(coefs[i].view(1, 2, 1, 512), basis)[0] for i in pid], 0)   # (persons*es, 768)
+            m, pos = build_inject_map_multi(ids.numpy(), [(ph, [k * es for k in range(len(pid))])], es)
+            e = tm.embed_tokens(ids)[0]
+            rows = [e[int(j)] if j >= 0 else z[-int(j) - 1] for j in m[0]]
+            c = tm.forward_embeds(torch.stack(rows, 0)[None])
+        assert _rel(c, case["c"]) < 1e-5, case["prompt"]
+        assert len(pos[0]) == len(pid) and all(len(p) >= 1 for p in pos[0])
