@@ -130,6 +130,18 @@ def run_infer(kind="tiny", steps=4, scale=5.0):
                             ("sks person , ks person and ata person", [1, 2, 7])):
             io = {"faces": None, "ids": torch.tensor([pid]), "num_ids": torch.tensor([len(pid)])}
             multi.append({"prompt": prompt, "ids": pid, "c": model.get_learned_conditioning([prompt], image_ori=io).clone()})
+    # a32: the embedding checkpoint the reference writes every 200 steps / reads back in stable_txt2img.py:230
+    # (embedding_manager.py:396-426): written by the reference's own save(), fp32 and fp16 variants
+    import tempfile
+    em = model.embedding_manager
+    with tempfile.TemporaryDirectory() as td:
+        em.save(os.path.join(td, "e32.pt"))
+        ck32 = torch.load(os.path.join(td, "e32.pt"))
+        em.save_fp16 = True
+        em.save(os.path.join(td, "e16.pt"))
+        ck16 = torch.load(os.path.join(td, "e16.pt"))
+        em.save_fp16 = False
+    torch.save({"fp32": ck32, "fp16": ck16, "coef_seed": 3}, os.path.join(GOLD, "embeddings_ref.pt"))
     out = {"kind": kind, "multi": multi, "steps": steps, "scale": scale, "coef_seed": 3, "prompts": prompts, "person_id": 3,
            "uc": uc.clone(), "c": c.clone(), "x_T": x_T.clone(), "samples": samples.clone(), "img": img.clone(),
            "ddim_timesteps": torch.as_tensor(np.asarray(sampler.ddim_timesteps).copy())}

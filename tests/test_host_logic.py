@@ -168,3 +168,36 @@ def test_bench_reference_arm_contract():
     assert out["metric"].startswith("celeb-basis training steps/sec") and out["n_gpus"] == 1
     assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0 and out["e2e"]["value"] == out["value"]
+
+
+def test_embedding_checkpoint_format_matches_reference(golden_dir, tmp_path):
+    """the file `EmbeddingManagerId.save` writes every checkpoint and `scripts/stable_txt2img.py:230` loads
+    (embedding_manager.py:396-426).  The fixture was written by the UNMODIFIED reference's save(); the mirror must read it
+    and write the same structure (keys, container types, dtypes, shapes) in both precisions."""
+    import torch.nn.functional as F
+    from celebbasis_b200 import workload
+    from ldm.models.diffusion.ddpm import LatentDiffusion
+    gold = torch.load(os.path.join(golden_dir, "embeddings_ref.pt"))
+    params = workload.model_params("tiny")
+    params["cond_stage_config"]["params"]["num_hidden_layers"] = 2
+    em = LatentDiffusion(**params).embedding_manager
+    g = torch.Generator().manual_seed(gold["coef_seed"])
+    coefs = [F.normalize(torch.randn(2, 1, 512, generator=g), dim=-1) for _ in range(10)]
+    for prec, save_fp16 in (("fp32", False), ("fp16", True)):
+        ref_file = tmp_path / f"ref_{prec}.pt"
+        torch.save(gold[prec], ref_file)
+        em.load(str(ref_file))                                             # reference-written file -> mirror
+        assert len(em.id_coefficients) == 10 and all(c.dtype == torch.float32 for c in em.id_coefficients)
+        tol = 0.0 if prec == "fp32" else 1e-3
+        for got, want in zip(em.id_coefficients, coefs):
+            assert (got - want).abs().max().item() <= tol
+        em.save_fp16 = save_fp16
+        out_file = tmp_path / f"mirror_{prec}.pt"
+        em.save(str(out_file))                                             # mirror-written file == reference structure
+        mine = torch.load(out_file)
+        assert set(mine.keys()) == set(gold[prec].keys())
+        for k in mine:
+            assert type(mine[k]) is type(gold[prec][k]) and len(mine[k]) == len(gold[prec][k])
+            for a, b in zip(mine[k], gold[prec][k]):
+                assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+    em.save_fp16 = False
