@@ -23,8 +23,8 @@ class CLIPTextEngine:
         self.eps = eps
         self.loss_scale = float(loss_scale)
         sd, p = state_dict, prefix
-        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
-        w16 = lambda t: t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+        f32 = lambda t: ops.to_device(t, self.dev)
+        w16 = lambda t: ops.to_device(t, self.dev, self.dt)
         self.tok_table = f32(sd[p + "embeddings.token_embedding.weight"])
         self.pos_table = f32(sd[p + "embeddings.position_embedding.weight"])
         self.hidden = self.tok_table.shape[1]

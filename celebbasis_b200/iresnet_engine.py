@@ -23,13 +23,11 @@ class IResNetEngine:
         self.dev = torch.device(device)
         self.dt = dtype
         sd, p = state_dict, prefix
-        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
+        f32 = lambda t: ops.to_device(t, self.dev)
 
         def conv_bn(wkey, bnpre, cin_pad=None):
-            w = sd[wkey].float()
             s, b = _bn_fold(sd, bnpre)
-            wf = w * s.view(-1, 1, 1, 1)
-            return ops.pack_conv_weight(wf.to(self.dev), self.dt, cin_pad=cin_pad), f32(b)
+            return ops.pack_conv_weight(sd[wkey], self.dt, device=self.dev, cin_pad=cin_pad, out_scale=s), f32(b)
 
         self.stem_w, self.stem_b = conv_bn(p + "conv1.weight", p + "bn1.", cin_pad=8)
         self.stem_slope = f32(sd[p + "prelu.weight"])
@@ -58,7 +56,7 @@ class IResNetEngine:
         sf, shf = _bn_fold(sd, p + "features.")
         Wr = Wr * sf.view(nf, 1, 1)
         bias = bias * sf + shf
-        self.fc_w = Wr.permute(0, 2, 1).reshape(nf, 49 * 512).to(self.dev).to(self.dt).contiguous()  # column = pix*512 + c
+        self.fc_w = ops.to_device(Wr.permute(0, 2, 1).reshape(nf, 49 * 512), self.dev, self.dt)  # column = pix*512 + c
         self.fc_b = f32(bias)
 
     @torch.no_grad()

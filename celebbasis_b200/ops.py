@@ -203,14 +203,31 @@ class Geo:
 # ------------------------------------------------------------------------------------------------
 # weight packing (host side, once per checkpoint load)
 # ------------------------------------------------------------------------------------------------
-def pack_conv_weight(w, dtype, cin_pad=None, cout_pad=None):
-    """[Cout][Cin][kh][kw] -> [kh*kw][Cout_pad][Cin_pad] (tap-major, Cin contiguous), as one 2-D matrix."""
+def pack_conv_weight(w, dtype, cin_pad=None, cout_pad=None, out_scale=None, device=None):
+    """[Cout][Cin][kh][kw] fp32 (host or device) -> [kh*kw][Cout_pad][Cin_pad] (tap-major, Cin contiguous) as one 2-D
+    matrix on the device (cb_pack_conv_weight); out_scale [Cout] folds a following eval BatchNorm into the weights."""
     cout, cin, kh, kw = w.shape
     cin_pad = cin_pad or cin
     cout_pad = cout_pad or cout
-    out = torch.zeros(kh * kw, cout_pad, cin_pad, dtype=dtype, device=w.device)
-    out[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(dtype)
-    return out.view(kh * kw * cout_pad, cin_pad).contiguous()
+    dev = torch.device(device) if device is not None else w.device
+    w32 = w.detach().to(dev, torch.float32).contiguous()
+    out = torch.empty(kh * kw * cout_pad, cin_pad, dtype=dtype, device=dev)
+    sc = out_scale.detach().to(dev, torch.float32).contiguous() if out_scale is not None else None
+    _lib.check(_L().cb_pack_conv_weight(_p(w32), _p(out), _dt(out), cout, cin, kh, kw, cout_pad, cin_pad, _p(sc), _st()),
+               "cb_pack_conv_weight")
+    return out
+
+
+def to_device(t, device, dtype=torch.float32, scale=1.0):
+    """Checkpoint tensor (host or device, any float dtype) -> contiguous device tensor of `dtype`; the conversion to a
+    16-bit operand type is a cb kernel (cb_convert_f32), not a torch cast."""
+    x = t.detach().to(device, torch.float32).contiguous()
+    if dtype == torch.float32 and scale == 1.0:
+        return x
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    if x.numel():
+        _lib.check(_L().cb_convert_f32(_p(x), _p(out), _dt(out), x.numel(), float(scale), _st()), "cb_convert_f32")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

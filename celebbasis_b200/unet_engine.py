@@ -127,10 +127,10 @@ class UNetEngine:
     # weight preparation
     # ------------------------------------------------------------------------------------------
     def _w16(self, t):
-        return t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+        return ops.to_device(t, self.dev, self.dt)
 
     def _f32(self, t):
-        return t.detach().to(self.dev, torch.float32).contiguous()
+        return ops.to_device(t, self.dev)
 
     def _build(self, sd):
         cfg = self.cfg
@@ -150,13 +150,13 @@ class UNetEngine:
         def res(prefix, cin, cout):
             w = {"kind": "res", "cin": cin, "cout": cout}
             w["g1"], w["b1"] = self._f32(g(prefix + "in_layers.0.weight")), self._f32(g(prefix + "in_layers.0.bias"))
-            w["w1"] = ops.pack_conv_weight(g(prefix + "in_layers.2.weight").to(self.dev), self.dt)
+            w["w1"] = ops.pack_conv_weight(g(prefix + "in_layers.2.weight"), self.dt, device=self.dev)
             emb_ws.append(g(prefix + "emb_layers.1.weight"))
             emb_bs.append(g(prefix + "emb_layers.1.bias") + g(prefix + "in_layers.2.bias"))
             w["emb_off"] = self._emb_off
             self._emb_off += cout
             w["g2"], w["b2"] = self._f32(g(prefix + "out_layers.0.weight")), self._f32(g(prefix + "out_layers.0.bias"))
-            w["w2"] = ops.pack_conv_weight(g(prefix + "out_layers.3.weight").to(self.dev), self.dt)
+            w["w2"] = ops.pack_conv_weight(g(prefix + "out_layers.3.weight"), self.dt, device=self.dev)
             w["bias2"] = self._f32(g(prefix + "out_layers.3.bias"))
             if cin != cout:
                 w["ws"] = self._w16(g(prefix + "skip_connection.weight").reshape(cout, cin))
@@ -187,11 +187,11 @@ class UNetEngine:
 
         def resample(kind, prefix, c):
             key = prefix + ("op." if kind == "down" else "conv.")
-            return {"kind": kind, "c": c, "w": ops.pack_conv_weight(g(key + "weight").to(self.dev), self.dt),
+            return {"kind": kind, "c": c, "w": ops.pack_conv_weight(g(key + "weight"), self.dt, device=self.dev),
                     "b": self._f32(g(key + "bias"))}
 
         # stem
-        self.stem_w = ops.pack_conv_weight(g("input_blocks.0.0.weight").to(self.dev), self.dt, cin_pad=self.in_pad)
+        self.stem_w = ops.pack_conv_weight(g("input_blocks.0.0.weight"), self.dt, device=self.dev, cin_pad=self.in_pad)
         self.stem_b = self._f32(g("input_blocks.0.0.bias"))
 
         self.input_blocks = []   # list of layer lists (block 0 = stem handled separately)
@@ -230,7 +230,7 @@ class UNetEngine:
         del kvw
         # head
         self.out_g, self.out_b = self._f32(g("out.0.weight")), self._f32(g("out.0.bias"))
-        self.out_w = ops.pack_conv_weight(g("out.2.weight").to(self.dev), self.dt, cout_pad=self.out_pad)
+        self.out_w = ops.pack_conv_weight(g("out.2.weight"), self.dt, device=self.dev, cout_pad=self.out_pad)
         ob = torch.zeros(self.out_pad, dtype=torch.float32, device=self.dev)
         ob[: self.out_ch] = self._f32(g("out.2.bias"))
         self.out_bias = ob

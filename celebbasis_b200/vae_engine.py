@@ -20,9 +20,9 @@ class VAEEncoderEngine:
         self.dt = dtype
         self.rt = res_dtype
         sd, p = state_dict, prefix
-        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
-        w16 = lambda t: t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
-        pack = lambda k, **kw: ops.pack_conv_weight(sd[p + k].to(self.dev), self.dt, **kw)
+        f32 = lambda t: ops.to_device(t, self.dev)
+        w16 = lambda t: ops.to_device(t, self.dev, self.dt)
+        pack = lambda k, **kw: ops.pack_conv_weight(sd[p + k], self.dt, device=self.dev, **kw)
         ch, mult, nres = ddconfig["ch"], ddconfig["ch_mult"], ddconfig["num_res_blocks"]
         self.in_ch = ddconfig["in_channels"]
         self.in_pad = _round_up(self.in_ch, 8)
@@ -33,9 +33,9 @@ class VAEEncoderEngine:
         def res(pre, cin, cout):
             w = {"cin": cin, "cout": cout,
                  "g1": f32(sd[pre + "norm1.weight"]), "b1": f32(sd[pre + "norm1.bias"]),
-                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"].to(self.dev), self.dt), "c1b": f32(sd[pre + "conv1.bias"]),
+                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"], self.dt, device=self.dev), "c1b": f32(sd[pre + "conv1.bias"]),
                  "g2": f32(sd[pre + "norm2.weight"]), "b2": f32(sd[pre + "norm2.bias"]),
-                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"].to(self.dev), self.dt), "c2b": f32(sd[pre + "conv2.bias"])}
+                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"], self.dt, device=self.dev), "c2b": f32(sd[pre + "conv2.bias"])}
             if cin != cout:
                 w["ws"] = w16(sd[pre + "nin_shortcut.weight"].reshape(cout, cin))
                 w["bs"] = f32(sd[pre + "nin_shortcut.bias"])
@@ -55,7 +55,7 @@ class VAEEncoderEngine:
             down = None
             if i != len(mult) - 1:
                 dk = p + f"encoder.down.{i}.downsample.conv."
-                down = {"w": ops.pack_conv_weight(sd[dk + "weight"].to(self.dev), self.dt), "b": f32(sd[dk + "bias"]), "c": bin_}
+                down = {"w": ops.pack_conv_weight(sd[dk + "weight"], self.dt, device=self.dev), "b": f32(sd[dk + "bias"]), "c": bin_}
             self.levels.append((blocks, down))
         self.mid1 = res(p + "encoder.mid.block_1.", bin_, bin_)
         self.mid2 = res(p + "encoder.mid.block_2.", bin_, bin_)
@@ -136,8 +136,8 @@ class VAEDecoderEngine:
         self.dt = dtype
         self.rt = res_dtype or dtype
         sd, p = state_dict, prefix
-        f32 = lambda t: t.detach().to(self.dev, torch.float32).contiguous()
-        w16 = lambda t: t.detach().to(self.dev, torch.float32).to(self.dt).contiguous()
+        f32 = lambda t: ops.to_device(t, self.dev)
+        w16 = lambda t: ops.to_device(t, self.dev, self.dt)
         ch, mult, nres = ddconfig["ch"], ddconfig["ch_mult"], ddconfig["num_res_blocks"]
         zc = ddconfig["z_channels"]
         self.zc, self.zpad = zc, _round_up(zc, 8)
@@ -153,9 +153,9 @@ class VAEDecoderEngine:
         def res(pre, cin, cout):
             w = {"cin": cin, "cout": cout,
                  "g1": f32(sd[pre + "norm1.weight"]), "b1": f32(sd[pre + "norm1.bias"]),
-                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"].to(self.dev), self.dt), "c1b": f32(sd[pre + "conv1.bias"]),
+                 "w1": ops.pack_conv_weight(sd[pre + "conv1.weight"], self.dt, device=self.dev), "c1b": f32(sd[pre + "conv1.bias"]),
                  "g2": f32(sd[pre + "norm2.weight"]), "b2": f32(sd[pre + "norm2.bias"]),
-                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"].to(self.dev), self.dt), "c2b": f32(sd[pre + "conv2.bias"])}
+                 "w2": ops.pack_conv_weight(sd[pre + "conv2.weight"], self.dt, device=self.dev), "c2b": f32(sd[pre + "conv2.bias"])}
             if cin != cout:
                 w["ws"] = w16(sd[pre + "nin_shortcut.weight"].reshape(cout, cin))
                 w["bs"] = f32(sd[pre + "nin_shortcut.bias"])
@@ -165,7 +165,7 @@ class VAEDecoderEngine:
 
         bin_ = ch * mult[-1]
         self.c_in = bin_
-        self.conv_in_w = ops.pack_conv_weight(sd[p + "decoder.conv_in.weight"].to(self.dev), self.dt, cin_pad=self.zpad)
+        self.conv_in_w = ops.pack_conv_weight(sd[p + "decoder.conv_in.weight"], self.dt, device=self.dev, cin_pad=self.zpad)
         self.conv_in_b = f32(sd[p + "decoder.conv_in.bias"])
         self.mid1 = res(p + "decoder.mid.block_1.", bin_, bin_)
         self.mid2 = res(p + "decoder.mid.block_2.", bin_, bin_)
@@ -186,11 +186,11 @@ class VAEDecoderEngine:
             up = None
             if i != 0:
                 uk = p + f"decoder.up.{i}.upsample.conv."
-                up = {"w": ops.pack_conv_weight(sd[uk + "weight"].to(self.dev), self.dt), "b": f32(sd[uk + "bias"]), "c": bin_}
+                up = {"w": ops.pack_conv_weight(sd[uk + "weight"], self.dt, device=self.dev), "b": f32(sd[uk + "bias"]), "c": bin_}
             self.levels.append((blocks, up))
         self.no_g, self.no_b = f32(sd[p + "decoder.norm_out.weight"]), f32(sd[p + "decoder.norm_out.bias"])
         self.out_rows = 16
-        self.conv_out_w = ops.pack_conv_weight(sd[p + "decoder.conv_out.weight"].to(self.dev), self.dt, cout_pad=self.out_rows)
+        self.conv_out_w = ops.pack_conv_weight(sd[p + "decoder.conv_out.weight"], self.dt, device=self.dev, cout_pad=self.out_rows)
         cb = torch.zeros(self.out_rows, dtype=torch.float32, device=self.dev)
         cb[: self.out_ch] = f32(sd[p + "decoder.conv_out.bias"])
         self.conv_out_b = cb

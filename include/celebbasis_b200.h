@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 2
+#define CB_ABI_VERSION 3
 #define CB_GN_WS_BYTES 131072
 
 /* element types */
@@ -307,6 +307,18 @@ int cb_attention_bwd_dq(const void* Q, long long ldq, const void* K, long long l
                         const void* O, long long ldo, const void* dO, long long lddo, const float* lse, float* delta,
                         void* dQ, long long lddq, void* dS, long long ldds, int dtype, int images, int heads, int nq,
                         int nk, int d, float scale, int causal, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Checkpoint-load-time packing (once per load_state_dict; the reference keeps fp32 nn.Parameters,
+ * ldm/modules/diffusionmodules/openaimodel.py:201-241, and lets cuDNN choose layouts per call).
+ * cb_pack_conv_weight: [Cout][Cin][kh][kw] fp32 -> [kh*kw][Cout_pad][Cin_pad] 16-bit (tap-major, Cin contiguous, zero
+ *   padded) -- the B operand of the implicit-GEMM convolution; out_scale (optional, [Cout]) folds an eval BatchNorm
+ *   that follows the convolution (ldm/modules/id_embedding/iresnet.py:41-58) into the weights.
+ * cb_convert_f32: out[i] = (o_dtype) (scale * x[i]) for any n.
+ * ------------------------------------------------------------------------------------------- */
+int cb_pack_conv_weight(const float* w, void* out, int o_dtype, int cout, int cin, int kh, int kw, int cout_pad,
+                        int cin_pad, const float* out_scale, void* stream);
+int cb_convert_f32(const float* x, void* out, int o_dtype, long long n, float scale, void* stream);
 
 #ifdef __cplusplus
 }
