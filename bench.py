@@ -30,19 +30,6 @@ METRIC = "celeb-basis training steps/sec (SD-v1 UNet 512^2, bs=1/GPU)"
 WORKLOAD = "configs[1]: single identity per GPU, 512x512, bs=1, SD-v1 UNet + CLIP text fwd/bwd + VAE encode + CosFace R100, AdamW on the 525,312 MLP weights"
 
 
-def _ncu_traffic():
-    """DRAM bytes per cb_gemm launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches)
-    from the newest committed ncu pass under profiles/ (written by the command in its "source" field), or None."""
-    import glob
-    best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic_*.json"))):
-        try:
-            best = json.load(open(f))
-        except Exception:
-            pass
-    return None if best is None else best.get("traffic_bytes_per_launch")
-
-
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -157,6 +144,7 @@ def cpu_reference_steps(n_timed, budget_s, min_steps=3):
     from celebbasis_b200.tokenizer import SyntheticCLIPTokenizer
     from oracle import torch_ref
     info = pick_cpu_threads()
+    min_steps = int(os.environ.get("CB_BENCH_CPU_MIN_STEPS", min_steps))      # test knob (tests/test_host_logic.py)
     params = workload.model_params("full")
     om = torch_ref.OracleModel(params, clip_layers=12)
     om.load_state_dict(synth.synth_state_dict(om, seed=0))
@@ -207,7 +195,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": bench_config(args.gpus),
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": info["threads"], "kind": "port", "sample": sample,
                          "thread_calibration_ms": info["calibration_ms"], "loss_first": losses[0]},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,14 +203,41 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def bench_config(world):
+    """The workload description both arms print (identical dicts => the driver's same_config check holds)."""
+    return {"workload": WORKLOAD, "per_gpu_batch": 1, "parallelism": f"dp{world}",
+            "l2": "inputs larger than L2: 2.1 GB of 16-bit weights + ~4 GB of activations are streamed every step (L2 = 126 MB)"}
+
+
+def _file_sha1(path):
+    import hashlib
+    with open(path, "rb") as f:
+        return hashlib.sha1(f.read()).hexdigest()
+
+
+def _ncu_traffic():
+    """DRAM bytes per cb_gemm launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the step's launches) from
+    the newest committed `ncu` pass under profiles/ -- reported only if that pass was taken on THIS version of the kernel
+    (the pass records the sha1 of cb_gemm.cu); otherwise null, never a stale constant."""
+    import glob
+    cur = _file_sha1(os.path.join(ROOT, "celebbasis_b200", "csrc", "cb_gemm.cu"))
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic*.json")), reverse=True):
+        try:
+            j = json.load(open(f))
+        except Exception:
+            continue
+        if j.get("kernel_source_sha1") == cur:
+            return j.get("traffic_bytes_per_launch"), os.path.basename(f)
+    return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from celebbasis_b200 import dist as cbd
     from celebbasis_b200 import lib, ops, synth, workload
-    from celebbasis_b200.tokenizer import SyntheticCLIPTokenizer
-    from celebbasis_b200.train_step import CelebBasisStep
-    from oracle import torch_ref  # only to enumerate checkpoint keys/shapes and for the cpu_baseline leg
+    from celebbasis_b200.compat import pytorch_lightning as pl
+    from ldm.models.diffusion.ddpm import LatentDiffusion
 
     world, rank, local = cbd.init()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
@@ -230,63 +245,52 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     assert lib.load().cb_device_ok() == 1, "not an sm_100 device"
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-
-    params = workload.model_params("full")
-    om = torch_ref.OracleModel(params, clip_layers=12)
-    sd = synth.synth_state_dict(om, seed=0)
-    del om
-    eng = CelebBasisStep(params, sd, synth.synth_celeb_basis(seed=0), dev, tokenizer=SyntheticCLIPTokenizer(),
-                         lr=cbd.scaled_lr(5e-3, 1) if world > 1 else 5e-3)
-    del sd
     B = 1
-    # ---- host-side inputs (pinned) and static device buffers -------------------------------------------------
+
+    # ---- the model through the reference-facing API: ldm.models.diffusion.ddpm.LatentDiffusion(**aigc_id.yaml params) ----
+    params = workload.model_params("full")
+    params["cond_stage_config"]["params"].update(device="cuda")
+    model = LatentDiffusion(**params)
+    model.load_state_dict(synth.synth_state_dict(model, seed=0), strict=False)
+    model = model.to(dev)
+    model.cond_stage_model.celeb_embeddings = synth.synth_celeb_basis(seed=0).to(dev)
+    model.learning_rate = cbd.scaled_lr(5e-3, B) if world > 1 else 5e-3      # main_id_embed.py:778-779
+    model.train()
+
+    # ---- host-side batches (pinned, as a DataLoader with pin_memory yields them): face_id.py:598-644 layout ------------
     n_host = 4
     host = []
     for i in range(n_host):
-        batch, draws = workload.synth_batch("full", B=B, seed=1234 + 101 * rank, step=i)
-        batch["image_ori"]["ids"] = torch.full((B, 2), rank % 10, dtype=torch.long)
-        host.append({"image": batch["image"].pin_memory(), "faces": batch["image_ori"]["faces"].pin_memory(),
-                     "t": draws["t"].pin_memory(), "noise": draws["noise"].pin_memory(),
-                     "eps": draws["posterior_eps"].pin_memory(), "caption": batch["caption"],
-                     "ids": batch["image_ori"]["ids"]})
-    st = {k: host[0][k].to(dev) for k in ("image", "faces", "t", "noise", "eps")}
-    ids, map_np, _ = eng.prepare(host[0]["caption"])
-    ids_dev, map_dev = ids.to(dev), torch.from_numpy(map_np).to(dev)
-    ids_person = host[0]["ids"]
-    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in ("image", "faces", "t", "noise", "eps"))
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        batch, _ = workload.synth_batch("full", B=B, seed=1234 + 101 * rank, step=i)
+        batch["image"] = batch["image"].pin_memory()
+        batch["image_ori"]["faces"] = batch["image_ori"]["faces"].pin_memory()
+        batch["image_ori"]["ids"] = torch.full((B, 2), rank % 10, dtype=torch.long).pin_memory()
+        host.append(batch)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (host[0]["image"], host[0]["image_ori"]["faces"],
+                                                           host[0]["image_ori"]["ids"], host[0]["image_ori"]["num_ids"]))
+    h2d_bytes += 4 * 64 * 64 * 4 + 77 * 8 + 77 * 4        # posterior eps (CPU generator, as the reference), token ids, row map
 
-    def step_device():
-        return eng.run(st["image"], st["faces"], ids_person, ids_dev, map_dev, st["t"], st["noise"], st["eps"])
-
-    # ---- eager warm-up (also builds every lazily created buffer), then capture the step as ONE CUDA graph -----
-    for _ in range(2):
-        loss_dev = step_device()
+    # ---- first API step builds the fused engine: eager warm-up (GEMM autotune), then the three step graphs -------------
+    opt = model.configure_optimizers()
+    dev_batch = {"image": host[0]["image"].to(dev), "caption": host[0]["caption"],
+                 "image_ori": {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host[0]["image_ori"].items()}}
+    loss, _ = model.shared_step(dev_batch)
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
     torch.cuda.synchronize()
-    graph, use_graph = None, not args.no_graph
-    n_before = lib.launch_count()
-    if use_graph:
-        try:
-            graph = torch.cuda.CUDAGraph()
-            ops.GEMM_RECORD = []
-            with torch.cuda.graph(graph):
-                loss_dev = step_device()
-            gemm_record, ops.GEMM_RECORD = ops.GEMM_RECORD, None
-        except Exception as e:  # pragma: no cover
-            sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); running eagerly\n")
-            graph, use_graph, ops.GEMM_RECORD = None, False, None
-            torch.cuda.synchronize()
-    if not use_graph:
-        ops.GEMM_RECORD = []
-        loss_dev = step_device()
-        gemm_record, ops.GEMM_RECORD = ops.GEMM_RECORD, None
-    launches_per_step = lib.launch_count() - n_before + 2      # + AdamW + step bump
+    G = model._fused
+    assert G is not None, "the fused CUDA-graph step did not engage"
+    eng = G.eng
+    launches_per_step = G.launches["pipe"] + 1              # chain + next batch's front end + AdamW
+
+    # ---- leg 1 (`value`): inputs resident in HBM; one step = one replay of G_pipe (this batch's trainable chain || the
+    #      next batch's frozen front end) + gradient all-reduce + AdamW ---------------------------------------------------
+    G.load_next(dev_batch["image"], dev_batch["image_ori"]["faces"], torch.randn(list(G.peps_n.shape)))
+    G.prefetch()
 
     def one_step():
-        if graph is not None:
-            graph.replay()
-        else:
-            step_device()
+        G.step(lookahead=True)
         cbd.allreduce_mean_(eng.grad)     # the single per-step collective (no-op at N=1)
         eng.optimizer_step()
 
@@ -305,39 +309,73 @@ def run_ours(args):
         cbd.barrier()
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         one_step()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms_total = timed(one_step, args.steps)
-    ms_per_step = ms_total / args.steps
+    ms_per_step = timed(one_step, args.steps) / args.steps
     value = world * B * 1000.0 / ms_per_step
+    # un-pipelined reference point: front end, then chain, back to back
+    def serial_step():
+        G.prefetch()
+        G.step(lookahead=False)
+        cbd.allreduce_mean_(eng.grad)
+        eng.optimizer_step()
+    serial_step()
+    ms_serial = timed(serial_step, max(3, args.steps // 2)) / max(3, args.steps // 2)
 
-    # ---- e2e: host buffers -> H2D -> step -> D2H loss, every step ------------------------------------------------
-    counter = {"i": 0}
+    # ---- leg 2 (`e2e`): the call a user of the reference makes -- Trainer.fit(model, data) (main_id_embed.py:748,812)
+    #      over HOST batches: per step H2D of the batch, tokenisation + row map on the host, t / noise draws, the fused
+    #      shared_step, loss.backward(), gradient all-reduce, FusedAdamW.step(), and a D2H read of the loss ------------------
+    class HostData:
+        def __init__(self, n):
+            self.n = n
 
-    def e2e_step():
-        h = host[counter["i"] % n_host]
-        counter["i"] += 1
-        for k in ("image", "faces", "t", "noise", "eps"):
-            st[k].copy_(h[k], non_blocking=True)
-        one_step()
-        loss_host.copy_(loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
+        def __iter__(self):
+            for i in range(self.n):
+                yield host[i % n_host]
 
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    class Timer(pl.Callback):
+        def __init__(self, w, k):
+            self.w, self.k, self.ms, self.last_loss = w, k, None, None
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def on_train_batch_start(self, trainer, module, batch, batch_idx, dl=0):
+            if batch_idx == self.w:
+                torch.cuda.synchronize()
+                cbd.barrier()
+                self.e0.record()
+
+        def on_train_batch_end(self, trainer, module, outputs, batch, batch_idx, dl=0):
+            self.last_loss = float(outputs["loss"].item())       # D2H read of the step's loss, every step
+            if batch_idx == self.w + self.k - 1:
+                self.e1.record()
+                torch.cuda.synchronize()
+                self.ms = self.e0.elapsed_time(self.e1)
+
+    timer = Timer(warm, args.steps)
+    trainer = pl.Trainer(gpus=f"{local},", max_steps=warm + args.steps, callbacks=[timer])
+    trainer.fit(model, train_dataloaders=HostData(warm + args.steps))
+    ms_e2e_t = torch.tensor([timer.ms], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e_t.item()) / args.steps
     clk = clocks.stop() if rank == 0 else None
-    final_loss = float(loss_host.item())
+    final_loss = timer.last_loss
 
-    # ---- roofline of the dominant kernel: replay exactly this step's GEMM launches as their own graph ----------
+    # ---- roofline of the dominant kernel: replay exactly one step's GEMM launches as their own graph ------------------
     roof = None
     if rank == 0:
         import ctypes
         from celebbasis_b200.lib import GemmDesc
         L = lib.load()
+        ops.GEMM_RECORD = []
+        G._body_pre()
+        G._body_main()
+        torch.cuda.synchronize()
+        gemm_record, ops.GEMM_RECORD = ops.GEMM_RECORD, None
         descs = [GemmDesc.from_buffer_copy(b) for b, _ in gemm_record]
         flops = sum(f for _, f in gemm_record)
         sp = ctypes.c_void_p
@@ -365,37 +403,45 @@ def run_ours(args):
         peaks, src = _peaks()
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         ach = flops / (gemm_ms * 1e-3) / 1e12
+        traffic, traffic_src = _ncu_traffic()
         roof = {"bound": "tensor", "kernel": "cb_gemm_kernel (tcgen05 GEMM / implicit-GEMM conv, all instantiations)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": _ncu_traffic(),
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": len(descs), "avg_launch_us": gemm_ms * 1e3 / len(descs),
                 "algorithmic_gflop_per_step": flops / 1e9, "gemm_ms_per_step": gemm_ms,
-                "gemm_share_of_step": gemm_ms / ms_per_step}
+                "gemm_share_of_serial_step": gemm_ms / ms_serial,
+                "whole_step_tflops": 2861.0 / ms_per_step, "whole_step_frac": 2861.0 / ms_per_step / peak}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on this box's host cores --------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        del eng, graph
+        del model, G, eng, trainer, opt
         torch.cuda.empty_cache()
-        times, _, threads = cpu_reference_steps(2, budget_s=60.0)
-        sec = min(times)
-        cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": threads, "kind": "port",
-               "sample": f"{len(times)} full bs=1 step(s) (fwd+bwd+AdamW, fp32, oracle/torch_ref.py on host cores); best"}
+        times, _, info = cpu_reference_steps(2, budget_s=90.0)
+        sec, n_timed = summarize_cpu(times)
+        cpu = {"value": 1.0 / sec, "unit": "steps/s", "cores": info["threads"], "kind": "port",
+               "sample": f"{len(times)} full bs=1 steps (fwd+bwd+AdamW, fp32, oracle/torch_ref.py) on {info['threads']} "
+                         f"threads (affinity {info['affinity']}, cgroup quota {info['cgroup_quota']}); first dropped as "
+                         f"cold, median of the other {n_timed}; per-step s: {[round(t, 1) for t in times]}"}
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate+residual (reference: f32 with TF32 convs)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "cuda_graph": bool(use_graph),
-                       "l2": "inputs larger than L2: 2.1 GB fp16 weights + ~4 GB activations are streamed every step (L2 = 126 MB)",
-                       "v100_published_it_s": 2.75, "final_loss": final_loss},
+            "config": bench_config(world),
             "e2e": {"value": world * B * 1000.0 / ms_e2e, "unit": "steps/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "api": "celebbasis_b200.compat pytorch_lightning.Trainer.fit(ldm LatentDiffusion, host batches): "
+                           "training_step -> loss.backward() -> grad all-reduce -> FusedAdamW.step() -> loss.item()"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
+            "pipeline": {"ms_per_step_pipelined": ms_per_step, "ms_per_step_serial": ms_serial,
+                         "note": "pipelined: the frozen no-grad front end (VAE encode, CosFace R100) of batch i+1 runs "
+                                 "concurrently with batch i's trainable chain; every step does all of its work once"},
+            "notes": {"cuda_graph": True, "final_loss": final_loss, "v100_published_it_s": 2.75},
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
@@ -409,7 +455,6 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

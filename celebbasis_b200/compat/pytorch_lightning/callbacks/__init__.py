@@ -11,6 +11,7 @@ class ModelCheckpoint(Callback):
         self.save_last, self.save_top_k, self.monitor = save_last, save_top_k, monitor
         self.every_n_train_steps, self.every_n_epochs = every_n_train_steps, every_n_epochs
         self.last_model_path = ""
+        self._last_saved_step = -1
 
     def _path(self, trainer):
         name = self.filename or "{epoch:06}"
@@ -30,7 +31,8 @@ class ModelCheckpoint(Callback):
 
     def on_train_batch_end(self, trainer, pl_module, outputs, batch, batch_idx, dataloader_idx=0):
         n = self.every_n_train_steps
-        if n and trainer.global_step > 0 and trainer.global_step % n == 0:
+        if n and trainer.global_step > 0 and trainer.global_step % n == 0 and trainer.global_step != self._last_saved_step:
+            self._last_saved_step = trainer.global_step      # accumulate_grad_batches > 1: one save per optimiser step
             self._save(trainer, self._path(trainer))
 
     def on_train_end(self, trainer, pl_module):

@@ -63,6 +63,10 @@ class Trainer:
         self.default_root_dir = default_root_dir or os.getcwd()
         self.gradient_clip_val = float(gradient_clip_val or 0.0)
         self.resume_from_checkpoint = resume_from_checkpoint
+        if resume_from_checkpoint:
+            import warnings
+            warnings.warn("Trainer stand-in: resume_from_checkpoint is accepted for CLI compatibility but optimiser / "
+                          "step state is not restored (the reference resumes weights through --actual_resume)")
         self.extra = kwargs
         self.global_step = 0
         self.current_epoch = 0
@@ -121,13 +125,19 @@ class Trainer:
     # ---- checkpointing ------------------------------------------------------------------------------------------------
     def save_checkpoint(self, filepath, weights_only=False):
         model = self.lightning_module
-        ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
-                "global_step": self.global_step, "epoch": self.current_epoch,
-                "pytorch-lightning_version": "1.5.9"}
-        if not weights_only:
-            ckpt["optimizer_states"] = [o.state_dict() for o in self.optimizers]
+        # the ~4 GB CPU copy of the state dict is materialised only if somebody still wants it after the module's
+        # on_save_checkpoint hook (the CelebBasis LatentDiffusion clears the checkpoint and writes embeddings.pt), rank 0 only
+        ckpt = {"global_step": self.global_step, "epoch": self.current_epoch, "pytorch-lightning_version": "1.5.9",
+                "state_dict": None}
         self._module_hook("on_save_checkpoint", ckpt)
         self._call("on_save_checkpoint", ckpt)
+        if "state_dict" in ckpt and ckpt["state_dict"] is None:
+            if self.global_rank == 0:
+                ckpt["state_dict"] = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+                if not weights_only:
+                    ckpt["optimizer_states"] = [o.state_dict() for o in self.optimizers]
+            else:
+                del ckpt["state_dict"]
         if self.global_rank == 0:
             os.makedirs(os.path.dirname(os.path.abspath(filepath)), exist_ok=True)
             torch.save(ckpt, filepath)
@@ -160,6 +170,43 @@ class Trainer:
             g.copy_(flat[off:off + n].view_as(g))
             off += n
 
+    def _lookahead(self, loader):
+        """(index, batch on the device, next batch on the device or None): one batch of look-ahead, each batch moved once."""
+        it = iter(loader)
+        try:
+            cur = _move(next(it), self.device)
+        except StopIteration:
+            return
+        idx = 0
+        while True:
+            try:
+                nxt = _move(next(it), self.device)
+            except StopIteration:
+                nxt = None
+            yield idx, cur, nxt
+            if nxt is None:
+                return
+            cur, idx = nxt, idx + 1
+
+    def _shard_loader(self, loader):
+        """Lightning's replace_sampler_ddp: with world_size > 1 every rank must see a disjoint shard of the dataset (the
+        reference relies on it: main_id_embed.py seeds all ranks identically and scales the LR by ngpu, :778-779)."""
+        if self.world_size <= 1:
+            return loader
+        from torch.utils.data import DataLoader
+        from torch.utils.data.distributed import DistributedSampler
+        if not isinstance(loader, DataLoader) or isinstance(getattr(loader, "sampler", None), DistributedSampler):
+            return loader
+        if loader.batch_size is None:
+            return loader
+        from torch.utils.data import RandomSampler
+        shuffle = isinstance(loader.sampler, RandomSampler)
+        sampler = DistributedSampler(loader.dataset, num_replicas=self.world_size, rank=self.global_rank, shuffle=shuffle)
+        return DataLoader(loader.dataset, batch_size=loader.batch_size, sampler=sampler, num_workers=loader.num_workers,
+                          collate_fn=loader.collate_fn, pin_memory=loader.pin_memory, drop_last=loader.drop_last,
+                          worker_init_fn=loader.worker_init_fn, persistent_workers=loader.persistent_workers
+                          if loader.num_workers > 0 else False)
+
     def fit(self, model, datamodule=None, train_dataloaders=None):
         self.lightning_module = model
         model.trainer = self
@@ -176,6 +223,7 @@ class Trainer:
             loader = datamodule.train_dataloader()
         else:
             loader = train_dataloaders
+        loader = self._shard_loader(loader)
         self.optimizers, self.lr_schedulers = self._unpack_optimizers(model.configure_optimizers())
         self._call("setup", "fit")
         self._call("on_pretrain_routine_start")
@@ -185,8 +233,13 @@ class Trainer:
         try:
             while not done:
                 self._call("on_train_epoch_start")
-                for batch_idx, batch in enumerate(loader):
-                    batch = _move(batch, self.device)
+                sampler = getattr(loader, "sampler", None)
+                if hasattr(sampler, "set_epoch"):
+                    sampler.set_epoch(self.current_epoch)      # Lightning does this for the DistributedSampler it installs
+                for batch_idx, batch, nxt in self._lookahead(loader):
+                    stage = getattr(model, "stage_next_batch", None)
+                    if callable(stage):
+                        stage(nxt)           # the module may overlap the next batch's frozen front end with this step
                     self._call("on_train_batch_start", batch, batch_idx, 0)
                     self._module_hook("on_train_batch_start", batch, batch_idx, 0)
                     out = model.training_step(batch, batch_idx)

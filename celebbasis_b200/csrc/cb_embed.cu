@@ -254,6 +254,24 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+
+__global__ void ema_rows_kernel(float* __restrict__ table, const long long* __restrict__ idx, int idx_stride,
+                                const float* __restrict__ src, int B, int row, int n_rows, float m) {
+    pdl_sync();
+    const int b = blockIdx.y;
+    const long long id = idx[(size_t)b * idx_stride];
+    if (id < 0 || id >= n_rows) return;
+    // samples of one batch that share an identity must update in batch order (the reference loops b = 0..B-1): only the
+    // block of the LAST sample with this identity folds all of them, in order
+    for (int b2 = b + 1; b2 < B; ++b2)
+        if (idx[(size_t)b2 * idx_stride] == id) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row; i += gridDim.x * blockDim.x) {
+        float v = table[(size_t)id * row + i];
+        for (int b1 = 0; b1 <= b; ++b1)
+            if (idx[(size_t)b1 * idx_stride] == id) v = m * v + (1.f - m) * src[(size_t)b1 * row + i];
+        table[(size_t)id * row + i] = v;
+    }
+}
 }  // namespace cb
 
 using namespace cb;
@@ -377,5 +395,17 @@ extern "C" int cb_posterior_sample(const float* moments, const float* eps, float
 CB_LAUNCH((posterior_sample_kernel), (unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream), moments, eps, z, N, Cz, HW, scale);
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
+    return 0;
+}
+
+extern "C" int cb_ema_rows(float* table, const long long* idx, int idx_stride, const float* src, int B, int row, int n_rows,
+                           float momentum, void* stream) {
+    CB_REQUIRE(table && idx && src && B > 0 && row > 0 && n_rows > 0 && idx_stride > 0, CB_ERR_ARG, "ema_rows: bad args");
+    const int gx = ceil_div(row, 256);
+    dim3 grid((unsigned)(gx < 8 ? gx : 8), (unsigned)B);
+    CB_LAUNCH((ema_rows_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), table, idx, idx_stride, src, B, row,
+              n_rows, momentum);
+    CB_CUDA(cudaGetLastError());
+    count_launches(1);
     return 0;
 }

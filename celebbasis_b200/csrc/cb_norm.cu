@@ -821,6 +821,10 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // flags: bit 0 = fuse SiLU, bit 1 = CB_GN_NO_GRID_BARRIER (never launch the single-kernel variant whose CTAs spin on a
+    // grid-wide arrival counter: required on any stream that runs concurrently with another GroupNorm stream)
+    const bool allow_fused = (act_silu & CB_GN_NO_GRID_BARRIER) == 0;
+    act_silu &= 1;
     // ws: CB_GN_WS_BYTES; [0, 2*N*G doubles) group sums of the two-kernel path, or per-CTA partial slots of the fused
     // path; the last 8 bytes hold the grid arrival counter
     unsigned* counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + CB_GN_WS_BYTES - 8);
@@ -831,7 +835,7 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
         const int sms = device_sm_count();
         const int nb = sms / N;
         const int xes = x_dtype == CB_F32 ? 4 : 2;
-        if (nb >= 1) {
+        if (nb >= 1 && allow_fused) {
             const int rpbf = ceil_div(HW, nb);
             const size_t smem = (size_t)rpbf * C * xes;
             if (smem <= 200 * 1024 && ((size_t)C * xes) % 16 == 0) {
@@ -898,10 +902,12 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
     CB_REQUIRE(dx_dtype == CB_F32 || dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
+    const bool allow_fused = (act_silu & CB_GN_NO_GRID_BARRIER) == 0;
+    act_silu &= 1;
     {
         const int sms = device_sm_count();
         const int nb = sms / N;
-        if (nb >= 1) {
+        if (nb >= 1 && allow_fused) {
             const int rpbf = ceil_div(HW, nb);
             const int xes = x_dtype == CB_F32 ? 4 : 2, ges = dy_dtype == CB_F32 ? 4 : 2;
             const size_t smem = (((size_t)rpbf * C * xes + 127) & ~(size_t)127) + (size_t)rpbf * C * ges;   // staged x + dy

@@ -44,6 +44,14 @@ def init(backend=None):
     return world, rank, local
 
 
+def world_size():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
 def allreduce_mean_(flat_grad):
     """In-place mean over ranks of the flat trainable-gradient buffer (the single per-step collective)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

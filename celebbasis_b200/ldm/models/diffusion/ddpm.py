@@ -79,6 +79,30 @@ class _MSEFn(torch.autograd.Function):
         return out, None
 
 
+def _plain(cfg):
+    """OmegaConf node / dict / list -> plain python containers."""
+    if isinstance(cfg, dict):
+        return {k: _plain(v) for k, v in cfg.items()}
+    if isinstance(cfg, (list, tuple)):
+        return [_plain(v) for v in cfg]
+    return cfg
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """The fused step computes loss AND d(loss)/d(W, b) in one CUDA-graph replay; this node hands those gradients to
+    autograd so that the reference's `loss.backward(); optimizer.step()` contract (Lightning's loop) is unchanged."""
+
+    @staticmethod
+    def forward(ctx, W, b, loss_dev, gW, gb):
+        ctx.save_for_backward(gW, gb)
+        return loss_dev.reshape(()).clone()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        gW, gb = ctx.saved_tensors
+        return gW * dloss, gb * dloss, None, None, None
+
+
 class DDPM(_Base):
     def __init__(self, unet_config, timesteps=1000, beta_schedule="linear", loss_type="l2", ckpt_path=None,
                  ignore_keys=[], load_only_unet=False, monitor="val/loss", use_ema=True, first_stage_key="image",
@@ -195,6 +219,15 @@ class LatentDiffusion(DDPM):
                  conditioning_key=None, scale_factor=1.0, scale_by_std=False, *args, **kwargs):
         self.num_timesteps_cond = default(num_timesteps_cond, 1)
         self.scale_by_std = scale_by_std
+        self._engine_params = _plain(dict(
+            unet_config=kwargs.get("unet_config"), first_stage_config=first_stage_config,
+            personalization_config=personalization_config, scale_factor=scale_factor,
+            timesteps=kwargs.get("timesteps", 1000), linear_start=kwargs.get("linear_start", 1e-4),
+            linear_end=kwargs.get("linear_end", 2e-2)))
+        self._fused = None            # StepGraphs of the CUDA-graph training step (built on first use)
+        self._fused_sig = None
+        self._staged_next = None      # look-ahead batch handed over by the training loop (stage_next_batch)
+        self.fused_step = os.environ.get("CB_FUSED_STEP", "1") != "0"
         assert self.num_timesteps_cond <= kwargs['timesteps']
         if conditioning_key is None:
             conditioning_key = 'concat' if concat_mode else 'crossattn'
@@ -314,8 +347,99 @@ class LatentDiffusion(DDPM):
 
     # ---- the training step (ddpm.py:921-936,948-1049,1069-1116) ---------------------------------------------------
     def shared_step(self, batch, **kwargs):
+        if self._fused_applicable(batch):
+            return self._fused_shared_step(batch)
         x, c = self.get_input(batch, self.first_stage_key)
         return self(x, c['caption'], face_img=c['image'], image_ori=c['image_ori'])
+
+    # ---- fused training step: the whole of shared_step + backward as CUDA-graph replays ---------------------------
+    def stage_next_batch(self, batch):
+        """Optional look-ahead hook for the training loop: the batch that the NEXT training_step call will receive (the
+        same object).  Its frozen front end (VAE encode, CosFace features) then overlaps this step's UNet work."""
+        self._staged_next = batch
+
+    def _fused_applicable(self, batch):
+        if not (self.fused_step and self.training and self.cond_stage_trainable and not self.unfreeze_model):
+            return False
+        if self.embedding_reg_weight > 0 or self.original_elbo_weight != 0 or self.l_simple_weight != 1.:
+            return False
+        io = batch.get("image_ori") if isinstance(batch, dict) else None
+        x = batch.get(self.first_stage_key) if isinstance(batch, dict) else None
+        if io is None or not torch.is_tensor(x) or x.dim() != 4 or x.shape[-1] != 3 or x.dtype != torch.float32:
+            return False
+        faces, nid = io.get("faces"), io.get("num_ids")
+        if not torch.is_tensor(faces) or faces.shape[:3] != x.shape[:3] or faces.shape[-1] % 3 != 0:
+            return False
+        if nid is None or not bool((torch.as_tensor(nid).cpu() == 1).all()):
+            return False           # two / three persons per prompt: the eager per-module path handles them
+        if getattr(self.cond_stage_model, "celeb_embeddings", None) is None:
+            return False
+        return next(self.model.parameters()).is_cuda
+
+    def _fused_build(self, batch):
+        from celebbasis_b200.step_graph import StepGraphs
+        from celebbasis_b200.train_step import CelebBasisStep
+        x = batch[self.first_stage_key]
+        faces = batch["image_ori"]["faces"]
+        B, hw, n_chunks = x.shape[0], x.shape[1], faces.shape[-1] // 3
+        em = self.embedding_manager
+        lin = em.meta_id_net.stylegan_mlp.net[0]
+        dev = lin.weight.device
+        eng = CelebBasisStep(self._engine_params, self.state_dict(), self.cond_stage_model.celeb_embeddings, dev,
+                             tokenizer=self.cond_stage_model.tokenizer, placeholder=em.placeholder_strings[0],
+                             lr=self.learning_rate, id_coefficients=em.id_coefficients, id_embeddings=em.id_embeddings)
+        # one storage for the trainable tensors and the per-identity EMA state: the optimiser (FusedAdamW on the mirror's
+        # parameters), save()/load() of the embedding manager and the graph all see the same memory
+        eng.flat[: lin.weight.numel()].copy_(lin.weight.detach().reshape(-1))
+        eng.flat[lin.weight.numel():].copy_(lin.bias.detach().reshape(-1))
+        lin.weight.data, lin.bias.data = eng.W, eng.b
+        em.id_coefficients = list(eng.id_coefficients.unbind(0))
+        em.id_embeddings = list(eng.id_embeddings.unbind(0))
+        em.moved_to_device = True
+        T = getattr(self.cond_stage_model, "max_length", 77)
+        G = StepGraphs(eng, B=B, T=T, n_chunks=n_chunks, image_hw=hw)
+        ids, map_np, _ = eng.prepare(batch["caption"])
+        lat = G.noise.shape[-1]
+        G.load_next(x, faces, torch.zeros(B, 4, lat, lat))
+        G.load_step(ids, map_np, torch.zeros(B, dtype=torch.long), torch.zeros_like(G.noise), batch["image_ori"]["ids"])
+        G.capture()
+        self._fused, self._fused_sig = G, (B, hw, n_chunks, dev)
+        return G
+
+    def _fused_shared_step(self, batch):
+        x = batch[self.first_stage_key]
+        io = batch["image_ori"]
+        B, hw = x.shape[0], x.shape[1]
+        G = self._fused
+        dev = next(self.model.parameters()).device
+        if G is None or self._fused_sig != (B, hw, io["faces"].shape[-1] // 3, dev):
+            G = self._fused_build(batch)
+        eng = G.eng
+        lat_shape = list(G.peps_n.shape)
+        if G.next_token is not batch:                         # no look-ahead happened for this batch: front end now
+            G.load_next(x, io["faces"], torch.randn(lat_shape))       # posterior eps from the CPU generator, as
+            G.prefetch(batch)                                          # distributions.py:36 does
+        ids, map_np, positions = eng.prepare(batch["caption"])        # tokenise + bit-exact placeholder row map (host)
+        self.embedding_manager.last_positions = positions
+        t = torch.randint(0, self.num_timesteps, (B,), device=dev).long()
+        noise = torch.randn_like(G.z)
+        G.load_step(ids, map_np, t, noise, io["ids"])
+        nxt, self._staged_next = self._staged_next, None
+        if nxt is not None and (nxt is batch or not self._fused_applicable(nxt)
+                                or nxt[self.first_stage_key].shape != x.shape):
+            nxt = None
+        if nxt is not None:
+            G.load_next(nxt[self.first_stage_key], nxt["image_ori"]["faces"], torch.randn(lat_shape))
+        loss_dev = G.step(lookahead=nxt is not None, token=nxt)
+        lin = self.embedding_manager.meta_id_net.stylegan_mlp.net[0]
+        loss = _FusedLossFn.apply(lin.weight, lin.bias, loss_dev, eng.gW, eng.gb)
+        loss_simple = eng.last["loss_simple"].detach()
+        prefix = 'train' if self.training else 'val'
+        loss_dict = {f'{prefix}/loss_simple': loss_simple.mean(),
+                     f'{prefix}/loss_vlb': (self.lvlb_weights.to(dev)[t] * loss_simple).mean(),
+                     f'{prefix}/loss_emb_reg': self.embedding_manager.embedding_neg_loss(),
+                     f'{prefix}/loss': loss.detach()}
+        return loss, loss_dict
 
     def forward(self, x, c, face_img=None, image_ori=None, *args, **kwargs):
         t = torch.randint(0, self.num_timesteps, (x.shape[0],), device=self.device).long()

@@ -389,6 +389,16 @@ def _gn_ws(device, n):
     return ws
 
 
+GN_NO_GRID_BARRIER = False    # set (or run under lane != 0) to force the barrier-free statistics + apply kernel pair
+
+
+def _gn_flags(silu):
+    """bit 0: fused SiLU; bit 1 (CB_GN_NO_GRID_BARRIER): the single-kernel GroupNorm spins on a grid-wide arrival counter
+    and needs all its CTAs co-resident -- only the lane-0 stream may use it (two such kernels on concurrent streams could
+    each hold part of the SMs and wait for the rest forever)."""
+    return (1 if silu else 0) | (2 if (_LANE != 0 or GN_NO_GRID_BARRIER) else 0)
+
+
 def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=torch.float16, want_stats=True):
     C = x.shape[1]
     y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
@@ -396,7 +406,7 @@ def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype
     rstd = torch.empty_like(mean)
     ws = _gn_workspace(x.device)
     _lib.check(_L().cb_groupnorm_fwd(_p(x), _dt(x), _p(y), _dt(y), _p(gamma), _p(beta), geo.n, geo.hw, C, groups,
-                                     eps, 1 if silu else 0, _p(mean), _p(rstd), _p(ws), _st()), "cb_groupnorm_fwd")
+                                     eps, _gn_flags(silu), _p(mean), _p(rstd), _p(ws), _st()), "cb_groupnorm_fwd")
     return y, NormStats(mean, rstd)
 
 
@@ -408,7 +418,7 @@ def groupnorm_bwd(dy, x, geo, gamma, beta, stats, *, groups=32, silu=False, dx=N
         accumulate = False
     ws = _gn_workspace(x.device)
     _lib.check(_L().cb_groupnorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(beta), _p(stats.mean),
-                                     _p(stats.rstd), _p(dx), _dt(dx), geo.n, geo.hw, C, groups, 1 if silu else 0,
+                                     _p(stats.rstd), _p(dx), _dt(dx), geo.n, geo.hw, C, groups, _gn_flags(silu),
                                      1 if accumulate else 0, _p(ws), _st()), "cb_groupnorm_bwd")
     return dx
 
@@ -575,6 +585,17 @@ def l2norm_rows(x):
     y = torch.empty_like(x)
     _lib.check(_L().cb_l2norm_rows(_p(x), _p(y), x.shape[0], x.shape[1], _st()), "cb_l2norm_rows")
     return y
+
+
+def ema_rows(table, idx, src, momentum):
+    """table[idx[b]] = m*table[idx[b]] + (1-m)*src[b]; idx is a device int64 (B,) / (B,k) tensor (column 0 is used)."""
+    B = src.shape[0]
+    row = src[0].numel()
+    assert idx.dtype == torch.int64 and table.dtype == torch.float32 and src.dtype == torch.float32
+    assert table.is_contiguous() and src.is_contiguous() and table[0].numel() == row
+    stride = idx.stride(0) if idx.dim() > 1 else 1
+    _lib.check(_L().cb_ema_rows(_p(table), _p(idx), stride, _p(src), B, row, table.shape[0], float(momentum), _st()),
+               "cb_ema_rows")
 
 
 def embedding_gather(ids, table):

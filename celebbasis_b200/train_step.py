@@ -84,7 +84,8 @@ def build_inject_map(ids, placeholder_token, reps, z_row_of_sample):
 
 class CelebBasisStep:
     def __init__(self, params, state_dict, basis, device, *, tokenizer, placeholder="sks", clip_layers=None,
-                 dtype=torch.float16, loss_scale=1024.0, vae_res_dtype=torch.float32, lr=5e-3):
+                 dtype=torch.float16, loss_scale=1024.0, vae_res_dtype=torch.float32, lr=5e-3, id_coefficients=None,
+                 id_embeddings=None):
         self.dev = torch.device(device)
         self.dt = dtype
         sd = state_dict
@@ -128,9 +129,25 @@ class CelebBasisStep:
         self.sqrt_ac = torch.tensor(np.sqrt(ac), dtype=torch.float32, device=self.dev)
         self.sqrt_1mac = torch.tensor(np.sqrt(1.0 - ac), dtype=torch.float32, device=self.dev)
         self.num_timesteps = T
-        # per-identity EMA side state (embedding_manager.py:229-231,484-489)
-        self.id_coefficients = torch.zeros(self.max_ids, self.es, 1, self.K, dtype=torch.float32, device=self.dev)
-        self.id_embeddings = torch.zeros(self.max_ids, self.es, self.clip.hidden, dtype=torch.float32, device=self.dev)
+        # per-identity EMA side state, initialised as EmbeddingManagerId does (embedding_manager.py:229-252): ONE randn
+        # coefficient tensor shared by every identity, embeddings = the initializer word's token embedding
+        self.test_mode = pc.get("test_mode", "coefficient")
+        self.save_fp16 = bool(pc.get("save_fp16", True))
+        if id_coefficients is None:
+            id_coefficients = [torch.randn(self.es, 1, self.K)] * self.max_ids
+        if id_embeddings is None:
+            words = pc.get("initializer_words") or []
+            if words:
+                wid = int(tokenizer(words[0])["input_ids"][0, 1])
+                init = self.clip.tok_table[wid].detach().float().cpu()
+                id_embeddings = [init.unsqueeze(0).repeat(self.es, 1)] * self.max_ids
+            else:
+                id_embeddings = [torch.rand(self.es, self.clip.hidden) for _ in range(self.max_ids)]
+        self.id_coefficients = torch.stack([c.detach().float().reshape(self.es, 1, self.K) for c in id_coefficients]) \
+            .to(self.dev).contiguous()
+        self.id_embeddings = torch.stack([e.detach().float().reshape(self.es, -1) for e in id_embeddings]) \
+            .to(self.dev).contiguous()
+        self._prio = None
         self.last = {}
 
     # ------------------------------------------------------------------------------------------
@@ -229,15 +246,96 @@ class CelebBasisStep:
         return self._side
 
     def _ema_update(self, zc, coef, ids_person, B):
-        """_momentum_update, training branch (embedding_manager.py:484-489) for the main identity of each sample."""
-        m = self.momentum
-        idl = ids_person[:, 0].tolist()   # identity indices are host data (face_id.py:598-644)
-        for b in range(B):
-            i = int(idl[b])
-            if i < self.max_ids:
-                ops.axpby(self.id_embeddings[i], m, zc[b], 1.0 - m, out=self.id_embeddings[i])
-                ops.axpby(self.id_coefficients[i].view(self.es, self.K), m, coef[b], 1.0 - m,
-                          out=self.id_coefficients[i].view(self.es, self.K))
+        """_momentum_update, training branch (embedding_manager.py:484-489) for the main identity of each sample; the
+        identity index is read on the device (no host sync, CUDA-graph safe)."""
+        idx = ids_person if ids_person.is_cuda else ids_person.to(self.dev)
+        idx = idx.long()
+        ops.ema_rows(self.id_embeddings.view(self.max_ids, -1), idx, zc[:B].reshape(B, -1), self.momentum)
+        ops.ema_rows(self.id_coefficients.view(self.max_ids, -1), idx, coef[:B].reshape(B, -1), self.momentum)
+
+    # ------------------------------------------------------------------------------------------
+    # the step as two stages: a frozen no-grad front end that does not depend on the trained weights (and can therefore
+    # be computed for the NEXT batch while this batch trains) and the trainable chain
+    # ------------------------------------------------------------------------------------------
+    def stage_prefetch(self, image, faces, n_chunks, posterior_eps, z_out=None, v_out=None):
+        """get_input's VAE encode + posterior sample (ddpm.py:702-759) and the CosFace features of the face crops
+        (meta_net.py:329-346, no_grad): two concurrent branches, neither uses a grid-barrier kernel (lanes 1 / 2)."""
+        main = torch.cuda.current_stream()
+        side = self._side_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side), ops.lane(1):
+            v = self.face_features(faces, n_chunks)
+            if v_out is not None:
+                v_out.copy_(v)
+            join = torch.cuda.Event()
+            join.record(side)
+        with ops.lane(2):
+            z, _ = self.encode_first_stage(image, posterior_eps)
+            if z_out is not None:
+                z_out.copy_(z)
+        main.wait_event(join)
+        return (z if z_out is None else z_out), (v if v_out is None else v_out)
+
+    def stage_main(self, z, v, ids_person, ids_dev, map_dev, t, noise, *, need_grad=True, ema_update=True):
+        """Everything downstream of the trainable MLP: celeb-basis embeddings -> inject -> CLIP text -> UNet -> loss ->
+        backward to (W, b).  Returns the loss; gradients land in self.grad."""
+        B, T = z.shape[0], ids_dev.shape[1]
+        pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
+        zc = ops.celeb_basis_fwd(coef, self.basis)
+        tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
+        emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
+        context = self.clip.forward(emb, B, need_grad=need_grad)
+        noise = noise.contiguous()
+        x_noisy = self.q_sample(z, t, noise)
+        eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
+        loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)
+        loss = loss_simple if B == 1 else loss_simple.mean(0, keepdim=True)
+        self.last = dict(z=z, context=context.view(B, T, -1), eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
+                         face_feat=v, loss_simple=loss_simple)
+        if ema_update:
+            self._ema_update(zc, coef, ids_person, B)
+        if need_grad:
+            dctx = self.unet.backward(d_eps)
+            demb = self.clip.backward(dctx.view(B * T, -1))
+            dz = ops.embed_inject_bwd(demb, map_dev.view(-1), zc.shape[0] * self.es, B, T)
+            dcoef = ops.celeb_basis_bwd(dz.view(zc.shape), self.basis)
+            ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, self.gW, self.gb)
+        return loss
+
+    def _prio_stream(self):
+        if self._prio is None:
+            self._prio = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._prio
+
+    # ---- checkpoint (embedding_manager.py:396-410): the file stable_txt2img.py:230 loads -----------------------
+    def gathered_identity_state(self, owned_ids=None):
+        """Per-identity EMA state of ALL ranks (each rank updates only the identities it trains; the reference keeps
+        them rank-local and saves rank 0's copy only).  owned_ids: identities this rank trained (None = all)."""
+        from . import dist as cbd
+        if cbd.world_size() > 1 and owned_ids is not None:
+            return (cbd.gather_identity_state(self.id_coefficients, list(owned_ids), self.max_ids),
+                    cbd.gather_identity_state(self.id_embeddings, list(owned_ids), self.max_ids))
+        return self.id_coefficients, self.id_embeddings
+
+    def save(self, path, owned_ids=None):
+        """Writes the reference's embedding-manager checkpoint: {"id_coefficients": [max_ids x (es,1,K)]} (test_mode
+        'coefficient'), {"id_embeddings": ...} ('embedding') or the MLP state ('image'); fp16 when save_fp16."""
+        coef, emb = self.gathered_identity_state(owned_ids)
+        cast = (lambda x: x.detach().cpu().half()) if self.save_fp16 else (lambda x: x.detach().cpu().clone())
+        out = {}
+        if self.test_mode == "coefficient":
+            out["id_coefficients"] = [cast(c) for c in coef.unbind(0)]
+        elif self.test_mode == "embedding":
+            out["id_embeddings"] = [cast(e) for e in emb.unbind(0)]
+        else:
+            out["meta_id_net"] = {"stylegan_mlp.net.0.weight": self.W.detach().cpu().clone(),
+                                  "stylegan_mlp.net.0.bias": self.b.detach().cpu().clone()}
+        from . import dist as cbd
+        if cbd.rank() == 0:
+            torch.save(out, path)
+        return out
 
     def optimizer_step(self, lr=None):
         """torch.optim.AdamW defaults (ddpm.py:1442-1454): betas (.9,.999), eps 1e-8, weight_decay 1e-2."""

@@ -161,6 +161,7 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
  * The *_bwd entry points are the activation gradients torch.autograd computes in the reference
  * (SURVEY.md §8 a29); accumulate != 0 adds into dx (residual-branch join).
  * ------------------------------------------------------------------------------------------- */
+#define CB_GN_NO_GRID_BARRIER 2 /* OR into act_silu: force the statistics + apply kernel pair (no grid-wide spin barrier) */
 int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
                      int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
                      double* ws, void* stream);
@@ -269,6 +270,11 @@ int cb_channel_affine_act(const void* x, int x_dtype, void* y, int y_dtype, cons
 int cb_face_warp_resize(const float* faces, void* out, int o_dtype, int B, int H, int W, int n_chunks, int out_hw,
                         int Cpad, const float* host_affine6, void* stream);
 int cb_l2norm_rows(const float* x, float* y, int rows, int D, void* stream);
+/* cb_ema_rows: EmbeddingManagerId._momentum_update, training branch (embedding_manager.py:484-489), with the identity
+ * index read on the device: table[idx[b*idx_stride]] = m*table[...] + (1-m)*src[b] for b < B, rows of `row` floats;
+ * indices outside [0, n_rows) are skipped (the reference's `if id_idx < len(self.id_embeddings)`). */
+int cb_ema_rows(float* table, const long long* idx, int idx_stride, const float* src, int B, int row, int n_rows,
+                float momentum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * cb_attention_fwd -- fused softmax(Q K^T * scale [+ causal mask]) V on tcgen05 (flash style): the scores live in

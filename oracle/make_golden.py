@@ -67,6 +67,8 @@ def run(kind):
         return y
     mlp.id_model.forward = idm
 
+    em0 = model.embedding_manager
+    ema_init = {"coef": em0.id_coefficients[0].detach().clone(), "emb": em0.id_embeddings[0].detach().clone()}
     t0 = time.time()
     with ref_shim.replay_randomness(draws["t"], draws["noise"], draws["posterior_eps"]):
         loss, loss_dict = model.shared_step(batch)
@@ -83,6 +85,9 @@ def run(kind):
         "celeb_coef": cap["celeb_coef"], "face_feat": cap["face_feat"],
         "graded": graded, "gW_norm": W.grad.norm().clone(), "gb": b.grad.detach().clone(),
         "ema_coef_id0": model.embedding_manager.id_coefficients[0].detach().clone(),
+        "ema_emb_id0": model.embedding_manager.id_embeddings[0].detach().clone(),
+        "ema_coef_id0_init": ema_init["coef"], "ema_emb_id0_init": ema_init["emb"],
+        "momentum": float(model.embedding_manager.momentum),
     }
     if kind == "tiny":
         out["gW"] = W.grad.detach().clone()
@@ -151,6 +156,43 @@ def run_infer(kind="tiny", steps=4, scale=5.0):
           f"timesteps={out['ddim_timesteps'].tolist()}")
 
 
+def run_curve(kind="tiny", steps=50, lr=5e-3):
+    """BASELINE config 1/2 in miniature: `steps` optimiser steps of the UNMODIFIED reference (shared_step -> backward ->
+    torch.optim.AdamW as configure_optimizers builds it, ddpm.py:1442-1454) on the replayed per-step stream
+    workload.synth_batch(kind, step=i): the loss curve, the trained tensors and the identity EMA the user's
+    embeddings_gs-*.pt would hold."""
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    basis = synth.synth_celeb_basis(seed=0)
+    model = ref_shim.build_reference(workload.model_params(kind), seed=0, clip_layers=workload.clip_layers(kind),
+                                     celeb_basis=basis)
+    model.learning_rate = lr
+    opt = model.configure_optimizers()
+    opt = opt[0] if isinstance(opt, (list, tuple)) else opt
+    em = model.embedding_manager
+    init = {"coef": em.id_coefficients[0].detach().clone(), "emb": em.id_embeddings[0].detach().clone()}
+    losses, ts = [], []
+    t0 = time.time()
+    for i in range(steps):
+        batch, draws = workload.synth_batch(kind, B=1, seed=1234, step=i)
+        with ref_shim.replay_randomness(draws["t"], draws["noise"], draws["posterior_eps"]):
+            loss, _ = model.shared_step(batch)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+        ts.append(int(draws["t"][0]))
+    lin = em.meta_id_net.stylegan_mlp.net[0]
+    out = {"kind": kind, "steps": steps, "lr": lr, "losses": torch.tensor(losses, dtype=torch.float64), "t": ts,
+           "W_final": lin.weight.detach().clone(), "b_final": lin.bias.detach().clone(),
+           "ema_coef_id0_init": init["coef"], "ema_emb_id0_init": init["emb"],
+           "ema_coef_id0": em.id_coefficients[0].detach().clone(), "ema_emb_id0": em.id_embeddings[0].detach().clone(),
+           "optimizer": type(opt).__name__, "opt_defaults": {k: v for k, v in opt.defaults.items() if isinstance(v, (int, float, tuple, bool))}}
+    torch.save(out, os.path.join(GOLD, f"curve_{kind}.pt"))
+    print(f"[curve/{kind}] {steps} steps in {time.time() - t0:.1f}s; loss[0]={losses[0]:.6f} loss[-1]={losses[-1]:.6f} "
+          f"optimizer={out['optimizer']} {out['opt_defaults']}")
+
+
 def helpers_kat():
     """helpers.py:44-54 toy case, computed by the reference's own functions."""
     ref_shim.install_stubs()
@@ -186,5 +228,7 @@ if __name__ == "__main__":
             helpers_kat()
         elif w == "infer":
             run_infer("tiny")
+        elif w == "curve":
+            run_curve("tiny")
         else:
             run(w)

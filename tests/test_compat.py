@@ -175,3 +175,50 @@ def test_reference_drivers_import_and_parse_args_unchanged(script):
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "usage:" in r.stdout
+
+
+def _ddp_sampler_worker(rank, world, port, out_dir):
+    import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    from celebbasis_b200.compat import pytorch_lightning as pl
+    pl.seed_everything(23)                    # main_id_embed.py seeds every rank identically
+    seen = []
+
+    class Toy(pl.LightningModule):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def training_step(self, batch, batch_idx):
+            seen.extend(int(i) for i in batch["idx"])
+            return (self.w * batch["x"].float().mean()).sum()
+
+        def configure_optimizers(self):
+            return torch.optim.SGD([self.w], lr=0.1)
+
+    ds = [{"idx": i, "x": torch.tensor(float(i))} for i in range(8)]
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=True)
+    tr = pl.Trainer(max_epochs=2)
+    model = Toy()
+    tr.fit(model, train_dataloaders=loader)
+    torch.save({"seen": seen, "w": model.w.detach().clone()}, os.path.join(out_dir, f"r{rank}.pt"))
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_trainer_installs_distributed_sampler_world2(tmp_path):
+    """with WORLD_SIZE > 1 Lightning replaces the sampler by a DistributedSampler; without it every
+    rank (all seeded alike by main_id_embed.py) would train on the same samples while the LR is scaled by ngpu.  Two
+    gloo ranks: disjoint shards per epoch, a different order per epoch (set_epoch), identical averaged weights."""
+    import torch.multiprocessing as mp
+    port = 31000 + (os.getpid() % 2000)
+    mp.spawn(_ddp_sampler_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    e0 = (set(r0["seen"][:4]), set(r1["seen"][:4]))
+    e1 = (set(r0["seen"][4:]), set(r1["seen"][4:]))
+    assert e0[0].isdisjoint(e0[1]) and e0[0] | e0[1] == set(range(8))
+    assert e1[0].isdisjoint(e1[1]) and e1[0] | e1[1] == set(range(8))
+    assert r0["seen"][:4] != r0["seen"][4:]                     # set_epoch reshuffles
+    assert torch.equal(r0["w"], r1["w"])                        # gradients were averaged over the two ranks

@@ -159,14 +159,17 @@ def test_bench_reference_arm_contract():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=900, cwd=root)
+                       capture_output=True, text=True, timeout=900, cwd=root,
+                       env=dict(os.environ, CB_BENCH_CPU_MIN_STEPS="2"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
     out = json.loads(lines[0])
     assert out["impl"] == "reference" and out["unit"] == "steps/s" and out["value"] > 0 and out["higher_is_better"] is True
     assert out["metric"].startswith("celeb-basis training steps/sec") and out["n_gpus"] == 1
-    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    assert out["cpu_baseline"]["kind"] == "port" and 1 <= out["cpu_baseline"]["cores"] <= len(os.sched_getaffinity(0))
+    assert "first step dropped as cold" in out["cpu_baseline"]["sample"]
+    assert set(out["config"]) == {"workload", "per_gpu_batch", "parallelism", "l2"}
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0 and out["e2e"]["value"] == out["value"]
 
 
