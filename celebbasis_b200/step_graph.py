@@ -120,8 +120,10 @@ class StepGraphs:
         self._body_pipe()
         torch.cuda.synchronize()
         pool = None
+        self.gemm_record = []       # (desc bytes, flops) of one whole step (pre + main): pointers into the graphs' pool
         for name, body in (("pre", self._body_pre), ("main", self._body_main), ("pipe", self._body_pipe)):
             n0 = lib.launch_count()
+            ops.GEMM_RECORD = [] if name != "pipe" else None
             if self.use_graphs:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):      # the graphs never run concurrently: one shared memory pool
@@ -131,6 +133,9 @@ class StepGraphs:
             else:
                 body()
             self.launches[name] = lib.launch_count() - n0
+            if ops.GEMM_RECORD is not None:
+                self.gemm_record += ops.GEMM_RECORD
+                ops.GEMM_RECORD = None
             if name != "pre":
                 self.outs[name] = (self.loss, self._last)
         torch.cuda.synchronize()
