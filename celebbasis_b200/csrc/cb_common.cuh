@@ -40,6 +40,12 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int device_sm_count();
+// one-warp-per-row LayerNorm (cb_norm.cu): fallback of the vectorised kernels in cb_layernorm.cu
+int layernorm_fwd_legacy(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, int M,
+                         int C, float eps, float* mean_out, float* rstd_out, void* stream);
+int layernorm_bwd_legacy(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma, const float* mean,
+                         const float* rstd, void* dx, int dx_dtype, void* dx_lp, int M, int C, int accumulate,
+                         void* stream);
 void count_launches(int n);  // bookkeeping for cb_launch_count()
 bool pdl_enabled();          // programmatic dependent launch on (default) unless CB_PDL=0
 

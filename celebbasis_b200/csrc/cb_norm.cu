@@ -949,8 +949,8 @@ CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, TG>), grid, nthr, 0, st, (const TG*)dy, (
     return 0;
 }
 
-extern "C" int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
-                                int M, int C, float eps, float* mean_out, float* rstd_out, void* stream) {
+int cb::layernorm_fwd_legacy(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
+                             int M, int C, float eps, float* mean_out, float* rstd_out, void* stream) {
     CB_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && C <= 64 * kLnMaxPairsPerLane, CB_ERR_ARG, "layernorm: bad shape M=%d C=%d", M, C);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(ceil_div(M, 4));
@@ -961,9 +961,9 @@ CB_LAUNCH((ln_fwd_kernel<TX, TY>), grid, 128, 0, st, (const TX*)x, (TY*)y, gamma
     return 0;
 }
 
-extern "C" int cb_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
-                                const float* mean, const float* rstd, void* dx, int dx_dtype, void* dx_lp, int M, int C,
-                                int accumulate, void* stream) {
+int cb::layernorm_bwd_legacy(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                             const float* mean, const float* rstd, void* dx, int dx_dtype, void* dx_lp, int M, int C,
+                             int accumulate, void* stream) {
     CB_REQUIRE(M > 0 && C > 0 && C % 2 == 0 && C <= 64 * kLnMaxPairsPerLane, CB_ERR_ARG, "layernorm_bwd: bad shape M=%d C=%d", M, C);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid(ceil_div(M, 4));

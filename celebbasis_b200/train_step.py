@@ -282,14 +282,26 @@ class CelebBasisStep:
         """Everything downstream of the trainable MLP: celeb-basis embeddings -> inject -> CLIP text -> UNet -> loss ->
         backward to (W, b).  Returns the loss; gradients land in self.grad."""
         B, T = z.shape[0], ids_dev.shape[1]
-        pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
-        zc = ops.celeb_basis_fwd(coef, self.basis)
-        tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
-        emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
-        context = self.clip.forward(emb, B, need_grad=need_grad)
+        # the text branch (MLP -> basis -> inject -> 12 CLIP layers, ~110 small launches) runs beside the UNet's prefix
+        # (timestep MLP, stem, first ResBlock, first self-attention): the UNet waits for the context at its first
+        # cross-attention
+        main = torch.cuda.current_stream()
+        aux = self._aux_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        aux.wait_event(fork)
+        with torch.cuda.stream(aux), ops.lane(3):
+            pre, coef, nrm = ops.celeb_mlp_fwd(v, self.W, self.b, self.es)
+            zc = ops.celeb_basis_fwd(coef, self.basis)
+            tok = ops.embedding_gather(ids_dev.view(-1), self.clip.tok_table)
+            emb = ops.embed_inject_fwd(tok, zc.view(-1, zc.shape[-1]), map_dev.view(-1), self.clip.pos_table, B, T)
+            context = self.clip.forward(emb, B, need_grad=need_grad)
+            ctx_ready = torch.cuda.Event()
+            ctx_ready.record(aux)
         noise = noise.contiguous()
         x_noisy = self.q_sample(z, t, noise)
-        eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad)
+        eps = self.unet.forward(x_noisy, t, context.view(B, T, -1), need_grad=need_grad, context_ready=ctx_ready)
+        main.wait_event(ctx_ready)      # (already implied by the UNet's first cross-attention; explicit for the EMA / backward)
         loss_simple, d_eps = ops.mse_fwd_bwd(eps, noise, 1.0, want_grad=need_grad)
         loss = loss_simple if B == 1 else loss_simple.mean(0, keepdim=True)
         self.last = dict(z=z, context=context.view(B, T, -1), eps=eps, x_noisy=x_noisy, coef=coef, celeb_z=zc,
@@ -303,6 +315,11 @@ class CelebBasisStep:
             dcoef = ops.celeb_basis_bwd(dz.view(zc.shape), self.basis)
             ops.celeb_mlp_bwd(dcoef, coef, nrm, pre, v, self.gW, self.gb)
         return loss
+
+    def _aux_stream(self):
+        if getattr(self, "_aux", None) is None:
+            self._aux = torch.cuda.Stream(device=self.dev, priority=-1)
+        return self._aux
 
     def _prio_stream(self):
         if self._prio is None:

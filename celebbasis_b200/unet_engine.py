@@ -62,20 +62,28 @@ class _Attn:
         return P
 
     @staticmethod
-    def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv):
+    def bwd(dO, q, k, v, P, *, images, heads, dh, nq, nk, scale, dq, dk, dv, offload=None):
+        """offload: optional _SideQueue -- the dK / dV GEMMs of a cross-attention block only feed the context gradient
+        that is assembled at the very end of the backward pass, so they leave the critical path."""
         if isinstance(P, tuple) and P[0] == "p+lse":
             _, Pm, lse, out, causal = P
             ldp = Pm.shape[1]
             dS = torch.empty_like(Pm)
             ops.attention_bwd_dq(q, k, v, out, dO, lse, dq, dS, images=images, heads=heads, dh=dh, nq=nq, nk=nk,
                                  scale=scale, causal=causal)
-            # dV = P^T dO ; dK = dS^T Q (dS already carries the softmax scale)
-            ops.bmm(Pm, dO, dv, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=dO.stride(0),
-                    ldd=dv.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * dO.stride(0),
-                    d_is=nk * dv.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
-            ops.bmm(dS, q, dk, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=q.stride(0),
-                    ldd=dk.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * q.stride(0),
-                    d_is=nk * dk.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+
+            def dkdv():
+                # dV = P^T dO ; dK = dS^T Q (dS already carries the softmax scale)
+                ops.bmm(Pm, dO, dv, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=dO.stride(0),
+                        ldd=dv.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * dO.stride(0),
+                        d_is=nk * dv.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+                ops.bmm(dS, q, dk, M=nk, N=dh, K=nq, heads=heads, images=images, lda=ldp, ldb=q.stride(0),
+                        ldd=dk.stride(0), a_hs=nq * ldp, b_hs=dh, d_hs=dh, a_is=heads * nq * ldp, b_is=nq * q.stride(0),
+                        d_is=nk * dk.stride(0), a_major=CB_MAJOR_MN, b_major=CB_MAJOR_MN)
+            if offload is not None:
+                offload.submit(dkdv, keep=(Pm, dO, dS, q, dv, dk))
+            else:
+                dkdv()
             return
         if isinstance(P, tuple):
             _, lse, out, causal = P
@@ -107,7 +115,39 @@ class _Attn:
                 d_is=nq * dq.stride(0), b_major=CB_MAJOR_MN, alpha=scale)
 
 
+class _SideQueue:
+    """Runs small launches that are off the critical path on a second stream (own workspace lane), ordered after the point
+    of submission; join() makes the current stream wait for all of them.  Operand tensors are kept alive until join()
+    (their memory must not be recycled by the submitting stream while the side stream still reads it)."""
+
+    def __init__(self, device, lane):
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.lane = lane
+        self.keep = []
+        self.pending = False
+
+    def submit(self, fn, keep=()):
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream), ops.lane(self.lane):
+            fn()
+        self.keep.append(keep)
+        self.pending = True
+
+    def join(self):
+        if self.pending:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self.pending = False
+        self.keep.clear()
+
+
 class UNetEngine:
+    SIDE_DKDV = True     # cross-attention dK / dV GEMMs on a side stream (they only feed d(context), assembled last)
+
     def __init__(self, cfg, state_dict, device, dtype=torch.float16, loss_scale=1024.0):
         self.cfg = dict(cfg)
         self.dev = torch.device(device)
@@ -122,6 +162,7 @@ class UNetEngine:
         self.out_pad = 16
         self._build(state_dict)
         self.tape = None
+        self._sideq = None
 
     # ------------------------------------------------------------------------------------------
     # weight preparation
@@ -273,7 +314,7 @@ class UNetEngine:
 
     def _xf_fwd(self, w, x, geo, kv_all, tape):
         c, dh, H = w["c"], w["dh"], self.heads
-        B, nq, nk = geo.n, geo.hw, kv_all.shape[0] // geo.n
+        B, nq = geo.n, geo.hw
         scale = dh ** -0.5
         n16, stn = ops.groupnorm(x, geo, w["gn"], w["bn"], eps=1e-6, silu=False, out_dtype=self.dt)
         h0 = ops.linear(n16, w["wpi"], w["bpi"], out_dtype=torch.float32)
@@ -287,6 +328,8 @@ class UNetEngine:
         # cross attention
         l2, s2 = ops.layernorm(h1, w["ln2g"], w["ln2b"], out_dtype=self.dt)
         q2 = ops.linear(l2, w["wq2"])
+        kv_all = kv_all()                                        # first use waits for the text encoder (see forward)
+        nk = kv_all.shape[0] // geo.n
         kv2 = kv_all[:, w["kv_off"]:w["kv_off"] + 2 * c]       # K | V of this block (projected once for all blocks)
         o2 = torch.empty(geo.rows, c, dtype=self.dt, device=self.dev)
         P2 = _Attn.fwd(q2, kv2[:, :c], kv2[:, c:], images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale, out=o2)
@@ -322,7 +365,7 @@ class UNetEngine:
         dq2 = torch.empty_like(q2) if to_input else None
         dkv2 = dkv_all[:, w["kv_off"]:w["kv_off"] + 2 * c]     # gradient slice of the batched context projection
         _Attn.bwd(dO, q2, kv2[:, :c], kv2[:, c:], P2, images=B, heads=H, dh=dh, nq=nq, nk=nk, scale=scale,
-                  dq=dq2, dk=dkv2[:, :c], dv=dkv2[:, c:])
+                  dq=dq2, dk=dkv2[:, :c], dv=dkv2[:, c:], offload=self._sideq_get())
         if not to_input:
             return None
         dl2 = ops.linear_dgrad(dq2, w["wq2"])
@@ -338,6 +381,13 @@ class UNetEngine:
         dn = ops.linear_dgrad(dr16, w["wpi"])
         ops.groupnorm_bwd(dn, x, geo, w["gn"], w["bn"], stn, silu=False, dx=dx, accumulate=True)
         return dx
+
+    def _sideq_get(self):
+        if not self.SIDE_DKDV:
+            return None
+        if self._sideq is None:
+            self._sideq = _SideQueue(self.dev, lane=4)
+        return self._sideq
 
     def _down_fwd(self, w, x, geo, tape):
         out, ogeo = ops.conv2d(ops.cast(x, self.dt), geo, w["w"], w["c"], bias=w["b"], stride=2,
@@ -377,8 +427,11 @@ class UNetEngine:
                 h, geo = self._up_fwd(w, h, geo, tape)
         return h, geo
 
-    def forward(self, x, t, context, need_grad=True):
-        """x: (B,in_ch,H,W) fp32 NCHW; t: (B,) int64; context: (B,T,ctx_dim) fp32.  Returns eps (B,out_ch,H,W) fp32."""
+    def forward(self, x, t, context, need_grad=True, context_ready=None):
+        """x: (B,in_ch,H,W) fp32 NCHW; t: (B,) int64; context: (B,T,ctx_dim) fp32.  Returns eps (B,out_ch,H,W) fp32.
+        context_ready: optional CUDA event after which `context` holds the text encoder's output (it may still be being
+        computed on another stream: nothing before the first cross-attention -- timestep MLP, stem, first ResBlock, the
+        first block's self-attention -- needs it)."""
         assert x.dtype == torch.float32 and context.dtype == torch.float32
         B = x.shape[0]
         tape = [] if need_grad else None
@@ -388,9 +441,16 @@ class UNetEngine:
         # SiLU(emb) is what every ResBlock consumes (openaimodel.py:222-226): fuse it into the 2nd linear
         e2 = ops.linear(e1, self.te2_w, self.te2_b, act=CB_ACT_SILU)
         emb_all = ops.linear(e2, self.emb_w, self.emb_b, out_dtype=torch.float32)
-        ctx16 = ops.cast(context.reshape(-1, self.ctx_dim), self.dt)
-        # the context is the same for all 16 transformer blocks: project it to every block's K and V in one GEMM
-        kv_all = ops.linear(ctx16, self.wkv_all) if self.wkv_all is not None else None
+        kv_state = {}
+
+        def kv_all():
+            # the context is the same for all 16 transformer blocks: project it to every block's K and V in one GEMM
+            if "kv" not in kv_state:
+                if context_ready is not None:
+                    torch.cuda.current_stream().wait_event(context_ready)
+                ctx16 = ops.cast(context.reshape(-1, self.ctx_dim), self.dt)
+                kv_state["kv"] = ops.linear(ctx16, self.wkv_all)
+            return kv_state["kv"]
         x16, geo = ops.nchw_to_nhwc(x.contiguous(), self.in_pad, self.dt)
         h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32)
         hs = [(h, geo)]
@@ -461,6 +521,8 @@ class UNetEngine:
                 # this activation also fed a skip connection: add that branch's gradient
                 dsk = dskips.pop()
                 ops.axpby(dh, 1.0, dsk, 1.0, out=dh)
+        if self._sideq is not None:
+            self._sideq.join()
         # d(context) = [dK | dV of every block] . [W_k ; W_v of every block]: one GEMM with K = sum 2C
         dctx = ops.linear_dgrad(dkv_all, self.wkv_all, out_dtype=torch.float32)
         out = ops.axpby(dctx, 1.0 / S)

@@ -149,7 +149,8 @@ def test_groupnorm_fwd_bwd(dev, n, hw, c, silu, eps, xdt):
     assert rel(acc, dx + 1) < 1e-5
 
 
-@pytest.mark.parametrize("m,c", [(4096, 320), (77, 768), (64, 1280), (3, 640)])
+@pytest.mark.parametrize("m,c", [(4096, 320), (77, 768), (64, 1280), (3, 640), (1024, 640), (256, 1280), (130, 2048),
+                                 (5, 66), (1025, 64), (9, 4100)])
 def test_layernorm_fwd_bwd(dev, m, c):
     from celebbasis_b200 import ops
     x = rnd(m, c, dtype=torch.float32, scale=3.0)
