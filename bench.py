@@ -447,6 +447,178 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config 4: txt2img
+T2I_METRIC = "DDIM txt2img images/sec (scripts/stable_txt2img.py semantics: 50 steps, eta 0, CFG 10, 512x512, 8 images/GPU)"
+T2I_WORKLOAD = ("configs[3]: DDIM txt2img, 50 steps, 512x512, n_samples 8 per GPU (UNet batch 16 under classifier-free "
+                "guidance), fp16 operands, + VAE decode; replicas across GPUs (no collective)")
+
+
+def t2i_config(world):
+    return {"workload": T2I_WORKLOAD, "per_gpu_batch": 8, "parallelism": f"replicas x{world}",
+            "l2": "inputs larger than L2: 1.7 GB of UNet weights + ~6 GB of batch-16 activations per UNet call (L2 = 126 MB)"}
+
+
+def run_txt2img(args):
+    """BASELINE config 4 through the reference-facing API: get_learned_conditioning -> DDIMSampler.sample ->
+    decode_first_stage (scripts/stable_txt2img.py:320-347).  `value`: conditioning + 50 DDIM steps + decode with the
+    prompts' conditioning resident; `e2e`: the whole script body per batch, host prompts in, images copied to the host."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from celebbasis_b200 import dist as cbd
+    from celebbasis_b200 import lib, ops, synth, workload
+    from ldm.models.diffusion.ddim import DDIMSampler
+    from ldm.models.diffusion.ddpm import LatentDiffusion
+    world, rank, local = cbd.init()
+    json_out, sys.stdout = sys.stdout, sys.stderr
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    assert lib.load().cb_device_ok() == 1 and world == args.gpus
+    params = workload.model_params("full")
+    params["cond_stage_config"]["params"].update(device="cuda")
+    model = LatentDiffusion(**params)
+    model.load_state_dict(synth.synth_state_dict(model, seed=0), strict=False)
+    model = model.to(dev).eval()
+    model.cond_stage_model.celeb_embeddings = synth.synth_celeb_basis(seed=0).to(dev)
+    g = torch.Generator().manual_seed(3 + rank)
+    model.embedding_manager.id_coefficients = [F.normalize(torch.randn(2, 1, 512, generator=g), dim=-1) for _ in range(10)]
+    B, steps, scale = 8, 50, 10.0
+    prompts = ["a photo of sks person"] * B
+    image_ori = {"faces": None, "ids": [[i % 10, i % 10] for i in range(B)], "num_ids": torch.ones(B, dtype=torch.long)}
+    sampler = DDIMSampler(model)
+    host_img = torch.empty(B, 3, 512, 512, dtype=torch.float32).pin_memory()
+
+    def conditioning():
+        with torch.no_grad():
+            return model.get_learned_conditioning([""] * B), model.get_learned_conditioning(prompts, image_ori=image_ori)
+
+    def sample(uc, c, n_steps):
+        with torch.no_grad():
+            x_T = torch.randn(B, 4, 64, 64, device=dev)
+            z, _ = sampler.sample(S=n_steps, conditioning=c, batch_size=B, shape=[4, 64, 64], verbose=False,
+                                  unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T)
+            return model.decode_first_stage(z)
+
+    ops.GEMM_RECORD = []                      # the UNet's batch-16 GEMMs, recorded while its inference graph is captured
+    uc, c = conditioning()
+    sample(uc, c, 2)                          # builds engines, autotunes, captures the UNet graph
+    gemm_record, ops.GEMM_RECORD = [r for r in ops.GEMM_RECORD], None
+    torch.cuda.synchronize()
+
+    def timed(fn, n):
+        cbd.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        cbd.barrier()
+        return float(ms.item())
+
+    n_batches = max(1, args.steps // 10)      # a "step" of this workload is one batch of 8 images (50 DDIM steps)
+    n0 = lib.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_batch = timed(lambda: sample(uc, c, steps), n_batches) / n_batches
+    launches = (lib.launch_count() - n0) // n_batches
+
+    def e2e_batch():
+        u, cc = conditioning()
+        img = sample(u, cc, steps)
+        host_img.copy_(torch.clamp((img + 1.0) / 2.0, 0.0, 1.0), non_blocking=True)      # stable_txt2img.py:348-349
+        torch.cuda.current_stream().synchronize()
+    ms_e2e = timed(e2e_batch, n_batches) / n_batches
+    clk = clocks.stop() if rank == 0 else None
+    roof = None
+    if rank == 0 and gemm_record:
+        import ctypes
+        from celebbasis_b200.lib import GemmDesc
+        L = lib.load()
+        descs = [GemmDesc.from_buffer_copy(b) for b, _ in gemm_record]
+        flops = sum(f for _, f in gemm_record)
+        gg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gg):
+            s_ = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for d in descs:
+                L.cb_gemm(ctypes.byref(d), s_)
+        for _ in range(2):
+            gg.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gg.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms = e0.elapsed_time(e1) / 5
+        peaks, src = _peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "cb_gemm_kernel launches of ONE UNet forward at batch 16 (one DDIM step)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": src + " bf16_tflops_sustained", "launches": len(descs), "gemm_ms_per_unet_call": gemm_ms,
+                "algorithmic_gflop_per_unet_call": flops / 1e9,
+                "whole_job_tflops_per_gpu": 82.9 * B / (ms_batch * 1e-3),
+                "whole_job_frac": 82.9 * B / (ms_batch * 1e-3) / peak}
+    if rank == 0:
+        out = {"metric": T2I_METRIC, "value": world * B * 1000.0 / ms_batch, "unit": "images/s", "n_gpus": world,
+               "steps": n_batches, "warmup": 1, "ms_per_step": ms_batch, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (reference: fp16 autocast)", "data": "synthetic",
+               "config": t2i_config(world),
+               "e2e": {"value": world * B * 1000.0 / ms_e2e, "unit": "images/s", "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": 2 * B * 77 * 8, "d2h_bytes_per_step": B * 3 * 512 * 512 * 4,
+                       "api": "ldm LatentDiffusion.get_learned_conditioning + DDIMSampler.sample + decode_first_stage"},
+               "gpu_launches": int(launches * n_batches), "gpu_launches_per_step": int(launches),
+               "notes": {"v100_published_img_s": 0.243, "algorithmic_tflop_per_image": 82.9},
+               "clocks": clk, "roofline": roof, "cpu_baseline": None}
+        print(json.dumps(out), file=json_out, flush=True)
+    sys.stdout = json_out
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_txt2img_reference(args):
+    """The reference's CPU path for config 4 (oracle port): a bounded sample -- 2 CFG DDIM steps for ONE image (UNet batch
+    2) + one VAE decode -- extrapolated to 50 steps: images/s = 1 / (50 * t_step + t_decode)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from celebbasis_b200 import synth, workload
+    from oracle import torch_ref
+    info = pick_cpu_threads()
+    params = workload.model_params("full")
+    om = torch_ref.OracleModel(params, clip_layers=12)
+    om.load_state_dict(synth.synth_state_dict(om, seed=0))
+    om.eval()
+    fs = params["first_stage_config"]["params"]
+    dec = torch_ref.AutoencoderKLDecode(fs["ddconfig"], fs["embed_dim"]).eval()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(1, 77, 768, generator=g)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        x1 = torch_ref.ddim_sample(om.model.diffusion_model, om.sched, ctx, ctx * 0.5, x, 2, 10.0)
+        t_step = (time.perf_counter() - t0) / 2
+        t0 = time.perf_counter()
+        dec(x1 / 0.18215)
+        t_dec = time.perf_counter() - t0
+    val = 1.0 / (50 * t_step + t_dec)
+    sample = (f"2 CFG DDIM steps (UNet batch 2) + 1 VAE decode for one 512x512 image on {info['threads']} threads, fp32, "
+              f"extrapolated to 50 steps: t_step {t_step:.2f} s, t_decode {t_dec:.2f} s")
+    print(json.dumps({"impl": "reference", "metric": T2I_METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 8e3 / val, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": t2i_config(args.gpus),
+                      "cpu_baseline": {"value": val, "unit": "images/s", "cores": info["threads"], "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -454,8 +626,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "txt2img"],
+                    help="train = BASELINE.json metric (configs[1]); txt2img = configs[3] (images/s)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "txt2img":
+        (run_txt2img_reference if args.impl == "reference" else run_txt2img)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
