@@ -200,3 +200,142 @@ class EmbeddingManagerId(nn.Module):
 
     def embedding_neg_loss(self):
         return self.id_neg_loss
+
+
+# =====================================================================================================================
+# vanilla Textual-Inversion manager (embedding_manager.py:38-184; configs/stable-diffusion/v1-finetune.yaml:23-30)
+# =====================================================================================================================
+DEFAULT_PLACEHOLDER_TOKEN = ["*"]
+PROGRESSIVE_SCALE = 2000
+
+
+def build_ti_map(tokens, placeholders, max_vectors_per_token, n_active):
+    """Host mirror of EmbeddingManager.forward's index arithmetic (embedding_manager.py:108-151) as a gather map.
+
+    tokens: (B, n) int64 host array; placeholders: [(token id, z_row_base, rows of that placeholder's parameter)] in the
+    dict's insertion order; max_vectors_per_token / n_active as in the reference (n_active = max_step_tokens).
+    Returns (map (B, n) int32: >= 0 original row of the same prompt, < 0: z row -(m+1)), new_tokens).  One vector per
+    token: every occurrence is replaced in place.  Several vectors: occurrences are expanded right-to-left, later tokens
+    shift right and the row is truncated to n -- and the token row is rewritten with the repeated placeholder id, which a
+    later placeholder's search sees, exactly like the reference's in-place update."""
+    tok = np.array(tokens, dtype=np.int64, copy=True)
+    B, n = tok.shape
+    src = np.tile(np.arange(n, dtype=np.int64), (B, 1))
+    for ptoken, base, rows in placeholders:
+        if max_vectors_per_token == 1:
+            hit = tok == int(ptoken)
+            src[hit] = -(int(base) + 1)
+            continue
+        nv = min(int(rows), int(n_active))
+        r_idx, c_idx = np.where(tok == int(ptoken))
+        if r_idx.size == 0:
+            continue
+        order = np.argsort(-c_idx, kind="stable")
+        for k in order:
+            row, col = int(r_idx[k]), int(c_idx[k])
+            tok[row] = np.concatenate([tok[row][:col], np.full(nv, int(ptoken), dtype=np.int64), tok[row][col + 1:]])[:n]
+            zrows = -(int(base) + np.arange(nv, dtype=np.int64) + 1)
+            src[row] = np.concatenate([src[row][:col], zrows, src[row][col + 1:]])[:n]
+    return src.astype(np.int32), tok
+
+
+class EmbeddingManager(nn.Module):
+    """Textual Inversion: one learnable (num_vectors_per_token, 768) embedding per placeholder string, written over /
+    inserted at the placeholder's position(s) of the token embeddings.  Same constructor keywords, attributes
+    (`string_to_token_dict`, `string_to_param_dict`, `initial_embeddings`), `forward` contract and `save/load` file format
+    as the reference; the row writes are the same gather kernel EmbeddingManagerId uses (cb_embed_inject_fwd/bwd)."""
+
+    def __init__(self, embedder, placeholder_strings=None, initializer_words=None, per_image_tokens=False,
+                 num_vectors_per_token=1, progressive_words=False, **kwargs):
+        super().__init__()
+        self.string_to_token_dict = {}
+        self.string_to_param_dict = nn.ParameterDict()
+        self.initial_embeddings = nn.ParameterDict()          # these are not optimised
+        self.progressive_words = progressive_words
+        self.progressive_counter = 0
+        self.max_vectors_per_token = num_vectors_per_token
+        assert hasattr(embedder, 'tokenizer'), "the SD-v1 path uses the CLIP text encoder (the BERT branch is LDM-only)"
+        self.is_clip = True
+        assert not per_image_tokens, "per_image_tokens is false in v1-finetune.yaml (ldm/data/personalized.py list)"
+        placeholder_strings = list(placeholder_strings or DEFAULT_PLACEHOLDER_TOKEN)
+        table = embedder.transformer.text_model.embeddings.token_embedding.weight
+        token_dim = table.shape[1]
+        for idx, placeholder_string in enumerate(placeholder_strings):
+            token = get_clip_token_for_string(embedder.tokenizer, placeholder_string)
+            if initializer_words and idx < len(initializer_words):
+                init_tok = get_clip_token_for_string(embedder.tokenizer, initializer_words[idx])
+                with torch.no_grad():
+                    init = table[int(init_tok)].detach().float().cpu().clone()
+                token_params = torch.nn.Parameter(init.unsqueeze(0).repeat(num_vectors_per_token, 1), requires_grad=True)
+                self.initial_embeddings[placeholder_string] = torch.nn.Parameter(
+                    init.unsqueeze(0).repeat(num_vectors_per_token, 1), requires_grad=False)
+            else:
+                token_params = torch.nn.Parameter(torch.rand(size=(num_vectors_per_token, token_dim), requires_grad=True))
+            self.string_to_token_dict[placeholder_string] = token
+            self.string_to_param_dict[placeholder_string] = token_params
+        self._zero_pos = None
+        self.last_map = None
+
+    def forward(self, tokenized_text, embedded_text, face_image=None, img_ori=None, celeb_embeddings=None):
+        b, n = tokenized_text.shape
+        device = embedded_text.device
+        placeholders, z_list, base = [], [], 0
+        steps = []
+        for key, ptoken in self.string_to_token_dict.items():
+            p = self.string_to_param_dict[key]
+            if self.max_vectors_per_token > 1 and self.progressive_words:
+                self.progressive_counter += 1
+                steps.append(1 + self.progressive_counter // PROGRESSIVE_SCALE)
+            else:
+                steps.append(self.max_vectors_per_token)
+            placeholders.append((int(ptoken), base, p.shape[0]))
+            z_list.append(p.to(device))
+            base += p.shape[0]
+        tok_host = tokenized_text.detach().cpu().numpy()
+        # per-placeholder active length: apply them one at a time so each sees its own max_step_tokens
+        cur_tok = tok_host
+        maps = np.tile(np.arange(n, dtype=np.int32), (b, 1))
+        for (ph, st) in zip(placeholders, steps):
+            m, cur_tok = build_ti_map(cur_tok, [ph], self.max_vectors_per_token, st)
+            # compose: rows of `m` index the CURRENT row order
+            sel = m >= 0
+            new = np.where(sel, np.take_along_axis(maps, np.clip(m, 0, n - 1), axis=1), m)
+            maps = new.astype(np.int32)
+        if self.max_vectors_per_token > 1:
+            tokenized_text.copy_(torch.from_numpy(cur_tok).to(tokenized_text.device))     # in-place, like the reference
+        self.last_map = maps
+        map_dev = torch.from_numpy(maps).to(device)
+        z_rows = torch.cat(z_list, 0).float()
+        if self._zero_pos is None or self._zero_pos.device != device or self._zero_pos.shape[0] < n:
+            self._zero_pos = torch.zeros(n, embedded_text.shape[-1], dtype=torch.float32, device=device)
+        return _InjectFn.apply(embedded_text, z_rows, map_dev, self._zero_pos)
+
+    def save(self, ckpt_path):
+        torch.save({"string_to_token": self.string_to_token_dict, "string_to_param": self.string_to_param_dict}, ckpt_path)
+
+    def load(self, ckpt_path):
+        ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+        self.string_to_token_dict = ckpt["string_to_token"]
+        self.string_to_param_dict = ckpt["string_to_param"]
+
+    def get_embedding_norms_squared(self):
+        all_params = torch.cat(list(self.string_to_param_dict.values()), axis=0)
+        return (all_params * all_params).sum(axis=-1)
+
+    def embedding_parameters(self):
+        return self.string_to_param_dict.parameters()
+
+    def trainable_parameters(self):
+        return []
+
+    def embedding_to_coarse_loss(self):
+        loss = 0.
+        num_embeddings = len(self.initial_embeddings)
+        for key in self.initial_embeddings:
+            optimized = self.string_to_param_dict[key]
+            coarse = self.initial_embeddings[key].clone().to(optimized.device)
+            loss = loss + (optimized - coarse) @ (optimized - coarse).T / num_embeddings
+        return loss
+
+    def embedding_neg_loss(self):
+        return 0.

@@ -198,37 +198,42 @@ class FrozenCLIPEmbedder(AbstractEncoder):
 
     @torch.no_grad()
     def _get_celeb_embeddings(self, n_components: int = 0):
-        """modules.py:472-624: per-token-column PCA basis (mean + n_components right-singular vectors) of the CLIP
-        token embeddings of ~650 celebrity names.  Init-time, host-side linear algebra (torch.svd on CPU, like the
-        reference); the hot path only consumes the resulting (es, 1+n_components, 768) tensor."""
+        """modules.py:472-624: the celeb basis -- per token column (use_flatten=False, aigc_id.yaml) or over all name
+        tokens (use_flatten=True, the constructor default) the mean + n_components right-singular vectors of the CLIP
+        token embeddings of the ~650 celebrity names, optionally after the sample reduction of :575-584.  Init-time,
+        host-side linear algebra (torch.svd on CPU, like the reference); the hot path only consumes the resulting
+        (num_embeds_per_token, 1+n_components, 768) tensor.
+
+        Faithful to two quirks of the reference: names are sorted after de-duplication (:479-487), and the `tok in
+        set_of_tensors` tests (:521-533) compare 0-dim tensors by identity and therefore never remove a repeated token."""
         with open(self.celeb_txt, "r") as f:
             names = f.read().splitlines()
-        names = sorted(set(names)) if self.rm_repeats else names
+        names = sorted(set(names)) if self.rm_repeats else sorted(names)
         table = self.transformer.text_model.embeddings.token_embedding.weight.detach().float().cpu()
         ids = [self.tokenizer(n, truncation=True, max_length=self.max_length, return_length=True,
                               return_overflowing_tokens=False, padding="max_length",
                               return_tensors="pt")["input_ids"][0] for n in names]
-        all_tokens = torch.stack(ids, 0)
-        cols = []
-        for j in range(all_tokens.shape[1]):
-            seen, col = set(), []
-            for i in range(all_tokens.shape[0]):
-                tok = int(all_tokens[i, j])
-                if tok >= 49406:
-                    continue
-                # NOTE: the reference tests `tok in set_of_tensors`, which compares by identity and therefore never
-                # de-duplicates (modules.py:517-531); keep every occurrence to stay faithful.
-                col.append(table[tok].unsqueeze(0))
-                seen.add(tok)
-            if col:
-                cols.append(torch.cat(col, 0))
+        all_tokens = torch.stack(ids, 0)                                  # (M, 77)
+        keep = all_tokens < 49406
+        if not self.use_flatten:
+            cols = [table[all_tokens[:, j][keep[:, j]]] for j in range(all_tokens.shape[1])]
+            cols = [c for c in cols if c.shape[0] > 0]
+        else:
+            cols = [table[all_tokens[keep]]]                              # row-major over (name, position), :535-544
+        self.celeb_cols_len = [int(c.shape[0]) for c in cols]
         out = []
         for j, x in enumerate(cols[: self.num_embeds_per_token]):
-            if self.use_svd:
+            if self.use_sample_reduce:                                    # :575-584
+                e = x.t()                                                 # (768, m)
+                u, s_, v = torch.svd(e - e.mean(dim=0, keepdims=True), some=False)
+                x = torch.matmul(e, v[:, : self.n_samples]).t()           # (r, 768)
+            if self.use_svd:                                              # :598-607 ("3dmm/pca-based svd")
                 c_mean = x.mean(dim=0, keepdims=True)
-                u, s, v = torch.svd(x - c_mean, some=False)
+                u, s_, v = torch.svd(x - c_mean, some=False)
                 x = torch.cat([c_mean, v.t()[:n_components]], dim=0)
             out.append(x.unsqueeze(0))
+        if self.use_flatten:
+            out = out * self.num_embeds_per_token                         # :617-618: the one flat basis, repeated
         self.celeb_embeddings = torch.cat(out, 0).to(self.device if torch.cuda.is_available() else "cpu")
 
     @torch.no_grad()

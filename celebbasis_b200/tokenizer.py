@@ -19,8 +19,11 @@ BOS, EOS = 49406, 49407
 
 
 class SyntheticCLIPTokenizer:
-    def __init__(self, max_length=77):
+    def __init__(self, max_length=77, phrases=None):
+        """phrases: optional {text: [ids]} table of REAL CLIP BPE ids for whole strings (the celebrity names of
+        infer_images/token_len.txt), looked up before the per-word fallback."""
         self.model_max_length = max_length
+        self.phrases = dict(phrases or {})
 
     @staticmethod
     def word_id(word):
@@ -31,7 +34,10 @@ class SyntheticCLIPTokenizer:
         return 1000 + h % 40000
 
     def encode_one(self, text, max_length):
-        ids = [BOS] + [self.word_id(w) for w in text.split()][: max_length - 2] + [EOS]
+        body = self.phrases.get(text)
+        if body is None:
+            body = [self.word_id(w) for w in text.split()]
+        ids = [BOS] + list(body)[: max_length - 2] + [EOS]
         return ids + [EOS] * (max_length - len(ids))
 
     def __call__(self, text, truncation=True, max_length=77, return_length=True, return_overflowing_tokens=False,

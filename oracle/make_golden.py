@@ -193,6 +193,87 @@ def run_curve(kind="tiny", steps=50, lr=5e-3):
           f"optimizer={out['optimizer']} {out['opt_defaults']}")
 
 
+def _token_len_table():
+    """infer_images/token_len.txt (written by modules.py:503-515 with the real CLIP BPE vocabulary): name -> real ids."""
+    import re
+    table = {}
+    with open(os.path.join(ref_shim.REF_ROOT, "infer_images", "token_len.txt")) as f:
+        for line in f:
+            m = re.match(r"\d+ (.*): len=\d+, token=\[(.*)\]\s*$", line)
+            if m:
+                table[m.group(1)] = [int(t) for t in m.group(2).split(",") if t.strip()]
+    return table
+
+
+def run_basis():
+    """f3: FrozenCLIPEmbedder._get_celeb_embeddings (modules.py:472-624) of the UNMODIFIED reference on its own name list
+    (infer_images/wiki_names_v2.txt) with the REAL CLIP token ids of infer_images/token_len.txt (names that file does not
+    list fall back to the synthetic per-word ids), a synthetic token-embedding table, three configurations."""
+    table = _token_len_table()
+    ref_shim.PHRASES.clear()
+    ref_shim.PHRASES.update(table)
+    ref_shim.install_stubs(2)
+    from ldm.modules.encoders.modules import FrozenCLIPEmbedder
+    names_path = os.path.join(ref_shim.REF_ROOT, "infer_images", "wiki_names_v2.txt")
+    with open(names_path) as f:
+        names = f.read().splitlines()
+    out = {"names": names, "phrases": {n: table[n] for n in set(names) if n in table}, "cases": []}
+    for cfg in (dict(use_flatten=False, use_sample_reduce=False), dict(use_flatten=True, use_sample_reduce=False),
+                dict(use_flatten=False, use_sample_reduce=True)):
+        torch.manual_seed(0)
+        emb = FrozenCLIPEmbedder(device="cpu", celeb_txt=names_path, use_celeb=False, use_svd=True, n_components=512,
+                                 rm_repeats=True, n_samples=513, num_embeds_per_token=2, **cfg)
+        sd = synth.synth_state_dict(emb, seed=0, prefix="cond_stage_model.")
+        emb.load_state_dict(sd, strict=False)
+        emb.use_celeb = True
+        emb._get_celeb_embeddings(512)
+        ce = emb.celeb_embeddings.detach().float().cpu()
+        out["cases"].append({"cfg": cfg, "shape": tuple(ce.shape), "mean_rows": ce[:, 0].clone(),
+                             "head": ce[:, :33].clone(), "row_norms": ce.norm(dim=-1).clone(),
+                             "gram_diag_err": float((ce[:, 1:] @ ce[:, 1:].transpose(1, 2)
+                                                     - torch.eye(ce.shape[1] - 1)).abs().max())})
+        print(f"[basis] {cfg}: shape {tuple(ce.shape)} |mean| {ce[:, 0].norm(dim=-1).tolist()}")
+    torch.save(out, os.path.join(GOLD, "celeb_basis.pt"))
+
+
+def run_ti():
+    """f4: the vanilla Textual-Inversion EmbeddingManager.forward of the UNMODIFIED reference (embedding_manager.py:38-184)
+    on CPU: one vector per token and three vectors per token (insertion with shifting), two placeholders, and the
+    checkpoint its save() writes."""
+    ref_shim.install_stubs(2)
+    from ldm.modules.encoders.modules import FrozenCLIPEmbedder
+    from ldm.modules.embedding_manager import EmbeddingManager
+    torch.manual_seed(0)
+    emb = FrozenCLIPEmbedder(device="cpu", use_celeb=False)
+    emb.load_state_dict(synth.synth_state_dict(emb, seed=0, prefix="cond_stage_model."), strict=False)
+    tok = emb.tokenizer
+    prompts = ["a photo of * person", "* and ks with a * face", "no placeholder here"]
+    cases = []
+    import tempfile
+    for nv in (1, 3):
+        torch.manual_seed(1)
+        em = EmbeddingManager(emb, placeholder_strings=["*", "ks"], initializer_words=None, num_vectors_per_token=nv)
+        ids = tok(prompts, truncation=True, max_length=77, return_length=True, return_overflowing_tokens=False,
+                  padding="max_length", return_tensors="pt")["input_ids"]
+        g = torch.Generator().manual_seed(5)
+        text = torch.randn(len(prompts), 77, 768, generator=g)
+        ids_in, text_in = ids.clone(), text.clone()
+        out = em(ids_in, text_in)
+        out.sum().backward() if out.requires_grad else None
+        with tempfile.TemporaryDirectory() as td:
+            em.save(os.path.join(td, "ti.pt"))
+            ck = torch.load(os.path.join(td, "ti.pt"), weights_only=False)
+        cases.append({"nv": nv, "ids": ids, "text_seed": 5, "text_sum": float(text.double().sum()),
+                      "out": out.detach().clone(), "ids_after": ids_in.clone(),
+                      "params": {k: v.detach().clone() for k, v in em.string_to_param_dict.items()},
+                      "tokens": {k: int(v) for k, v in em.string_to_token_dict.items()},
+                      "grads": {k: (v.grad.detach().clone() if v.grad is not None else None)
+                                for k, v in em.string_to_param_dict.items()},
+                      "ckpt_keys": sorted(ck.keys()), "ckpt_types": {k: type(v).__name__ for k, v in ck.items()}})
+        print(f"[ti] nv={nv}: out {tuple(out.shape)} ids_after[1][:12]={ids_in[1][:12].tolist()}")
+    torch.save({"prompts": prompts, "cases": cases}, os.path.join(GOLD, "ti_manager.pt"))
+
+
 def helpers_kat():
     """helpers.py:44-54 toy case, computed by the reference's own functions."""
     ref_shim.install_stubs()
@@ -230,5 +311,9 @@ if __name__ == "__main__":
             run_infer("tiny")
         elif w == "curve":
             run_curve("tiny")
+        elif w == "basis":
+            run_basis()
+        elif w == "ti":
+            run_ti()
         else:
             run(w)

@@ -30,6 +30,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from celebbasis_b200.tokenizer import BOS, EOS, KNOWN_TOKENS, SyntheticCLIPTokenizer  # noqa: E402
 
 
+PHRASES = {}        # {text: real CLIP BPE ids}: set by make_golden.py for the celeb-basis fixture (infer_images/token_len.txt)
+
+
 class _Cfg(dict):
     """dict with attribute access, enough of OmegaConf for ldm.util.instantiate_from_config / ddpm.py."""
 
@@ -116,7 +119,7 @@ def install_stubs(clip_layers=12):
     from transformers import CLIPTextConfig, CLIPTextModel, CLIPTokenizer
 
     def tok_from_pretrained(*a, **k):
-        return SyntheticCLIPTokenizer()
+        return SyntheticCLIPTokenizer(phrases=PHRASES)
 
     def model_from_pretrained(*a, **k):
         cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=clip_layers,

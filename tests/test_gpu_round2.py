@@ -414,3 +414,34 @@ def test_inference_txt2img_size_vs_port(dev):
 def om_basis(dev):
     from celebbasis_b200 import synth
     return synth.synth_celeb_basis(seed=0).to(dev)
+
+
+def test_textual_inversion_manager_vs_reference_golden(dev, golden_dir):
+    """f4: the vanilla EmbeddingManager (v1-finetune.yaml) on the inject kernel: forward rows are COPIES, so the output must
+    equal the UNMODIFIED reference's bit for bit; the gradient of each placeholder's parameter sums over its occurrences."""
+    from ldm.modules.embedding_manager import EmbeddingManager
+    from ldm.modules.encoders.modules import FrozenCLIPEmbedder
+    gold = torch.load(os.path.join(golden_dir, "ti_manager.pt"), weights_only=False)
+    emb = FrozenCLIPEmbedder(device="cuda", use_celeb=False, num_hidden_layers=1)
+    for case in gold["cases"]:
+        nv = case["nv"]
+        em = EmbeddingManager(emb, placeholder_strings=list(case["tokens"].keys()), initializer_words=None,
+                              num_vectors_per_token=nv)
+        for k, v in case["params"].items():
+            assert int(em.string_to_token_dict[k]) == case["tokens"][k]
+            em.string_to_param_dict[k].data.copy_(v)
+        em = em.to(dev)
+        g = torch.Generator().manual_seed(case["text_seed"])
+        text = torch.randn(len(gold["prompts"]), 77, 768, generator=g).to(dev)
+        ids = case["ids"].clone().to(dev)
+        out = em(ids, text)
+        assert torch.equal(out.cpu(), case["out"]), nv
+        if nv > 1:
+            assert torch.equal(ids.cpu(), case["ids_after"])
+        out.sum().backward()
+        for k, gref in case["grads"].items():
+            got = em.string_to_param_dict[k].grad
+            if gref is None:
+                assert got is None or float(got.abs().max()) == 0
+            else:
+                assert torch.allclose(got.cpu(), gref, atol=1e-6), (nv, k)

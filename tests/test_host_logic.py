@@ -204,3 +204,62 @@ def test_embedding_checkpoint_format_matches_reference(golden_dir, tmp_path):
             for a, b in zip(mine[k], gold[prec][k]):
                 assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
     em.save_fp16 = False
+
+
+def test_celeb_basis_construction_vs_reference(golden_dir, tmp_path):
+    """FrozenCLIPEmbedder._get_celeb_embeddings (modules.py:472-624).  The fixture was produced by the
+    UNMODIFIED reference on infer_images/wiki_names_v2.txt with the real CLIP BPE ids of infer_images/token_len.txt
+    (oracle/make_golden.py basis): per-column basis (aigc_id.yaml), the flattened basis (constructor default) and the
+    sample-reduced variant.  Singular vectors are compared up to sign."""
+    from celebbasis_b200 import synth
+    from celebbasis_b200.tokenizer import SyntheticCLIPTokenizer
+    from ldm.modules.encoders.modules import FrozenCLIPEmbedder
+    gold = torch.load(os.path.join(golden_dir, "celeb_basis.pt"), weights_only=False)
+    names_file = tmp_path / "names.txt"
+    names_file.write_text("\n".join(gold["names"]) + "\n")
+    for case in gold["cases"]:
+        emb = FrozenCLIPEmbedder(device="cpu", celeb_txt=str(names_file), use_celeb=False, use_svd=True, n_components=512,
+                                 rm_repeats=True, n_samples=513, num_embeds_per_token=2, num_hidden_layers=1, **case["cfg"])
+        emb.tokenizer = SyntheticCLIPTokenizer(phrases=gold["phrases"])
+        sd = synth.synth_state_dict(emb, seed=0, prefix="cond_stage_model.")
+        emb.load_state_dict({k: v for k, v in sd.items() if "token_embedding" in k}, strict=False)
+        emb._get_celeb_embeddings(512)
+        ce = emb.celeb_embeddings.float().cpu()
+        assert tuple(ce.shape) == tuple(case["shape"]) == (2, 513, 768)
+        assert torch.allclose(ce[:, 0], case["mean_rows"], atol=1e-6), case["cfg"]
+        assert torch.allclose(ce.norm(dim=-1), case["row_norms"], atol=1e-4)
+        head = case["head"]
+        cosv = (ce[:, 1:33] * head[:, 1:33]).sum(-1).abs()                  # right-singular vectors: up to sign
+        assert float(cosv.min()) > 0.9999, (case["cfg"], float(cosv.min()))
+        eye = torch.eye(512)
+        assert float((ce[0, 1:] @ ce[0, 1:].t() - eye).abs().max()) < 1e-4    # orthonormal basis rows
+        if case["cfg"]["use_flatten"]:
+            assert torch.equal(ce[0], ce[1])                                   # the one flat basis, repeated (:617-618)
+
+
+def test_textual_inversion_row_map_vs_reference(golden_dir):
+    """SURVEY f4 (integer path, bit-exact): the host row map of the vanilla EmbeddingManager reproduces the UNMODIFIED
+    reference's forward (embedding_manager.py:96-151) -- replacement for one vector per token, right-to-left expansion with
+    truncation for three, the in-place token rewrite a later placeholder sees."""
+    from ldm.modules.embedding_manager import build_ti_map
+    gold = torch.load(os.path.join(golden_dir, "ti_manager.pt"), weights_only=False)
+    for case in gold["cases"]:
+        g = torch.Generator().manual_seed(case["text_seed"])
+        text = torch.randn(len(gold["prompts"]), 77, 768, generator=g)
+        assert abs(float(text.double().sum()) - case["text_sum"]) < 1e-6
+        nv = case["nv"]
+        placeholders, base, z = [], 0, []
+        for key, tok in case["tokens"].items():
+            placeholders.append((tok, base, nv))
+            z.append(case["params"][key])
+            base += nv
+        m, new_tok = build_ti_map(case["ids"].numpy(), placeholders, nv, nv)
+        zr = torch.cat(z, 0)
+        out = torch.empty_like(text)
+        for b in range(text.shape[0]):
+            for i in range(77):
+                out[b, i] = text[b, m[b, i]] if m[b, i] >= 0 else zr[-(m[b, i] + 1)]
+        assert torch.equal(out, case["out"]), nv
+        if nv > 1:
+            assert torch.equal(torch.from_numpy(new_tok), case["ids_after"])
+        assert case["ckpt_keys"] == ["string_to_param", "string_to_token"]
