@@ -41,6 +41,8 @@ SIGS = {
     "cb_face_warp_resize": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "cb_l2norm_rows": [_p, _p, _i, _i, _p],
     "cb_ema_rows": [_p, _p, _i, _p, _i, _i, _i, _f, _p],
+    "cb_face_augment": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "cb_paste_resized": [_p, _i, _i, _p, _p, _i, _i, _i, _p],
     "cb_pack_conv_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "cb_convert_f32": [_p, _p, _i, _l, _f, _p],
 }

@@ -173,14 +173,16 @@ class Trainer:
     def _lookahead(self, loader):
         """(index, batch on the device, next batch on the device or None): one batch of look-ahead, each batch moved once."""
         it = iter(loader)
+        prep = getattr(self.lightning_module, "preprocess_batch", None)      # device-side data path, if the module has one
+        prep = prep if callable(prep) else (lambda b: b)
         try:
-            cur = _move(next(it), self.device)
+            cur = prep(_move(next(it), self.device))
         except StopIteration:
             return
         idx = 0
         while True:
             try:
-                nxt = _move(next(it), self.device)
+                nxt = prep(_move(next(it), self.device))
             except StopIteration:
                 nxt = None
             yield idx, cur, nxt

@@ -346,7 +346,16 @@ class LatentDiffusion(DDPM):
         return out
 
     # ---- the training step (ddpm.py:921-936,948-1049,1069-1116) ---------------------------------------------------
+    def preprocess_batch(self, batch):
+        """RAW batches of the ldm.data.face_id mirror (uint8 images + drawn augmentation parameters) -> the batch dict the
+        reference's DataLoader yields, with the pixel work done on this module's device (celebbasis_b200.data_path)."""
+        from celebbasis_b200 import data_path
+        if data_path.is_raw_batch(batch):
+            return data_path.device_augment(batch, self.device)
+        return batch
+
     def shared_step(self, batch, **kwargs):
+        batch = self.preprocess_batch(batch)
         if self._fused_applicable(batch):
             return self._fused_shared_step(batch)
         x, c = self.get_input(batch, self.first_stage_key)

@@ -65,3 +65,27 @@ def synth_batch(kind="full", B=1, seed=1234, step=0):
              "noise": torch.randn(B, 4, lat, lat, generator=gt),
              "posterior_eps": torch.randn(B, 4, lat, lat, generator=gt)}
     return batch, draws
+
+
+def synth_face_files(out_dir, n=4, hw=64, seed=0):
+    """n deterministic smooth colour images (stand-ins for aligned face crops) written as lossless PNGs named like the
+    reference's fixtures (`0000N_idN.png`: identity = file stem) + the pickle FaceIdDataset* reads (gen_pickle.py: a list
+    of paths).  Returns (pickle path, list of image paths)."""
+    import os
+    import pickle
+    import numpy as np
+    from PIL import Image
+    os.makedirs(out_dir, exist_ok=True)
+    rng = np.random.RandomState(seed)
+    paths = []
+    for i in range(n):
+        low = rng.rand(8, 8, 3)
+        img = np.asarray(Image.fromarray((low * 255).astype(np.uint8)).resize((hw, hw), Image.BICUBIC), dtype=np.float32)
+        img = np.clip(img + rng.randn(hw, hw, 3) * 6.0, 0, 255).astype(np.uint8)
+        p = os.path.join(out_dir, f"{i:05d}_id{i}.png")
+        Image.fromarray(img).save(p)
+        paths.append(p)
+    pk = os.path.join(out_dir, "ffhq.pickle")
+    with open(pk, "wb") as f:
+        pickle.dump(paths, f)
+    return pk, paths

@@ -326,6 +326,21 @@ int cb_pack_conv_weight(const float* w, void* out, int o_dtype, int cout, int ci
                         int cin_pad, const float* out_scale, void* stream);
 int cb_convert_f32(const float* x, void* out, int o_dtype, long long n, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side data path: the pixel work of FaceIdDatasetStyleGAN3.__getitem__
+ * (ldm/data/face_id.py:526-532 transform chain, :451-470 _add_bg, :598-644).  Random draws stay on the host.
+ * cb_face_augment: uint8 [B][H][W][3] -> RandomHorizontalFlip, ColorJitter (ops in the drawn order, torchvision tensor
+ *   arithmetic), ToTensor, Normalize(0.5,0.5): fp32 in [-1,1] written into channels [c_off, c_off+3) of an
+ *   [B][H][W][c_total] tensor (the `faces` stack).  iparams [B][5] = {flip, op order x4 (0 brightness, 1 contrast,
+ *   2 saturation, 3 hue, <0 skip)}, fparams [B][4] = {brightness, contrast, saturation, hue factor}; ws: B doubles.
+ * cb_paste_resized: _add_bg -- out [B][H][W][3] = -1 with the face (channels [c_off, c_off+3) of faces) resized
+ *   bilinearly (align_corners=True, ATen index math) to (rh, rw) and pasted at (pos_h, pos_w); geo [B][4].
+ * ------------------------------------------------------------------------------------------- */
+int cb_face_augment(const unsigned char* src_u8, const int* iparams, const float* fparams, double* ws, float* out, int B,
+                    int H, int W, int c_total, int c_off, void* stream);
+int cb_paste_resized(const float* faces, int c_total, int c_off, const int* geo, float* out, int B, int H, int W,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

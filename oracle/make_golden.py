@@ -274,6 +274,38 @@ def run_ti():
     torch.save({"prompts": prompts, "cases": cases}, os.path.join(GOLD, "ti_manager.pt"))
 
 
+def run_data():
+    """f2: FaceIdDatasetOneShot.__getitem__ of the UNMODIFIED reference (PIL + torchvision transforms on the host) on
+    synthetic images: captions, identity lists, the tensors it yields and the state of the three RNGs after each item (the
+    device data path must consume exactly the same draws)."""
+    import hashlib
+    import pickle
+    import random
+    import tempfile
+    ref_shim.install_stubs(2)
+    from ldm.data.face_id import FaceIdDatasetOneShot
+    hw = 64
+    with tempfile.TemporaryDirectory() as td:
+        pk, _ = workload.synth_face_files(td, n=4, hw=hw, seed=0)
+        items = []
+        for split, diff in (("train", 0), ("train", 1)):
+            random.seed(11)
+            np.random.seed(11)
+            torch.manual_seed(11)
+            ds = FaceIdDatasetOneShot(pk, num_ids=3, specific_ids=[0, 1, 3], image_size=hw, repeats=5, split=split,
+                                      diff_cnt=diff)
+            for i in (0, 4, 7):
+                ex = ds[i]
+                dig = hashlib.sha1(pickle.dumps((random.getstate(), np.random.get_state()[1].tobytes(),
+                                                 np.random.get_state()[2], torch.get_rng_state().numpy().tobytes()))).hexdigest()
+                items.append({"split": split, "diff_cnt": diff, "index": i, "caption": ex["caption"],
+                              "ids": ex["image_ori"]["ids"].clone(), "num_ids": ex["image_ori"]["num_ids"],
+                              "image": ex["image"].clone(), "faces": ex["image_ori"]["faces"].clone(), "rng_digest": dig,
+                              "len": len(ds)})
+    torch.save({"hw": hw, "items": items, "seed": 11}, os.path.join(GOLD, "data_path.pt"))
+    print("[data]", [(it["index"], it["caption"], it["ids"].tolist()) for it in items])
+
+
 def helpers_kat():
     """helpers.py:44-54 toy case, computed by the reference's own functions."""
     ref_shim.install_stubs()
@@ -313,6 +345,8 @@ if __name__ == "__main__":
             run_curve("tiny")
         elif w == "basis":
             run_basis()
+        elif w == "data":
+            run_data()
         elif w == "ti":
             run_ti()
         else:

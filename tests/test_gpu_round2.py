@@ -445,3 +445,64 @@ def test_textual_inversion_manager_vs_reference_golden(dev, golden_dir):
                 assert got is None or float(got.abs().max()) == 0
             else:
                 assert torch.allclose(got.cpu(), gref, atol=1e-6), (nv, k)
+
+
+def test_device_data_path_vs_reference_and_torchvision(dev, golden_dir, tmp_path):
+    """f2 (device half): cb_face_augment / cb_paste_resized on the same draws.
+    (1) vs torchvision's tensor kernels (adjust_brightness/contrast/saturation/hue, hflip) + F.interpolate(align_corners)
+        + paste on the same parameters: colour <= 1e-3, geometry exact (same pixels are background);
+    (2) vs the tensors the UNMODIFIED reference dataset produced (PIL ops, which round to uint8 after every jitter step):
+        within the uint8 quantisation of four ops."""
+    import random
+    import torchvision.transforms.functional as TF
+    from celebbasis_b200 import data_path, workload
+    from ldm.data.face_id import FaceIdDatasetOneShot
+    gold = torch.load(os.path.join(golden_dir, "data_path.pt"), weights_only=False)
+    hw = gold["hw"]
+    pk, _ = workload.synth_face_files(str(tmp_path), n=4, hw=hw, seed=0)
+    items = iter(gold["items"])
+    for split, diff in (("train", 0), ("train", 1)):
+        random.seed(gold["seed"])
+        np.random.seed(gold["seed"])
+        torch.manual_seed(gold["seed"])
+        ds = FaceIdDatasetOneShot(pk, num_ids=3, specific_ids=[0, 1, 3], image_size=hw, repeats=5, split=split, diff_cnt=diff)
+        for i in (0, 4, 7):
+            g = next(items)
+            ex = ds[i]
+            batch = torch.utils.data.default_collate([ex])
+            out = data_path.device_augment(batch, dev)
+            img, faces = out["image"][0].cpu(), out["image_ori"]["faces"][0].cpu()
+            assert faces.shape == g["faces"].shape and img.shape == g["image"].shape
+            # (1) torchvision tensor path on the same draws
+            k = ex["image_u8"].shape[0]
+            ref_faces = []
+            for j in range(k):
+                t = ex["image_u8"][j].permute(2, 0, 1).float() / 255.0
+                ip, fp = ex["aug_i"][j].tolist(), ex["aug_f"][j].tolist()
+                if ip[0]:
+                    t = TF.hflip(t)
+                for op in ip[1:]:
+                    if op == 0:
+                        t = TF.adjust_brightness(t, fp[0])
+                    elif op == 1:
+                        t = TF.adjust_contrast(t, fp[1])
+                    elif op == 2:
+                        t = TF.adjust_saturation(t, fp[2])
+                    elif op == 3:
+                        t = TF.adjust_hue(t, fp[3])
+                ref_faces.append(((t - 0.5) / 0.5).permute(1, 2, 0))
+            ref_faces = torch.cat(ref_faces, -1)
+            assert float((faces - ref_faces).abs().max()) < 1e-3, float((faces - ref_faces).abs().max())
+            rh, rw, ph, pw = ex["aug_geo"].tolist()
+            small = F.interpolate(ref_faces[..., :3].permute(2, 0, 1)[None], (rh, rw), mode="bilinear", align_corners=True)[0]
+            ref_img = -torch.ones(hw, hw, 3)
+            ref_img[ph:ph + rh, pw:pw + rw] = small.permute(1, 2, 0)
+            assert float((img - ref_img).abs().max()) < 1e-3
+            bg = torch.ones(hw, hw, dtype=torch.bool)
+            bg[ph:ph + rh, pw:pw + rw] = False
+            assert float((img[bg] + 1).abs().max()) == 0.0                       # geometry: exact
+            # (2) the reference's own (PIL) output: uint8 rounding after each of the four jitter ops
+            assert float((faces - g["faces"]).abs().max()) < 4e-2, float((faces - g["faces"]).abs().max())
+            assert float((faces - g["faces"]).abs().mean()) < 6e-3
+            assert float((img - g["image"]).abs().max()) < 4e-2
+            assert out["caption"] == [g["caption"]] and out["image_ori"]["ids"].tolist() == [g["ids"].tolist()]

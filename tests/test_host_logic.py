@@ -263,3 +263,44 @@ def test_textual_inversion_row_map_vs_reference(golden_dir):
         if nv > 1:
             assert torch.equal(torch.from_numpy(new_tok), case["ids_after"])
         assert case["ckpt_keys"] == ["string_to_param", "string_to_token"]
+
+
+def _rng_digest():
+    import hashlib
+    import pickle
+    import random
+    return hashlib.sha1(pickle.dumps((random.getstate(), np.random.get_state()[1].tobytes(), np.random.get_state()[2],
+                                      torch.get_rng_state().numpy().tobytes()))).hexdigest()
+
+
+def test_data_path_draws_match_reference(golden_dir, tmp_path):
+    """SURVEY f2 (host half): the dataset mirror makes exactly the reference's random draws -- after every __getitem__ the
+    state of python's `random`, numpy's and torch's generators equals the state the UNMODIFIED reference dataset left
+    behind (fixture: oracle/make_golden.py data), and captions / identity lists / dataset length are identical."""
+    import random
+    from celebbasis_b200 import workload
+    from ldm.data.face_id import FaceIdDatasetOneShot
+    gold = torch.load(os.path.join(golden_dir, "data_path.pt"), weights_only=False)
+    pk, _ = workload.synth_face_files(str(tmp_path), n=4, hw=gold["hw"], seed=0)
+    items = iter(gold["items"])
+    for split, diff in (("train", 0), ("train", 1)):
+        random.seed(gold["seed"])
+        np.random.seed(gold["seed"])
+        torch.manual_seed(gold["seed"])
+        ds = FaceIdDatasetOneShot(pk, num_ids=3, specific_ids=[0, 1, 3], image_size=gold["hw"], repeats=5, split=split,
+                                  diff_cnt=diff)
+        for i in (0, 4, 7):
+            g = next(items)
+            ex = ds[i]
+            assert len(ds) == g["len"] and ex["caption"] == g["caption"]
+            assert ex["image_ori"]["ids"].tolist() == g["ids"].tolist() and ex["image_ori"]["num_ids"] == g["num_ids"]
+            assert _rng_digest() == g["rng_digest"], (split, diff, i)
+            k = 2 + 2 * diff
+            assert ex["image_u8"].shape == (k, gold["hw"], gold["hw"], 3) and ex["image_u8"].dtype == torch.uint8
+            rh, rw, ph, pw = ex["aug_geo"].tolist()
+            # the pasted rectangle of the reference's `image` is where it differs from the -1 background
+            ref_img = g["image"]
+            inside = ref_img[ph:ph + rh, pw:pw + rw]
+            outside = ref_img.clone()
+            outside[ph:ph + rh, pw:pw + rw] = -1.0
+            assert float((outside + 1.0).abs().max()) == 0.0 and inside.shape[:2] == (rh, rw)
