@@ -499,10 +499,11 @@ def run_txt2img(args):
                                   unconditional_guidance_scale=scale, unconditional_conditioning=uc, eta=0.0, x_T=x_T)
             return model.decode_first_stage(z)
 
-    ops.GEMM_RECORD = []                      # the UNet's batch-16 GEMMs, recorded while its inference graph is captured
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    UNetModel.CAPTURE_GEMM_SINK = gemm_record = []   # the UNet's batch-16 GEMMs, recorded while its graph is captured
     uc, c = conditioning()
     sample(uc, c, 2)                          # builds engines, autotunes, captures the UNet graph
-    gemm_record, ops.GEMM_RECORD = [r for r in ops.GEMM_RECORD], None
+    UNetModel.CAPTURE_GEMM_SINK = None
     torch.cuda.synchronize()
 
     def timed(fn, n):

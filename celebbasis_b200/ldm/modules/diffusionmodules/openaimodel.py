@@ -148,6 +148,7 @@ class UNetModel(nn.Module):
         return self._engine
 
     GRAPH_INFERENCE = True     # no-grad forwards (the DDIM loop) replay one CUDA graph per input shape
+    CAPTURE_GEMM_SINK = None   # optional list receiving (GemmDesc bytes, flops) of the launches captured into those graphs
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         assert y is None, "class-conditional UNets are not on the CelebBasis path"
@@ -170,14 +171,16 @@ class UNetModel(nn.Module):
             ts = timesteps.detach().long().contiguous().clone()
             cs = context.detach().float().contiguous().clone()
             from celebbasis_b200 import ops as _ops
-            rec, _ops.GEMM_RECORD = _ops.GEMM_RECORD, None       # a GEMM recorder (bench.py) sees the captured launches only
             for _ in range(2):                                   # eager: GEMM autotune + lazily created workspaces
                 eng.forward(xs, ts, cs, need_grad=False)
             torch.cuda.synchronize()
-            _ops.GEMM_RECORD = rec
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = eng.forward(xs, ts, cs, need_grad=False)
+            prev, _ops.GEMM_RECORD = _ops.GEMM_RECORD, self.CAPTURE_GEMM_SINK   # bench.py: the captured launches only
+            try:                                                                 # (their buffers live in the graph's pool)
+                with torch.cuda.graph(g):
+                    out = eng.forward(xs, ts, cs, need_grad=False)
+            finally:
+                _ops.GEMM_RECORD = prev
             ent = cache[key] = (g, xs, ts, cs, out)
         g, xs, ts, cs, out = ent
         xs.copy_(x)

@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--gpus", default="0,")
     args = ap.parse_args()
+    args.ref, args.work = os.path.abspath(args.ref), os.path.abspath(args.work)
     import numpy as np
     import torch
     from celebbasis_b200 import synth, workload
