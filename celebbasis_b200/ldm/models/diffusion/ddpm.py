@@ -497,6 +497,48 @@ class LatentDiffusion(DDPM):
         loss_dict.update({f'{prefix}/loss': loss})
         return loss, loss_dict
 
+    # ---- image logging (ddpm.py:1305-1440; called by main.ImageLogger every batch_frequency steps) --------------------
+    @torch.no_grad()
+    def sample_log(self, cond, batch_size, ddim, ddim_steps, **kwargs):
+        assert ddim, "the CelebBasis configs log with the DDIM sampler"
+        from ldm.models.diffusion.ddim import DDIMSampler
+        shape = (self.channels, self.image_size, self.image_size)
+        return DDIMSampler(self).sample(ddim_steps, batch_size, shape, cond, verbose=False, **kwargs)
+
+    @torch.no_grad()
+    def log_images(self, batch, N=8, n_row=4, sample=True, ddim_steps=50, ddim_eta=1., return_keys=None,
+                   quantize_denoised=True, inpaint=False, plot_denoise_rows=False, plot_progressive_rows=False,
+                   plot_diffusion_rows=False, **kwargs):
+        """inputs / reconstruction / rendered captions / DDIM samples (plain and with guidance 5.0), as the reference logs
+        them (the inpainting, progressive and diffusion-row panels are off in every CelebBasis config)."""
+        from ldm.util import log_txt_as_img
+        assert not (inpaint or plot_denoise_rows or plot_progressive_rows or plot_diffusion_rows)
+        batch = self.preprocess_batch(batch)
+        log = dict()
+        z, c, x, xrec, xc = self.get_input(batch, self.first_stage_key, return_first_stage_outputs=True,
+                                           force_c_encode=True, return_original_cond=True, bs=N)
+        c = c['caption']
+        N = min(x.shape[0], N)
+        log["inputs"] = x
+        log["reconstruction"] = xrec
+        if self.model.conditioning_key is not None and self.cond_stage_key in ["caption"]:
+            log["conditioning"] = log_txt_as_img((x.shape[2], x.shape[3]), batch["caption"][:N])
+        if sample:
+            with self.ema_scope("Plotting"):
+                samples, _ = self.sample_log(cond=c, batch_size=N, ddim=ddim_steps is not None, ddim_steps=ddim_steps,
+                                             eta=ddim_eta)
+            log["samples"] = self.decode_first_stage(samples)
+            uc = self.get_learned_conditioning(len(c) * [""])
+            sample_scaled, _ = self.sample_log(cond=c, batch_size=N, ddim=ddim_steps is not None, ddim_steps=ddim_steps,
+                                               eta=ddim_eta, unconditional_guidance_scale=5.0,
+                                               unconditional_conditioning=uc)
+            log["samples_scaled"] = self.decode_first_stage(sample_scaled)
+        if return_keys:
+            if np.intersect1d(list(log.keys()), return_keys).shape[0] == 0:
+                return log
+            return {key: log[key] for key in return_keys}
+        return log
+
     # ---- optimisation / checkpoint cadence (ddpm.py:1442-1454,1519-1528) --------------------------------------------
     def configure_optimizers(self):
         lr = self.learning_rate

@@ -174,6 +174,8 @@ class UNetModel(nn.Module):
             for _ in range(2):                                   # eager: GEMM autotune + lazily created workspaces
                 eng.forward(xs, ts, cs, need_grad=False)
             torch.cuda.synchronize()
+            from celebbasis_b200 import lib as _lib
+            n0 = _lib.launch_count()
             g = torch.cuda.CUDAGraph()
             prev, _ops.GEMM_RECORD = _ops.GEMM_RECORD, self.CAPTURE_GEMM_SINK   # bench.py: the captured launches only
             try:                                                                 # (their buffers live in the graph's pool)
@@ -181,10 +183,12 @@ class UNetModel(nn.Module):
                     out = eng.forward(xs, ts, cs, need_grad=False)
             finally:
                 _ops.GEMM_RECORD = prev
+            self.__dict__.setdefault("_graph_launches", {})[key] = _lib.launch_count() - n0
             ent = cache[key] = (g, xs, ts, cs, out)
         g, xs, ts, cs, out = ent
         xs.copy_(x)
         ts.copy_(timesteps)
         cs.copy_(context)
         g.replay()
+        self.__dict__["_replayed_launches"] = self.__dict__.get("_replayed_launches", 0) + self._graph_launches[key]
         return out

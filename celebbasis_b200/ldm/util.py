@@ -44,3 +44,22 @@ def cfg_get(cfg, *keys, default=None):
         except Exception:
             return default
     return cur
+
+
+def log_txt_as_img(wh, xc, size=10):
+    """ldm/util.py:17-38: the captions rendered as (B,3,H,W) images in [-1,1] for the image logger (host, PIL)."""
+    import numpy as np
+    import torch
+    from PIL import Image, ImageDraw, ImageFont
+    txts = []
+    for cap in xc:
+        txt = Image.new("RGB", wh, color="white")
+        draw = ImageDraw.Draw(txt)
+        nc = max(1, int(40 * (wh[0] / 256)))
+        lines = "\n".join(cap[start:start + nc] for start in range(0, len(cap), nc))
+        try:
+            draw.text((0, 0), lines, fill="black", font=ImageFont.load_default())
+        except UnicodeEncodeError:
+            print("Cant encode string for logging. Skipping.")
+        txts.append(np.array(txt).transpose(2, 0, 1) / 127.5 - 1.0)
+    return torch.tensor(np.stack(txts))
