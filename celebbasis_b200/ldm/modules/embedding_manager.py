@@ -159,8 +159,11 @@ class EmbeddingManagerId(nn.Module):
     def _embedding_to_device(self, device):
         if self.moved_to_device:
             return
-        self.id_embeddings = [x.to(device) for x in self.id_embeddings]
-        self.id_coefficients = [x.to(device) for x in self.id_coefficients]
+        # a checkpoint written in test_mode 'coefficient' carries no id_embeddings (load() leaves None), and vice versa
+        if self.id_embeddings is not None:
+            self.id_embeddings = [x.to(device) for x in self.id_embeddings]
+        if self.id_coefficients is not None:
+            self.id_coefficients = [x.to(device) for x in self.id_coefficients]
         self.moved_to_device = True
 
     # ---- checkpoint format (embedding_manager.py:396-426) -------------------------------------------------------
