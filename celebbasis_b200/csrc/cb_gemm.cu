@@ -35,6 +35,9 @@ struct GemmParams {
     void* D;
     int d_dtype;
     long long ldd, d_bs, d_bs2;
+    void* D2;          // optional second destination (same value, own dtype / row pitch)
+    int d2_dtype;
+    long long ldd2;
     int batch_inner;
     int d_transposed;
     int vec_ok;
@@ -150,6 +153,13 @@ __device__ __forceinline__ void store_any(void* base, int dtype, long long idx, 
     else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
 }
 
+// 8 consecutive values -> 16-byte aligned destination of any output dtype (second destination D2)
+__device__ __forceinline__ void store8_any(void* base, int dtype, long long idx, const float (&f)[8]) {
+    if (dtype == CB_F32) store8<float>(reinterpret_cast<float*>(base) + idx, f);
+    else if (dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(base) + idx, f);
+    else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + idx, f);
+}
+
 // Epilogue for 8 consecutive columns of one output row (one thread).  Kept deliberately small: the epilogue runs once
 // per CTA, so its cost is dominated by cold instruction fetch (~300 cycles per 128 B line of straight-line code).
 // Residual values of one 32-column chunk of this thread's row, fetched as raw 16-byte words BEFORE the accumulator is
@@ -242,6 +252,7 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
         if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
         else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
         else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
+        if (p.D2) store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col, f);
     } else {
         for (int j = 0; j < ncols; ++j) {
             float v = f[j];
@@ -249,6 +260,7 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             const long long didx = p.d_transposed ? (d_off + (long long)(col + j) * p.ldd + grow)
                                                   : (d_off + grow * p.ldd + col + j);
             store_any(p.D, p.d_dtype, didx, v);
+            if (p.D2) store_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + j, v);
         }
     }
 }
@@ -292,6 +304,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += r[j];
         }
+        if (p.D2) store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + g * 8, f);
         if (p.d_dtype == CB_F32) {
             float* dst = reinterpret_cast<float*>(p.D) + didx + g * 8;
             const uint4 a = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
@@ -653,12 +666,16 @@ CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    const long long ctas = (long long)grid.x * grid.y * grid.z;
-    static const int env_force = getenv("CB_GEMM_STAGES") ? atoi(getenv("CB_GEMM_STAGES")) : 0;   // tuning aid
-    const int force = p.force_stages ? p.force_stages : env_force;
-    if (force == 3) return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
-    if (force == 6 || ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
-    return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
+    if constexpr (BN == 256) {
+        return launch_s<BN, A_MN, B_MN, 4>(tA, tB, p, grid, st);   // 48 KiB stages: 4-deep ring, one CTA per SM
+    } else {
+        const long long ctas = (long long)grid.x * grid.y * grid.z;
+        static const int env_force = getenv("CB_GEMM_STAGES") ? atoi(getenv("CB_GEMM_STAGES")) : 0;   // tuning aid
+        const int force = p.force_stages ? p.force_stages : env_force;
+        if (force == 3) return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
+        if (force == 6 || ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
+        return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
+    }
 }
 
 // Measured on B200 (tools/gemm_timeline.py): one SM pulls ~80 GB/s of operand tiles out of L2, i.e. a k-iteration of a
@@ -688,6 +705,7 @@ static int pick_bn(const cb_gemm_desc& d, int m_tiles, int kiters) {
     }
     static const int env_bn = getenv("CB_GEMM_BN") ? atoi(getenv("CB_GEMM_BN")) : 0;   // tuning aid
     const int force_bn = d.tile_n > 0 ? d.tile_n : env_bn;
+    if (force_bn == 256 && N >= 256) return 256;    // 128x256 tile: only on request (per-shape autotuner / caller)
     for (int i = 0; i < nc; ++i)
         if (cands[i] == force_bn) return force_bn;
     int best = cands[0];
@@ -826,6 +844,16 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     p.d_bs = d.d_batch_stride;
     p.d_bs2 = d.d_batch_stride2;
     p.d_transposed = d.d_transposed;
+    p.D2 = d.D2;
+    p.d2_dtype = d.d2_dtype;
+    p.ldd2 = d.ldd2;
+    if (d.D2) {
+        CB_REQUIRE(d.batch == 1 && !d.d_transposed, CB_ERR_ARG, "cb_gemm: D2 needs batch == 1 and a non-transposed D");
+        CB_REQUIRE(d.d2_dtype >= CB_F16 && d.d2_dtype <= CB_F32, CB_ERR_ARG, "cb_gemm: bad d2_dtype");
+        const int es2 = d.d2_dtype == CB_F32 ? 4 : 2;
+        CB_REQUIRE((reinterpret_cast<uintptr_t>(d.D2) & 15u) == 0 && (d.ldd2 * es2) % 16 == 0 && d.ldd2 >= d.N, CB_ERR_ALIGN,
+                   "cb_gemm: D2 must be 16-byte aligned with a 16-byte multiple row pitch >= N");
+    }
     p.bias = d.bias;
     p.bias_row_div = d.bias_row_div;
     p.ldbias = d.ldbias;
@@ -904,9 +932,11 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     if (!a_mn && !b_mn) {
         if (BN == 64) return launch<64, false, false>(tA, tB, p, grid, st);
         if (BN == 128) return launch<128, false, false>(tA, tB, p, grid, st);
+        if (BN == 256) return launch<256, false, false>(tA, tB, p, grid, st);
         return launch<160, false, false>(tA, tB, p, grid, st);
     } else if (!a_mn && b_mn) {
         if (BN == 64) return launch<64, false, true>(tA, tB, p, grid, st);
+        if (BN == 256) return launch<256, false, true>(tA, tB, p, grid, st);
         return launch<128, false, true>(tA, tB, p, grid, st);
     } else {
         if (BN == 64) return launch<64, true, true>(tA, tB, p, grid, st);

@@ -377,7 +377,7 @@ template <typename TX, typename TG, typename TD>
 __global__ void __launch_bounds__(kGnThreads)
 gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const double* __restrict__ ws, TD* __restrict__ dx, int HW, int C, int G, int act,
+                    const double* __restrict__ ws, TD* __restrict__ dx, TG* __restrict__ dx_lp, int HW, int C, int G, int act,
                     int accumulate, int rows_per_block, int PW, int RY, int chunks) {
     pdl_sync();
     __shared__ float s_1[64], s_2[64];
@@ -418,6 +418,7 @@ gn_bwd_apply_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
                 o.y += p.y;
             }
             Vec2<TD>::st(dx + off, o);
+            if (dx_lp) Vec2<TG>::st(dx_lp + off, o);      // 16-bit copy for the dgrad GEMM that consumes dx next
         }
     }
 }
@@ -588,8 +589,8 @@ template <typename TX, typename TG, typename TD>
 __global__ void __launch_bounds__(kGnFusedThreads)
 gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    double* __restrict__ ws, unsigned* __restrict__ counter, TD* __restrict__ dx, int HW, int C, int G,
-                    int act, int accumulate, int rows_per_block, int PW, int RY, int chunks) {
+                    double* __restrict__ ws, unsigned* __restrict__ counter, TD* __restrict__ dx, TG* __restrict__ dx_lp,
+                    int HW, int C, int G, int act, int accumulate, int rows_per_block, int PW, int RY, int chunks) {
     // shared memory stages this CTA's rows of x and dy (two bulk copies); xhat / dz*gamma are recomputed from them
     extern __shared__ __align__(128) unsigned char gn_smem[];
     TX* sx = reinterpret_cast<TX*>(gn_smem);
@@ -680,6 +681,7 @@ gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
                 o.y += p.y;
             }
             Vec2<TD>::st(dx + off, o);
+            if (dx_lp) Vec2<TG>::st(dx_lp + off, o);      // 16-bit copy for the dgrad GEMM that consumes dx next
         }
     }
 }
@@ -894,7 +896,8 @@ CB_LAUNCH((gn_apply_kernel<TX, TY>), grid, nthr, 0, st, (const TX*)x, (TY*)y, ga
 
 extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
                                 const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype,
-                                int N, int HW, int C, int G, int act_silu, int accumulate, double* ws, void* stream) {
+                                void* dx_lp, int N, int HW, int C, int G, int act_silu, int accumulate, double* ws,
+                                void* stream) {
     int rc = gn_check(N, HW, C, G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -920,7 +923,7 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
                     auto kern = gn_fused_bwd_kernel<TX, TG, TDX>;                                                                     \
                     static bool set = false;                                                                                         \
                     if (!set) { CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; } \
-                    CB_LAUNCH((kern), gridf, gs.pw * ryf, smem, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, counter, (TDX*)dx, HW, C, G, act_silu, accumulate, rpbf, gs.pw, ryf, gs.chunks); \
+                    CB_LAUNCH((kern), gridf, gs.pw * ryf, smem, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, counter, (TDX*)dx, (TG*)dx_lp, HW, C, G, act_silu, accumulate, rpbf, gs.pw, ryf, gs.chunks); \
                 }))
                 if (dx_dtype == CB_F32) { CB_GN_BWD_FUSED(float); } else { CB_GN_BWD_FUSED(TG); }
 #undef CB_GN_BWD_FUSED
@@ -938,11 +941,11 @@ CB_LAUNCH((gn_bwd_stats_kernel<TX, TG>), grid, nthr, 0, st, (const TG*)dy, (cons
     // dx dtype: f32 or the gradient dtype
     if (dx_dtype == CB_F32) {
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, float>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, float>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (float*)dx, (TG*)dx_lp, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     } else {
         CB_REQUIRE(dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
         CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG,
-CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, TG>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
+CB_LAUNCH((gn_bwd_apply_kernel<TX, TG, TG>), grid, nthr, 0, st, (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, ws, (TG*)dx, (TG*)dx_lp, HW, C, G, act_silu, accumulate, rpb, gs.pw, gs.ry, gs.chunks)));
     }
     CB_CUDA(cudaGetLastError());
     cb::count_launches(2);

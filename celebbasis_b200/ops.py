@@ -80,7 +80,13 @@ TUNE_LOG = None     # set to a list to collect (key, table of candidate times)
 def _tune_key(d):
     return (d.M, d.N, d.K, d.batch, d.batch_inner, d.ab_dtype, d.a_major, d.b_major, d.conv, d.img_n, d.img_h, d.img_w,
             d.out_h, d.out_w, d.kh, d.kw, d.stride, d.flip_taps, d.d_dtype, d.d_transposed, 1 if d.R else 0, d.r_dtype,
-            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd)
+            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd, (d.d2_dtype + 1) if d.D2 else 0)
+
+
+def _set_out2(d, out2):
+    if out2 is not None:
+        assert out2.dim() == 2 and out2.stride(1) == 1
+        d.D2, d.d2_dtype, d.ldd2 = out2.data_ptr(), _dt(out2), out2.stride(0)
 
 
 def _autotune(d, key):
@@ -89,6 +95,8 @@ def _autotune(d, key):
     taps = d.kh * d.kw if d.conv else 1
     kiters = taps * ((d.K + 63) // 64)
     bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
+    if d.N >= 256 and d.a_major != CB_MAJOR_MN and M >= 1024:
+        bns = bns + [256]          # 128x256 tiles (4-stage ring, one CTA per SM): fewer operand bytes per flop for large GEMMs
     cands = [(0, 0, 0)]
     for bn in bns:
         tiles = ((d.N + bn - 1) // bn) * ((M + 127) // 128) * d.batch
@@ -115,6 +123,14 @@ def _autotune(d, key):
         sc = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device="cuda")
         _tune_scratch[dev] = sc
     t.D, t.R = sc.data_ptr(), None
+    if d.D2:
+        off = (nbytes + 255) // 256 * 256
+        n2 = int(d.ldd2 * M + d.N + 64) * (4 if d.d2_dtype == CB_F32 else 2)
+        if sc.numel() < off + n2:
+            sc = torch.empty(off + n2, dtype=torch.uint8, device="cuda")
+            _tune_scratch[dev] = sc
+            t.D = sc.data_ptr()
+        t.D2 = sc.data_ptr() + off
     L = _L()
     times = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,7 +254,7 @@ def gemm_raw(A, B, D, **kw):
     return raw.gemm(A, B, D, **kw)
 
 
-def linear(x, w, bias=None, *, out_dtype=None, out=None, act=CB_ACT_NONE, residual=None, alpha=1.0):
+def linear(x, w, bias=None, *, out_dtype=None, out=None, act=CB_ACT_NONE, residual=None, alpha=1.0, out2=None):
     """y[M][N] = act(alpha * x[M][K] @ w[N][K]^T + bias) + residual."""
     M, K = x.shape
     N = w.shape[0]
@@ -255,6 +271,7 @@ def linear(x, w, bias=None, *, out_dtype=None, out=None, act=CB_ACT_NONE, residu
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha, d.act = alpha, act
+    _set_out2(d, out2)
     _gemm(d, "cb_gemm(linear)")
     return out
 
@@ -279,7 +296,7 @@ def linear_dgrad(dy, w, *, out_dtype=None, out=None, residual=None, alpha=1.0):
 
 
 def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1), out_dtype=None, out=None,
-           residual=None, bias_per_image=False, ldbias=None, act=CB_ACT_NONE, cout_rows=None):
+           residual=None, bias_per_image=False, ldbias=None, act=CB_ACT_NONE, cout_rows=None, out2=None):
     """Implicit-GEMM convolution on an NHWC activation matrix.
 
     x: [geo.rows][Cin]; wpack: [k*k*cout_rows][Cin] from pack_conv_weight; pad=(top,bottom,left,right).
@@ -310,6 +327,7 @@ def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha, d.act = 1.0, act
+    _set_out2(d, out2)
     _gemm(d, "cb_gemm(conv2d)")
     return out, ogeo
 
@@ -411,14 +429,14 @@ def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype
 
 
 def groupnorm_bwd(dy, x, geo, gamma, beta, stats, *, groups=32, silu=False, dx=None, accumulate=False,
-                  dx_dtype=torch.float32):
+                  dx_dtype=torch.float32, dx_lp=None):
     C = x.shape[1]
     if dx is None:
         dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
         accumulate = False
     ws = _gn_workspace(x.device)
     _lib.check(_L().cb_groupnorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(gamma), _p(beta), _p(stats.mean),
-                                     _p(stats.rstd), _p(dx), _dt(dx), geo.n, geo.hw, C, groups, _gn_flags(silu),
+                                     _p(stats.rstd), _p(dx), _dt(dx), _p(dx_lp), geo.n, geo.hw, C, groups, _gn_flags(silu),
                                      1 if accumulate else 0, _p(ws), _st()), "cb_groupnorm_bwd")
     return dx
 

@@ -254,10 +254,12 @@ class UNetEngine:
                 ds *= 2
         self.middle = [res("middle_block.0.", ch, ch), xf("middle_block.1.", ch), res("middle_block.2.", ch, ch)]
         self.output_blocks = []
+        self.cat_split = []      # (channels of h, channels of the popped skip) per output block
         idx = 0
         for level, m in list(enumerate(mult))[::-1]:
             for i in range(nres + 1):
                 ich = chans.pop()
+                self.cat_split.append((ch, ich))
                 layers = [res(f"output_blocks.{idx}.0.", ch + ich, mc * m)]
                 ch = mc * m
                 if ds in attn_res:
@@ -283,7 +285,7 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------
-    def _res_fwd(self, w, x, geo, emb_all, tape):
+    def _res_fwd(self, w, x, geo, emb_all, tape, out=None, out2=None):
         cout = w["cout"]
         a16, st1 = ops.groupnorm(x, geo, w["g1"], w["b1"], eps=1e-5, silu=True, out_dtype=self.dt)
         bias1 = emb_all[:, w["emb_off"]: w["emb_off"] + cout]
@@ -294,14 +296,17 @@ class UNetEngine:
             resid = x
         else:
             resid = ops.linear(ops.cast(x, self.dt), w["ws"], w["bs"], out_dtype=torch.float32)
-        out, _ = ops.conv2d(b16, geo, w["w2"], cout, bias=w["bias2"], out_dtype=torch.float32, residual=resid)
+        out, _ = ops.conv2d(b16, geo, w["w2"], cout, bias=w["bias2"], out_dtype=torch.float32, residual=resid, out=out,
+                            out2=out2)
         if tape is not None:
             tape.append(("res", w, geo, x, st1, h16, st2))
         return out
 
-    def _res_bwd(self, rec, dout):
+    def _res_bwd(self, rec, dout, dout16=None):
+        """dout16: 16-bit copy of dout when the producing GroupNorm-backward kernel emitted one (else cast here)."""
         _, w, geo, x, st1, h16, st2 = rec
-        dout16 = ops.cast(dout, self.dt)
+        if dout16 is None:
+            dout16 = ops.cast(dout, self.dt)
         db16, _ = ops.conv2d_dgrad(dout16, geo, w["w2"], w["cout"])
         dh16 = ops.groupnorm_bwd(db16, h16, geo, w["g2"], w["b2"], st2, silu=True, dx_dtype=self.dt)
         da16, _ = ops.conv2d_dgrad(dh16, geo, w["w1"], w["cin"])
@@ -312,7 +317,7 @@ class UNetEngine:
         ops.groupnorm_bwd(da16, x, geo, w["g1"], w["b1"], st1, silu=True, dx=dx, accumulate=True)
         return dx
 
-    def _xf_fwd(self, w, x, geo, kv_all, tape):
+    def _xf_fwd(self, w, x, geo, kv_all, tape, out=None, out2=None):
         c, dh, H = w["c"], w["dh"], self.heads
         B, nq = geo.n, geo.hw
         scale = dh ** -0.5
@@ -339,7 +344,7 @@ class UNetEngine:
         g16 = ops.linear(l3, w["wff1"], w["bff1"])
         u16 = ops.geglu(g16)
         h3 = ops.linear(u16, w["wff2"], w["bff2"], out_dtype=self.dt, residual=h2)
-        out = ops.linear(h3, w["wpo"], w["bpo"], out_dtype=torch.float32, residual=x)
+        out = ops.linear(h3, w["wpo"], w["bpo"], out_dtype=torch.float32, residual=x, out=out, out2=out2)
         if tape is not None:
             tape.append(("xf", w, geo, x, stn, h0, s1, qkv, P1, h1, s2, q2, kv2, P2, h2, s3, g16, nk))
         return out
@@ -354,6 +359,7 @@ class UNetEngine:
         scale = dh ** -0.5
         dx = dout
         dr = ops.linear_dgrad(ops.cast(dout, self.dt), w["wpo"], out_dtype=torch.float32)  # d h3 (fp32 running)
+        dx16 = torch.empty(dout.shape, dtype=self.dt, device=self.dev) if to_input else None
         # feed-forward
         du = ops.linear_dgrad(ops.cast(dr, self.dt), w["wff2"])
         dg = ops.geglu_bwd(du, g16)
@@ -379,7 +385,8 @@ class UNetEngine:
         ops.layernorm_bwd(dl1, h0, w["ln1g"], s1, dx=dr, accumulate=True, dx_lp=dr16)
         # proj_in + group norm
         dn = ops.linear_dgrad(dr16, w["wpi"])
-        ops.groupnorm_bwd(dn, x, geo, w["gn"], w["bn"], stn, silu=False, dx=dx, accumulate=True)
+        ops.groupnorm_bwd(dn, x, geo, w["gn"], w["bn"], stn, silu=False, dx=dx, accumulate=True, dx_lp=dx16)
+        self._last_dx16 = dx16      # 16-bit copy of the returned gradient (the next ResBlock's dgrad operand)
         return dx
 
     def _sideq_get(self):
@@ -389,9 +396,9 @@ class UNetEngine:
             self._sideq = _SideQueue(self.dev, lane=4)
         return self._sideq
 
-    def _down_fwd(self, w, x, geo, tape):
+    def _down_fwd(self, w, x, geo, tape, out=None, out2=None):
         out, ogeo = ops.conv2d(ops.cast(x, self.dt), geo, w["w"], w["c"], bias=w["b"], stride=2,
-                               out_dtype=torch.float32)
+                               out_dtype=torch.float32, out=out, out2=out2)
         if tape is not None:
             tape.append(("down", w, geo, ogeo))
         return out, ogeo
@@ -402,9 +409,9 @@ class UNetEngine:
         dx, _ = ops.conv2d_dgrad(z, zgeo, w["w"], w["c"], out_dtype=torch.float32)
         return dx
 
-    def _up_fwd(self, w, x, geo, tape):
+    def _up_fwd(self, w, x, geo, tape, out=None, out2=None):
         u, ugeo = ops.upsample2x(ops.cast(x, self.dt), geo)
-        out, _ = ops.conv2d(u, ugeo, w["w"], w["c"], bias=w["b"], out_dtype=torch.float32)
+        out, _ = ops.conv2d(u, ugeo, w["w"], w["c"], bias=w["b"], out_dtype=torch.float32, out=out, out2=out2)
         if tape is not None:
             tape.append(("up", w, geo, ugeo))
         return out, ugeo
@@ -414,17 +421,26 @@ class UNetEngine:
         du, _ = ops.conv2d_dgrad(ops.cast(dout, self.dt), ugeo, w["w"], w["c"])
         return ops.upsample2x_bwd(du, geo, dx_dtype=torch.float32)
 
-    def _run_layers(self, layers, h, geo, emb_all, kv_all, tape):
-        for w in layers:
+    def _run_layers(self, layers, h, geo, emb_all, kv_all, tape, out=None, out2=None):
+        """out / out2: destinations of the LAST layer's result (see forward: skip-connection concat without copies);
+        they are callables geo -> 2-D view because the geometry of an up / down layer's output is only known here."""
+        for i, w in enumerate(layers):
             k = w["kind"]
-            if k == "res":
-                h = self._res_fwd(w, h, geo, emb_all, tape)
-            elif k == "xf":
-                h = self._xf_fwd(w, h, geo, kv_all, tape)
-            elif k == "down":
-                h, geo = self._down_fwd(w, h, geo, tape)
+            last = i == len(layers) - 1
+            if k in ("down", "up"):
+                ogeo = ops.Geo(geo.n, geo.h // 2, geo.w // 2) if k == "down" else ops.Geo(geo.n, 2 * geo.h, 2 * geo.w)
             else:
-                h, geo = self._up_fwd(w, h, geo, tape)
+                ogeo = geo
+            o = out(ogeo) if (last and out is not None) else None
+            o2 = out2(ogeo) if (last and out2 is not None) else None
+            if k == "res":
+                h = self._res_fwd(w, h, geo, emb_all, tape, out=o, out2=o2)
+            elif k == "xf":
+                h = self._xf_fwd(w, h, geo, kv_all, tape, out=o, out2=o2)
+            elif k == "down":
+                h, geo = self._down_fwd(w, h, geo, tape, out=o, out2=o2)
+            else:
+                h, geo = self._up_fwd(w, h, geo, tape, out=o, out2=o2)
         return h, geo
 
     def forward(self, x, t, context, need_grad=True, context_ready=None):
@@ -452,23 +468,40 @@ class UNetEngine:
                 kv_state["kv"] = ops.linear(ctx16, self.wkv_all)
             return kv_state["kv"]
         x16, geo = ops.nchw_to_nhwc(x.contiguous(), self.in_pad, self.dt)
-        h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32)
-        hs = [(h, geo)]
-        for layers in self.input_blocks:
-            h, geo = self._run_layers(layers, h, geo, emb_all, kv_all, tape)
+        # Skip connections without copies (torch.cat([h, hs.pop()], dim=1), openaimodel.py:737-739): the concat buffer of
+        # every output block is allocated up front; the GEMM epilogue that produces a skip activation also stores it into
+        # columns [c1, c1+c2) of the block that will pop it (second destination), and the epilogue that produces the
+        # previous block's result writes columns [0, c1) directly.
+        n_out = len(self.output_blocks)
+        cats = [None] * n_out
+
+        def cat_buf(k, g):
+            if cats[k] is None:
+                c1, c2 = self.cat_split[k]
+                cats[k] = torch.empty(g.rows, c1 + c2, dtype=torch.float32, device=self.dev)
+            return cats[k]
+
+        def skip_dst(m):          # hs[m] is popped by output block n_out-1-m
+            k = n_out - 1 - m
+            return lambda g: cat_buf(k, g)[:, self.cat_split[k][0]:]
+
+        def head_dst(k):          # the tensor entering output block k lands in columns [0, c1) of its concat buffer
+            return lambda g: cat_buf(k, g)[:, : self.cat_split[k][0]]
+
+        h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32, out2=skip_dst(0)(geo))
+        for m, layers in enumerate(self.input_blocks, start=1):
+            h, geo = self._run_layers(layers, h, geo, emb_all, kv_all, tape, out2=skip_dst(m))
             if tape is not None:
                 tape.append(("push",))
-            hs.append((h, geo))
-        h, geo = self._run_layers(self.middle, h, geo, emb_all, kv_all, tape)
-        for layers in self.output_blocks:
-            skip, _ = hs.pop()
-            c1, c2 = h.shape[1], skip.shape[1]
-            cat = torch.empty(geo.rows, c1 + c2, dtype=torch.float32, device=self.dev)
-            ops.axpby(h, 1.0, out=cat[:, :c1])
-            ops.axpby(skip, 1.0, out=cat[:, c1:])
+        h, geo = self._run_layers(self.middle, h, geo, emb_all, kv_all, tape, out=head_dst(0))
+        for k, layers in enumerate(self.output_blocks):
+            c1, c2 = self.cat_split[k]
+            cat = cats[k]
+            assert cat is not None and cat.shape[0] == geo.rows
             if tape is not None:
                 tape.append(("cat", c1, c2))
-            h, geo = self._run_layers(layers, cat, geo, emb_all, kv_all, tape)
+            h, geo = self._run_layers(layers, cat, geo, emb_all, kv_all, tape,
+                                      out=head_dst(k + 1) if k + 1 < n_out else None)
         a16, sto = ops.groupnorm(h, geo, self.out_g, self.out_b, eps=1e-5, silu=True, out_dtype=self.dt)
         y, _ = ops.conv2d(a16, geo, self.out_w, self.out_ch, bias=self.out_bias, out_dtype=torch.float32,
                           cout_rows=self.out_pad)
@@ -493,14 +526,16 @@ class UNetEngine:
         d32, _ = ops.nchw_to_nhwc(d_eps.contiguous(), self.out_pad, torch.float32)
         dy16 = ops.cast(d32, self.dt, scale=S)
         da16, _ = ops.conv2d_dgrad(dy16, geo, self.out_w, self.mc, cout_rows=self.out_pad)
-        dh = ops.groupnorm_bwd(da16, h_head, geo, self.out_g, self.out_b, sto, silu=True, dx_dtype=torch.float32)
+        dh16 = torch.empty(h_head.shape, dtype=self.dt, device=self.dev)
+        dh = ops.groupnorm_bwd(da16, h_head, geo, self.out_g, self.out_b, sto, silu=True, dx_dtype=torch.float32, dx_lp=dh16)
         dskips = []
         first_xf = next((i for i, r in enumerate(tape) if r[0] == "xf"), -1)
         while tape:
             rec = tape.pop()
             k = rec[0]
             if k == "res":
-                dh = self._res_bwd(rec, dh)
+                dh = self._res_bwd(rec, dh, dh16)
+                dh16 = None
             elif k == "xf":
                 if len(tape) == first_xf:
                     # first transformer block in forward order: nothing before it (stem, ResBlock, its own self-attention)
@@ -509,18 +544,20 @@ class UNetEngine:
                     tape.clear()
                     break
                 dh = self._xf_bwd(rec, dh, dkv_all)
+                dh16 = self._last_dx16
             elif k == "down":
-                dh = self._down_bwd(rec, dh)
+                dh, dh16 = self._down_bwd(rec, dh), None
             elif k == "up":
-                dh = self._up_bwd(rec, dh)
+                dh, dh16 = self._up_bwd(rec, dh), None
             elif k == "cat":
                 _, c1, c2 = rec
                 dskips.append(dh[:, c1:])
-                dh = ops.axpby(dh[:, :c1], 1.0)
+                dh, dh16 = ops.axpby(dh[:, :c1], 1.0), None
             elif k == "push":
                 # this activation also fed a skip connection: add that branch's gradient
                 dsk = dskips.pop()
                 ops.axpby(dh, 1.0, dsk, 1.0, out=dh)
+                dh16 = None
         if self._sideq is not None:
             self._sideq.join()
         # d(context) = [dK | dV of every block] . [W_k ; W_v of every block]: one GEMM with K = sum 2C

@@ -138,13 +138,22 @@ typedef struct cb_gemm_desc {
      * {start, setup done, first stage full, last MMA issued, accumulator ready, exit, 4th stage full, -}. */
     void* debug_timeline;
 
-    /* tuning overrides, 0 = the library's cost model: tile width (64 / 128 / 160; 160 only with K-major B) and the
+    /* tuning overrides, 0 = the library's cost model: tile width (64 / 128 / 160 / 256; 160 only with K-major B) and the
      * number of split-K slices (1 = no split; ignored when the workspace cannot hold it).  The host autotuner
      * (celebbasis_b200/ops.py) times the candidates once per shape and passes the winner here. */
     int32_t tile_n;
     int32_t splits;
     int32_t stages;      /* 0 = auto, 3 = 3-stage ring / 2 CTAs per SM, 6 = 6-stage ring / 1 CTA per SM */
     int32_t reserved0;
+
+    /* second destination (optional, batch == 1, not transposed): the same epilogue value is also written to
+     * D2[row][col] (row pitch ldd2 elements, dtype d2_dtype).  Used to place a UNet skip activation straight into the
+     * concat buffer of the output block that will consume it (torch.cat([h, hs.pop()], dim=1), openaimodel.py:737-739)
+     * and for 16-bit copies of fp32 results. */
+    void* D2;
+    int64_t ldd2;
+    int32_t d2_dtype;
+    int32_t reserved1;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);
@@ -161,13 +170,15 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
  * The *_bwd entry points are the activation gradients torch.autograd computes in the reference
  * (SURVEY.md §8 a29); accumulate != 0 adds into dx (residual-branch join).
  * ------------------------------------------------------------------------------------------- */
+/* cb_groupnorm_bwd: dx_lp (optional, dtype of dy): the result is also written as a 16-bit copy -- the operand of the
+ * dgrad GEMM that consumes dx next (saves a cast launch per ResBlock / transformer block of the backward pass). */
 #define CB_GN_NO_GRID_BARRIER 2 /* OR into act_silu: force the statistics + apply kernel pair (no grid-wide spin barrier) */
 int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
                      int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
                      double* ws, void* stream);
 int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
-                     const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, int N, int HW,
-                     int C, int G, int act_silu, int accumulate, double* ws, void* stream);
+                     const float* beta, const float* mean, const float* rstd, void* dx, int dx_dtype, void* dx_lp, int N,
+                     int HW, int C, int G, int act_silu, int accumulate, double* ws, void* stream);
 int cb_layernorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta, int M,
                      int C, float eps, float* mean_out, float* rstd_out, void* stream);
 /* dx_lp (optional): a second copy of the final dx in dy's 16-bit dtype, for the GEMM that consumes it next */

@@ -362,3 +362,110 @@ def test_flash_attention_fwd(dev, nq, nk, dh, heads, images, causal, want_p):
         ldp = (nk + 7) // 8 * 8
         pr = P.view(images, heads, nq, ldp)
         assert rel(pr[..., :nk], att) < 3e-3 and float(pr[..., nk:].abs().max() if ldp > nk else 0) == 0
+
+
+# ---------------------------------------------------------------------------------------------------- round-2 additions
+@pytest.mark.parametrize("splits", [0, 4])
+def test_gemm_second_destination_and_strided_out(dev, splits):
+    """cb_gemm D2: the epilogue value is also stored at a second address with its own dtype / row pitch (the UNet's
+    skip-connection concat without copies) -- fast path, ragged-N slow path and the split-K last-CTA path."""
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import GemmDesc
+    for (M, N, K) in ((256, 320, 640), (200, 72, 128)):
+        x, w = rnd(M, K), rnd(N, K)
+        bias = rnd(N, dtype=torch.float32)
+        res = rnd(M, N, dtype=torch.float32)
+        cat = torch.full((M, N + 96), -7.0, dtype=torch.float32, device="cuda")
+        cat16 = torch.full((M, 2 * N), -7.0, dtype=torch.float16, device="cuda")
+        ref = x.float() @ w.float().t() + bias + res
+        if splits:
+            # force split-K through the descriptor override
+            orig = ops._gemm
+
+            def forced(d, what):
+                d.splits = splits
+                return orig(d, what)
+            ops._gemm = forced
+        try:
+            y = ops.linear(x, w, bias, out=cat[:, 96:], residual=res, out2=cat16[:, N:])
+        finally:
+            if splits:
+                ops._gemm = orig
+        assert rel(cat[:, 96:], ref) < 2e-3 and rel(cat16[:, N:], ref) < 2e-3
+        assert float((cat[:, :96] + 7).abs().max()) == 0 and float((cat16[:, :N] + 7).abs().max()) == 0
+    # conv with a second destination
+    g = ops.Geo(2, 16, 16)
+    xi = rnd(g.rows, 64)
+    wc = torch.randn(128, 64, 3, 3, device="cuda") * 0.05
+    pack = ops.pack_conv_weight(wc, torch.float16)
+    d2 = torch.zeros(g.rows, 128 + 32, dtype=torch.float32, device="cuda")
+    y, _ = ops.conv2d(xi, g, pack, 128, out_dtype=torch.float16, out2=d2[:, 32:])
+    refc = F.conv2d(xi.float().view(2, 16, 16, 64).permute(0, 3, 1, 2), wc.half().float(), padding=1)
+    refc = refc.permute(0, 2, 3, 1).reshape(g.rows, 128)
+    assert rel(y, refc) < 2e-3 and rel(d2[:, 32:], refc) < 2e-3 and float(d2[:, :32].abs().max()) == 0
+
+
+def test_gemm_tile256(dev):
+    """128x256 output tiles (tile_n = 256, 4-stage ring): K-major and MN-major B, conv and ragged N."""
+    from celebbasis_b200 import ops
+    orig = ops._gemm
+
+    def forced(d, what):
+        d.tile_n = 256
+        return orig(d, what)
+    ops._gemm = forced
+    try:
+        x, w = rnd(1024, 640), rnd(1280, 640)
+        y = ops.linear(x, w, out_dtype=torch.float32)
+        assert rel(y, x.float() @ w.float().t()) < 2e-3
+        dy = rnd(1024, 1280)
+        dx = ops.linear_dgrad(dy, w, out_dtype=torch.float32)          # B read MN-major
+        assert rel(dx, dy.float() @ w.float()) < 2e-3
+        x2, w2 = rnd(512, 320), rnd(600, 320)                          # N = 600: 256 + 256 + 88
+        y2 = ops.linear(x2, w2, out_dtype=torch.float32)
+        assert rel(y2, x2.float() @ w2.float().t()) < 2e-3
+        g = ops.Geo(1, 32, 32)
+        xi = rnd(g.rows, 320)
+        wc = torch.randn(512, 320, 3, 3, device="cuda") * 0.02
+        yc, _ = ops.conv2d(xi, g, ops.pack_conv_weight(wc, torch.float16), 512, out_dtype=torch.float32)
+        refc = F.conv2d(xi.float().view(1, 32, 32, 320).permute(0, 3, 1, 2), wc.half().float(), padding=1)
+        assert rel(yc, refc.permute(0, 2, 3, 1).reshape(g.rows, 512)) < 2e-3
+    finally:
+        ops._gemm = orig
+
+
+def test_groupnorm_bwd_emits_16bit_copy(dev):
+    from celebbasis_b200 import ops
+    for (hw, c) in ((32, 640), (128, 128)):          # fused single-kernel path / streaming two-kernel path
+        geo = ops.Geo(1, hw, hw)
+        x = rnd(geo.rows, c, dtype=torch.float32, scale=2.0)
+        gm, bt = rnd(c, dtype=torch.float32) * 0.1 + 1, rnd(c, dtype=torch.float32) * 0.1
+        dy = rnd(geo.rows, c)
+        _, st = ops.groupnorm(x, geo, gm, bt, silu=True)
+        dx = ops.groupnorm_bwd(dy, x, geo, gm, bt, st, silu=True)
+        lp = torch.full((geo.rows, c), float("nan"), dtype=torch.float16, device="cuda")
+        dx2 = ops.groupnorm_bwd(dy, x, geo, gm, bt, st, silu=True, dx_lp=lp)
+        assert rel(dx2, dx) < 1e-5 and rel(lp, dx) < 1e-3
+
+
+def test_ema_rows_and_prep_kernels(dev):
+    from celebbasis_b200 import ops
+    table = rnd(10, 2 * 768, dtype=torch.float32)
+    t0 = table.clone()
+    src = rnd(3, 2 * 768, dtype=torch.float32)
+    idx = torch.tensor([[4, 4], [7, 7], [4, 4]], device="cuda")        # identity 4 appears twice: batch order matters
+    ops.ema_rows(table, idx, src, 0.99)
+    exp = t0.clone()
+    for b, i in enumerate([4, 7, 4]):
+        exp[i] = 0.99 * exp[i] + 0.01 * src[b]
+    assert torch.allclose(table, exp, atol=1e-6)
+    idx_bad = torch.tensor([[11, 0]], device="cuda")                    # out of range: skipped, like the reference's `if`
+    ops.ema_rows(table, idx_bad, src[:1].contiguous(), 0.5)
+    assert torch.allclose(table, exp, atol=1e-6)
+    w = torch.randn(24, 10, 3, 3)
+    sc = torch.rand(24) + 0.5
+    pk = ops.pack_conv_weight(w, torch.float16, cin_pad=16, cout_pad=32, out_scale=sc, device="cuda")
+    ref = torch.zeros(9, 32, 16)
+    ref[:, :24, :10] = (w * sc.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(9, 24, 10)
+    assert rel(pk.float().cpu(), ref.view(9 * 32, 16)) < 1e-3
+    assert rel(ops.to_device(torch.arange(7.0), "cuda", torch.float16).cpu(), torch.arange(7.0)) == 0
