@@ -95,7 +95,7 @@ def _autotune(d, key):
     taps = d.kh * d.kw if d.conv else 1
     kiters = taps * ((d.K + 63) // 64)
     bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
-    if d.N >= 256 and d.a_major != CB_MAJOR_MN and M >= 1024:
+    if d.N >= 256 and d.a_major != CB_MAJOR_MN and M >= 1024 and os.environ.get("CB_GEMM_TILE256", "1") != "0":
         bns = bns + [256]          # 128x256 tiles (4-stage ring, one CTA per SM): fewer operand bytes per flop for large GEMMs
     cands = [(0, 0, 0)]
     for bn in bns:

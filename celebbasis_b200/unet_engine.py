@@ -14,6 +14,8 @@ but runs it as an explicit tape of kernel launches:
     (SURVEY.md §8 a29): activation gradients down to d(context); no weight gradients, no d(emb).
     Gradients are carried fp16 with a static loss scale; residual-stream gradients are fp32.
 """
+import os
+
 import torch
 
 from . import ops
@@ -147,6 +149,7 @@ class _SideQueue:
 
 class UNetEngine:
     SIDE_DKDV = True     # cross-attention dK / dV GEMMs on a side stream (they only feed d(context), assembled last)
+    CAT_INPLACE = os.environ.get("CB_UNET_CAT_INPLACE", "1") != "0"   # skip-connection concat through GEMM epilogues
 
     def __init__(self, cfg, state_dict, device, dtype=torch.float16, loss_scale=1024.0):
         self.cfg = dict(cfg)
@@ -488,20 +491,30 @@ class UNetEngine:
         def head_dst(k):          # the tensor entering output block k lands in columns [0, c1) of its concat buffer
             return lambda g: cat_buf(k, g)[:, : self.cat_split[k][0]]
 
-        h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32, out2=skip_dst(0)(geo))
+        inplace = self.CAT_INPLACE
+        h, _ = ops.conv2d(x16, geo, self.stem_w, self.mc, bias=self.stem_b, out_dtype=torch.float32,
+                          out2=skip_dst(0)(geo) if inplace else None)
+        hs = [h]
         for m, layers in enumerate(self.input_blocks, start=1):
-            h, geo = self._run_layers(layers, h, geo, emb_all, kv_all, tape, out2=skip_dst(m))
+            h, geo = self._run_layers(layers, h, geo, emb_all, kv_all, tape, out2=skip_dst(m) if inplace else None)
             if tape is not None:
                 tape.append(("push",))
-        h, geo = self._run_layers(self.middle, h, geo, emb_all, kv_all, tape, out=head_dst(0))
+            hs.append(h)
+        h, geo = self._run_layers(self.middle, h, geo, emb_all, kv_all, tape, out=head_dst(0) if inplace else None)
         for k, layers in enumerate(self.output_blocks):
             c1, c2 = self.cat_split[k]
-            cat = cats[k]
-            assert cat is not None and cat.shape[0] == geo.rows
+            skip = hs.pop()
+            if inplace:
+                cat = cats[k]
+                assert cat is not None and cat.shape[0] == geo.rows
+            else:
+                cat = torch.empty(geo.rows, c1 + c2, dtype=torch.float32, device=self.dev)
+                ops.axpby(h, 1.0, out=cat[:, :c1])
+                ops.axpby(skip, 1.0, out=cat[:, c1:])
             if tape is not None:
                 tape.append(("cat", c1, c2))
             h, geo = self._run_layers(layers, cat, geo, emb_all, kv_all, tape,
-                                      out=head_dst(k + 1) if k + 1 < n_out else None)
+                                      out=head_dst(k + 1) if (inplace and k + 1 < n_out) else None)
         a16, sto = ops.groupnorm(h, geo, self.out_g, self.out_b, eps=1e-5, silu=True, out_dtype=self.dt)
         y, _ = ops.conv2d(a16, geo, self.out_w, self.out_ch, bias=self.out_bias, out_dtype=torch.float32,
                           cout_rows=self.out_pad)
