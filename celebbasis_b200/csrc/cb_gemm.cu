@@ -607,6 +607,207 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile with ONE
+// tcgen05.mma stream issued by the leader CTA.  Each CTA stages its own 128 rows of A and HALF of the B tile
+// (BN/2 columns); the MMA reads both halves, so per output element each SM pulls half as many B bytes out of
+// L2 as the single-CTA kernel -- the L2->SM ingest limit (~42 B/clk/SM) is what caps 128 x BN tiles at ~50 %
+// of the tensor peak on the large-M GEMMs (VAE 512^2/256^2 convolutions, CFG-batched inference).
+//   * TMA loads of both CTAs credit their bytes to the LEADER's full[] barrier (.cta_group::2, peer bit cleared);
+//   * tcgen05.commit.multicast frees the stage in both CTAs and publishes the accumulator to both epilogues;
+//   * each CTA's epilogue reads its own 128 TMEM lanes.  No split-K in this variant.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int kStages>
+struct PairCfg {
+    static constexpr int kTmemCols = BN <= 128 ? 128 : 256;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = (BN / 2) * BK * 2;          // this CTA's half of the B tile
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, bool B_MN, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GemmParams p) {
+    using Cfg = PairCfg<BN, kStages>;
+    constexpr int HN = BN / 2;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m_tile = blockIdx.x;                 // the pair covers m tiles (2j, 2j+1)
+    const int n0 = blockIdx.y * BN;
+    const int bz = blockIdx.z;
+    const int zi = bz % p.batch_inner;
+    const int zo = bz / p.batch_inner;
+
+    int m0 = 0, ow0 = 0, oh0 = 0, img0 = 0;
+    if (p.conv) {
+        const int tw = m_tile % p.tiles_w;
+        const int th = (m_tile / p.tiles_w) % p.tiles_h;
+        const int ti = m_tile / (p.tiles_w * p.tiles_h);
+        ow0 = tw * p.box_w;
+        oh0 = th * p.box_h;
+        img0 = ti * p.box_i;
+    } else {
+        m0 = m_tile * BM;
+    }
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();            // the peer's barriers exist before any remote arrive / complete_tx can reach them
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_sync();
+
+    const int kiters = p.taps * p.kchunks;
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (leader) mbar_arrive_expect_tx(full_bar(s), 2u * (p.a_bytes + (unsigned)Cfg::kBBytes));
+                const int tap = it / p.kchunks;
+                const int kc = it - tap * p.kchunks;
+                const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
+                const uint32_t b_dst = a_dst + Cfg::kABytes;
+                const int tap_b = p.flip_taps ? (p.taps - 1 - tap) : tap;
+                if (p.conv) {
+                    const int r = tap / p.kw, sx = tap - r * p.kw;
+                    tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, ow0 * p.stride + sx - p.pad_left,
+                                     oh0 * p.stride + r - p.pad_top, img0);
+                } else {
+                    tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, m0, zi, zo);
+                }
+                const int nh = n0 + (int)rank * HN;          // this CTA's half of the B tile
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < HN / 64; ++j)
+                        tma_load_4d_pair(b_dst + j * 8192, &tmB, full_bar(s), nh + j * 64,
+                                         tap_b * p.b_tap_rows + kc * BK, zi, zo);
+                } else {
+                    tma_load_4d_pair(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + nh, zi, zo);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
+                const uint32_t b_src = a_src + Cfg::kABytes;
+                const int kc = it % p.kchunks;
+                const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : (BK / 16);
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t adesc = umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
+                    const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
+                                                : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
+                    umma_f16_pair(tmem_base, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit_pair(empty_bar(s));        // frees this stage in BOTH CTAs once the MMAs above retire
+            }
+            umma_commit_pair(tmem_full_bar);
+        }
+    } else {
+        // ===================== epilogue (each CTA: its own 128 rows) =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        bool row_valid;
+        long long grow;
+        if (p.conv) {
+            const int per_img = p.box_h * p.box_w;
+            const int bi = r / per_img;
+            const int rem = r - bi * per_img;
+            const int bh = rem / p.box_w;
+            const int bw = rem - bh * p.box_w;
+            const int img = img0 + bi, oh = oh0 + bh, ow = ow0 + bw;
+            row_valid = (bi < p.box_i) && (img < p.img_n) && (oh < p.out_h) && (ow < p.out_w);
+            grow = ((long long)img * p.out_h + oh) * p.out_w + ow;
+        } else {
+            grow = m0 + r;
+            row_valid = grow < p.M;
+        }
+        const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
+        const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
+        const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
+        const int ncols_tile = min(BN, p.N - n0);
+        __shared__ __align__(16) float s_bias[BN + 8];
+        const float* sb = nullptr;
+        if (p.bias) {
+            const long long tile_row0 = p.conv ? (((long long)img0 * p.out_h + oh0) * p.out_w + ow0) : (long long)m0;
+            const long long brow0 = p.bias_row_div > 0 ? tile_row0 / p.bias_row_div : 0;
+            for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = i < ncols_tile ? p.bias[brow0 * p.ldbias + n0 + i] : 0.f;
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (brow == brow0) sb = s_bias;
+        }
+        const bool r_fast = p.R && p.vec_ok && !p.d_transposed && row_valid;
+        const long long r_row = r_off + grow * p.ldr + n0;
+        ResidualChunk rc_cur, rc_next;
+        if (r_fast && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c * 32 < ncols_tile; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32(trow + c * 32, acc);
+            const bool pre = r_fast && ncols_tile - c * 32 >= 32;
+            if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
+            tmem_ld_wait();
+            if (row_valid && p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
+                epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+            } else if (row_valid) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                    if (nc > 0) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
+                        epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                    }
+                }
+            }
+            rc_cur = rc_next;
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();            // both CTAs are done with TMEM (and with each other's shared memory) before it is freed
+    if (warp == 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -676,6 +877,22 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
         if (force == 6 || ctas <= device_sm_count()) return launch_s<BN, A_MN, B_MN, 6>(tA, tB, p, grid, st);
         return launch_s<BN, A_MN, B_MN, 3>(tA, tB, p, grid, st);
     }
+}
+
+template <int BN, bool B_MN>
+static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    constexpr int kSt = BN == 256 ? 6 : 6;
+    using Cfg = PairCfg<BN, kSt>;
+    static bool attr_done = false;
+    auto kern = cb_gemm_pair_kernel<BN, B_MN, kSt>;
+    if (!attr_done) {
+        CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_done = true;
+    }
+    CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
+    CB_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
 }
 
 // Measured on B200 (tools/gemm_timeline.py): one SM pulls ~80 GB/s of operand tiles out of L2, i.e. a k-iteration of a
@@ -815,8 +1032,11 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         }
     }
 
-    const int BN = pick_bn(d, m_tiles, p.taps * p.kchunks);
-    p.b_bytes = (unsigned)BN * BK * es;
+    // CTA-pair variant on request (desc.cta_pair = 1; the host autotuner decides): 256 x BN tiles, K-major A, no split-K
+    const bool pair = d.cta_pair == 1 && !a_mn && m_tiles >= 2 && d.N >= 64;
+    const int BN = pair ? ((d.tile_n == 128 || d.N <= 128) ? 128 : 256) : pick_bn(d, m_tiles, p.taps * p.kchunks);
+    const int b_box_rows = pair ? BN / 2 : BN;
+    p.b_bytes = (unsigned)b_box_rows * BK * es;
     {
         const uint64_t brows_total = (uint64_t)(d.conv ? (int64_t)p.taps * d.b_tap_rows : (b_mn ? d.K : d.N));
         const uint64_t dflt = (uint64_t)(d.ldb * (int64_t)brows_total);
@@ -832,7 +1052,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         } else {
             uint64_t dims[4] = {(uint64_t)d.K, brows_total, (uint64_t)b_in, (uint64_t)b_out};
             uint64_t strides[3] = {(uint64_t)d.ldb * es, bs * es, bs2 * es};
-            uint32_t box[4] = {BK, (uint32_t)BN, 1, 1};
+            uint32_t box[4] = {BK, (uint32_t)b_box_rows, 1, 1};
             int rc = make_tmap(&tB, d.ab_dtype, 4, d.B, dims, strides, box, estr);
             if (rc) return rc;
         }
@@ -869,7 +1089,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         static const int mode = getenv("CB_GEMM_DBG_MODE") ? atoi(getenv("CB_GEMM_DBG_MODE")) : 0;
         p.dbg_mode = mode;
     }
-    p.idesc = umma_idesc_f16(BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
+    p.idesc = umma_idesc_f16(pair ? 2 * BM : BM, BN, d.ab_dtype == CB_BF16, a_mn, b_mn);
     {
         const int des = d.d_dtype == CB_F32 ? 4 : 2;
         bool ok = ((reinterpret_cast<uintptr_t>(d.D) & 15u) == 0) && ((d.ldd * des) % 16 == 0) &&
@@ -927,8 +1147,15 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
             }
         }
     }
-    dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)(d.batch * p.splits));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (pair) {
+        p.splits = 1;
+        p.kiters_per_split = p.taps * p.kchunks;
+        dim3 pgrid((unsigned)(2 * ceil_div(m_tiles, 2)), (unsigned)ceil_div(d.N, BN), (unsigned)d.batch);
+        if (b_mn) return BN == 128 ? launch_pair<128, true>(tA, tB, p, pgrid, st) : launch_pair<256, true>(tA, tB, p, pgrid, st);
+        return BN == 128 ? launch_pair<128, false>(tA, tB, p, pgrid, st) : launch_pair<256, false>(tA, tB, p, pgrid, st);
+    }
+    dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)(d.batch * p.splits));
     if (!a_mn && !b_mn) {
         if (BN == 64) return launch<64, false, false>(tA, tB, p, grid, st);
         if (BN == 128) return launch<128, false, false>(tA, tB, p, grid, st);

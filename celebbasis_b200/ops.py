@@ -71,6 +71,7 @@ def _splitk_workspace(device):
 # shape times the candidates on the device (CUDA-graph replay of 8 launches each, output redirected to scratch) and
 # later launches -- including the ones captured into the step graph -- pass the winner in desc.tile_n / desc.splits.
 AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
+CTA_PAIR = os.environ.get("CB_GEMM_CTA_PAIR", "1") != "0"      # let the autotuner try the tcgen05 cta_group::2 kernel
 _TUNE = {}
 _tune_scratch = {}
 _tune_stream = {}
@@ -97,18 +98,23 @@ def _autotune(d, key):
     bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
     if d.N >= 256 and d.a_major != CB_MAJOR_MN and M >= 1024 and os.environ.get("CB_GEMM_TILE256", "1") != "0":
         bns = bns + [256]          # 128x256 tiles (4-stage ring, one CTA per SM): fewer operand bytes per flop for large GEMMs
-    cands = [(0, 0, 0)]
+    cands = [(0, 0, 0, 0)]
     for bn in bns:
         tiles = ((d.N + bn - 1) // bn) * ((M + 127) // 128) * d.batch
-        cands.append((bn, 1, 0))
+        cands.append((bn, 1, 0, 0))
         if tiles <= 148:
-            cands.append((bn, 1, 3))          # 3-stage ring: leaves room for the next kernel's CTAs on the SM
+            cands.append((bn, 1, 3, 0))          # 3-stage ring: leaves room for the next kernel's CTAs on the SM
         if tiles < 148:
             for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
                 if tiles * sp <= 320 and kiters // sp >= 2:
-                    cands.append((bn, sp, 0))
+                    cands.append((bn, sp, 0, 0))
                     if tiles * sp <= 148:
-                        cands.append((bn, sp, 3))
+                        cands.append((bn, sp, 3, 0))
+    if CTA_PAIR and d.a_major != CB_MAJOR_MN and M >= 2048 and d.N >= 128 and not d.d_transposed:
+        # tcgen05 cta_group::2: a 2-CTA cluster per 256 x bn tile (half the B bytes per SM); large-M GEMMs only
+        cands.append((128, 1, 0, 1))
+        if d.N >= 256:
+            cands.append((256, 1, 0, 1))
     t = GemmDesc.from_buffer_copy(bytes(d))
     # scratch output large enough for any addressing the descriptor can produce
     inner = d.batch_inner if d.batch_inner > 0 else d.batch
@@ -141,8 +147,8 @@ def _autotune(d, key):
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         sp_ = ctypes.c_void_p(side.cuda_stream)
-        for bn, sp, stg in cands:
-            t.tile_n, t.splits, t.stages = bn, sp, stg
+        for bn, sp, stg, pair in cands:
+            t.tile_n, t.splits, t.stages, t.cta_pair = bn, sp, stg, pair
             if L.cb_gemm(ctypes.byref(t), sp_) != 0:
                 continue
             g = torch.cuda.CUDAGraph()
@@ -161,23 +167,23 @@ def _autotune(d, key):
                 e1.record(side)
                 e1.synchronize()
                 best = min(best, e0.elapsed_time(e1) * 125.0)     # us per launch
-            times[(bn, sp, stg)] = best
+            times[(bn, sp, stg, pair)] = best
             del g
     cur.wait_stream(side)
-    base = times.get((0, 0, 0), 1e9)
-    win = min(times, key=times.get) if times else (0, 0, 0)
+    base = times.get((0, 0, 0, 0), 1e9)
+    win = min(times, key=times.get) if times else (0, 0, 0, 0)
     if times.get(win, 1e9) > 0.97 * base:     # keep the library's own choice unless the gain is real
-        win = (0, 0, 0)
+        win = (0, 0, 0, 0)
     _TUNE[key] = win
     if TUNE_LOG is not None:
-        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}": round(v, 2) for k, v in times.items()}, win))
+        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}": round(v, 2) for k, v in times.items()}, win))
     log_path = os.environ.get("CB_GEMM_TUNE_LOG")
     if log_path:
         import json
         with open(log_path, "a") as f:
             f.write(json.dumps({"M": M, "N": d.N, "K": d.K, "batch": d.batch, "conv": d.conv, "kh": d.kh, "b_major": d.b_major,
                                 "a_major": d.a_major, "d_dtype": d.d_dtype, "win": list(win),
-                                "us": {f"{k[0]}x{k[1]}s{k[2]}": round(v, 2) for k, v in times.items()}}) + "\n")
+                                "us": {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}": round(v, 2) for k, v in times.items()}}) + "\n")
     return win
 
 
@@ -186,13 +192,13 @@ def _gemm(d, what):
     d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     if GEMM_DEBUG_TIMELINE is not None:
         d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
-    if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0:
+    if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0 and d.cta_pair == 0:
         key = _tune_key(d)
         win = _TUNE.get(key)
         if win is None and not torch.cuda.is_current_stream_capturing():
             win = _autotune(d, key)
         if win is not None:
-            d.tile_n, d.splits, d.stages = win
+            d.tile_n, d.splits, d.stages, d.cta_pair = win
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M

@@ -144,7 +144,8 @@ typedef struct cb_gemm_desc {
     int32_t tile_n;
     int32_t splits;
     int32_t stages;      /* 0 = auto, 3 = 3-stage ring / 2 CTAs per SM, 6 = 6-stage ring / 1 CTA per SM */
-    int32_t reserved0;
+    int32_t cta_pair;    /* 1 = tcgen05 cta_group::2 variant: a 2-CTA cluster computes a 256 x (128|256) tile, each CTA staging
+                          * its 128 rows of A and half of the B tile (K-major A, no split-K); 0 = single-CTA tiles */
 
     /* second destination (optional, batch == 1, not transposed): the same epilogue value is also written to
      * D2[row][col] (row pitch ldd2 elements, dtype d2_dtype).  Used to place a UNet skip activation straight into the

@@ -469,3 +469,42 @@ def test_ema_rows_and_prep_kernels(dev):
     ref[:, :24, :10] = (w * sc.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(9, 24, 10)
     assert rel(pk.float().cpu(), ref.view(9 * 32, 16)) < 1e-3
     assert rel(ops.to_device(torch.arange(7.0), "cuda", torch.float16).cpu(), torch.arange(7.0)) == 0
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_cta_pair(dev, bn):
+    """tcgen05 cta_group::2 variant (desc.cta_pair = 1): a 2-CTA cluster per 256 x bn tile.  Linear K-major / MN-major B,
+    3x3 convolution (padding, ragged rows), odd tile counts, bias + residual + second destination."""
+    from celebbasis_b200 import ops
+    orig = ops._gemm
+
+    def forced(d, what):
+        d.cta_pair, d.tile_n = 1, bn
+        return orig(d, what)
+    ops._gemm = forced
+    try:
+        x, w = rnd(4096, 320), rnd(640, 320)
+        bias, res = rnd(640, dtype=torch.float32), rnd(4096, 640, dtype=torch.float32)
+        y = ops.linear(x, w, bias, out_dtype=torch.float32, residual=res)
+        assert rel(y, x.float() @ w.float().t() + bias + res) < 2e-3
+        dy = rnd(4096, 640)
+        dx = ops.linear_dgrad(dy, w, out_dtype=torch.float32)                  # MN-major B
+        assert rel(dx, dy.float() @ w.float()) < 2e-3
+        x3, w3 = rnd(128 * 5 + 40, 192), rnd(300, 192)                          # odd number of m tiles, ragged M and N
+        y3 = ops.linear(x3, w3, out_dtype=torch.float16)
+        assert rel(y3, x3.float() @ w3.float().t()) < 2e-3
+        g = ops.Geo(2, 48, 48)                                                  # 4608 rows: 36 tiles; 48-wide rows: ragged boxes
+        xi = rnd(g.rows, 128)
+        wc = torch.randn(256, 128, 3, 3, device="cuda") * 0.03
+        d2 = torch.zeros(g.rows, 256 + 64, dtype=torch.float32, device="cuda")
+        yc, _ = ops.conv2d(xi, g, ops.pack_conv_weight(wc, torch.float16), 256, out_dtype=torch.float32, out2=d2[:, 64:])
+        refc = F.conv2d(xi.float().view(2, 48, 48, 128).permute(0, 3, 1, 2), wc.half().float(), padding=1)
+        refc = refc.permute(0, 2, 3, 1).reshape(g.rows, 256)
+        assert rel(yc, refc) < 2e-3 and rel(d2[:, 64:], refc) < 2e-3
+        dyc = rnd(g.rows, 256)
+        dxc, _ = ops.conv2d_dgrad(dyc, g, ops.pack_conv_weight(wc, torch.float16), 128, out_dtype=torch.float32)
+        xr = xi.float().view(2, 48, 48, 128).permute(0, 3, 1, 2).requires_grad_(True)
+        F.conv2d(xr, wc.half().float(), padding=1).backward(dyc.float().view(2, 48, 48, 256).permute(0, 3, 1, 2))
+        assert rel(dxc, xr.grad.permute(0, 2, 3, 1).reshape(g.rows, 128)) < 2e-3
+    finally:
+        ops._gemm = orig

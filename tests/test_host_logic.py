@@ -140,7 +140,7 @@ def test_gemm_autotune_key_and_lanes():
     b.conv, b.kh, b.kw = 1, 3, 3
     assert ops._tune_key(a) != ops._tune_key(b)
     b = GemmDesc.from_buffer_copy(bytes(a))
-    b.tile_n, b.splits, b.stages = 128, 3, 3          # tuning overrides are not part of the shape key
+    b.tile_n, b.splits, b.stages, b.cta_pair = 128, 3, 3, 1   # tuning overrides are not part of the shape key
     assert ops._tune_key(a) == ops._tune_key(b)
     assert ops._LANE == 0
     with ops.lane(1):
