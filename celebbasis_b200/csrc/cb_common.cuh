@@ -289,6 +289,18 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
         : "memory");
 }
 
+// arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+
 // ---- UMMA descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 |
 // [46,48) version=1 | [49,52) base offset | [61,64) layout (2 = SWIZZLE_128B).

@@ -9,6 +9,7 @@
 // the TMA out-of-bounds zero fill, stride-2 is the tensor-map traversal stride.
 // Two CTAs are resident per SM (3-stage ring each) so one tile's epilogue overlaps the
 // other's MMA main loop.
+#include <algorithm>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -618,17 +619,22 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 template <int BN, int kStages>
 struct PairCfg {
-    static constexpr int kTmemCols = BN <= 128 ? 128 : 256;
+    static constexpr int kAccCols = BN <= 128 ? 128 : 256;      // TMEM columns of one accumulator
+    static constexpr int kTmemCols = 2 * kAccCols;              // two accumulators: epilogue(i) overlaps mainloop(i+1)
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = (BN / 2) * BK * 2;          // this CTA's half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
+// Persistent: gridDim.x = 2 * (number of clusters <= SMs / 2); cluster c works on tiles c, c + C, c + 2C, ... of the
+// (batch, m-pair, n-tile) space with n fastest (consecutive clusters share the same A rows in L2).  The shared-memory
+// ring and its phases run on across tiles; the accumulator alternates between two TMEM regions so the MMAs of tile i+1
+// start while the epilogue warps of both CTAs still drain tile i (tmem_full[acc] / tmem_empty[acc] barriers).
 template <int BN, bool B_MN, int kStages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ GemmParams p) {
+                    const __grid_constant__ GemmParams p, int n_ntiles, int n_mpairs, int total_tiles) {
     using Cfg = PairCfg<BN, kStages>;
     constexpr int HN = BN / 2;
     extern __shared__ uint8_t smem_raw[];
@@ -636,30 +642,15 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    const int m_tile = blockIdx.x;                 // the pair covers m tiles (2j, 2j+1)
-    const int n0 = blockIdx.y * BN;
-    const int bz = blockIdx.z;
-    const int zi = bz % p.batch_inner;
-    const int zo = bz / p.batch_inner;
-
-    int m0 = 0, ow0 = 0, oh0 = 0, img0 = 0;
-    if (p.conv) {
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int ti = m_tile / (p.tiles_w * p.tiles_h);
-        ow0 = tw * p.box_w;
-        oh0 = th * p.box_h;
-        img0 = ti * p.box_i;
-    } else {
-        m0 = m_tile * BM;
-    }
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -668,7 +659,10 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 2);        // one arrival per CTA of the pair (used on the leader only)
+        }
         mbar_fence_init();
         fence_proxy_async_smem();
     }
@@ -682,123 +676,174 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     pdl_sync();
 
     const int kiters = p.taps * p.kchunks;
+    // tile t -> (batch z, m-pair, n-tile); this CTA's m tile = 2 * pair + rank
+    auto tile_coords = [&](int t, int& bz, int& m_tile, int& n0) {
+        const int nt = t % n_ntiles;
+        const int r = t / n_ntiles;
+        n0 = nt * BN;
+        m_tile = 2 * (r % n_mpairs) + (int)rank;
+        bz = r / n_mpairs;
+    };
+    auto tile_origin = [&](int m_tile, int& m0, int& ow0, int& oh0, int& img0) {
+        m0 = ow0 = oh0 = img0 = 0;
+        if (p.conv) {
+            const int tw = m_tile % p.tiles_w;
+            const int th = (m_tile / p.tiles_w) % p.tiles_h;
+            const int ti = m_tile / (p.tiles_w * p.tiles_h);
+            ow0 = tw * p.box_w;
+            oh0 = th * p.box_h;
+            img0 = ti * p.box_i;
+        } else {
+            m0 = m_tile * BM;
+        }
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer (both CTAs) =====================
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                if (leader) mbar_arrive_expect_tx(full_bar(s), 2u * (p.a_bytes + (unsigned)Cfg::kBBytes));
-                const int tap = it / p.kchunks;
-                const int kc = it - tap * p.kchunks;
-                const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
-                const uint32_t b_dst = a_dst + Cfg::kABytes;
-                const int tap_b = p.flip_taps ? (p.taps - 1 - tap) : tap;
-                if (p.conv) {
-                    const int r = tap / p.kw, sx = tap - r * p.kw;
-                    tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, ow0 * p.stride + sx - p.pad_left,
-                                     oh0 * p.stride + r - p.pad_top, img0);
-                } else {
-                    tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, m0, zi, zo);
-                }
+            int git = 0;
+            for (int t = cid; t < total_tiles; t += nclusters) {
+                int bz, m_tile, n0, m0, ow0, oh0, img0;
+                tile_coords(t, bz, m_tile, n0);
+                tile_origin(m_tile, m0, ow0, oh0, img0);
+                const int zi = bz % p.batch_inner, zo = bz / p.batch_inner;
                 const int nh = n0 + (int)rank * HN;          // this CTA's half of the B tile
-                if (B_MN) {
+                for (int it = 0; it < kiters; ++it, ++git) {
+                    const int s = git % kStages;
+                    const uint32_t ph = (git / kStages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(full_bar(s), 2u * (p.a_bytes + (unsigned)Cfg::kBBytes));
+                    const int tap = it / p.kchunks;
+                    const int kc = it - tap * p.kchunks;
+                    const uint32_t a_dst = smem_base + s * Cfg::kStageBytes;
+                    const uint32_t b_dst = a_dst + Cfg::kABytes;
+                    const int tap_b = p.flip_taps ? (p.taps - 1 - tap) : tap;
+                    if (p.conv) {
+                        const int r = tap / p.kw, sx = tap - r * p.kw;
+                        tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, ow0 * p.stride + sx - p.pad_left,
+                                         oh0 * p.stride + r - p.pad_top, img0);
+                    } else {
+                        tma_load_4d_pair(a_dst, &tmA, full_bar(s), kc * BK, m0, zi, zo);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int j = 0; j < HN / 64; ++j)
-                        tma_load_4d_pair(b_dst + j * 8192, &tmB, full_bar(s), nh + j * 64,
-                                         tap_b * p.b_tap_rows + kc * BK, zi, zo);
-                } else {
-                    tma_load_4d_pair(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + nh, zi, zo);
+                        for (int j = 0; j < HN / 64; ++j)
+                            tma_load_4d_pair(b_dst + j * 8192, &tmB, full_bar(s), nh + j * 64,
+                                             tap_b * p.b_tap_rows + kc * BK, zi, zo);
+                    } else {
+                        tma_load_4d_pair(b_dst, &tmB, full_bar(s), kc * BK, tap_b * p.b_tap_rows + nh, zi, zo);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
             // ===================== MMA issuer (leader CTA only) =====================
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(full_bar(s), ph);
+            int git = 0, lt = 0;
+            for (int t = cid; t < total_tiles; t += nclusters, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(tempty_bar(acc), (((unsigned)lt >> 1) & 1u) ^ 1u);      // both epilogues drained this accumulator
                 tc_fence_after();
-                const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
-                const uint32_t b_src = a_src + Cfg::kABytes;
-                const int kc = it % p.kchunks;
-                const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : (BK / 16);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adesc = umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
-                    const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
-                                                : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
-                    umma_f16_pair(tmem_base, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
+                for (int it = 0; it < kiters; ++it, ++git) {
+                    const int s = git % kStages;
+                    const uint32_t ph = (git / kStages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + s * Cfg::kStageBytes;
+                    const uint32_t b_src = a_src + Cfg::kABytes;
+                    const int kc = it % p.kchunks;
+                    const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : (BK / 16);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t adesc = umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
+                        const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
+                                                    : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
+                        umma_f16_pair(d_tmem, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(empty_bar(s));        // frees this stage in BOTH CTAs once the MMAs above retire
                 }
-                umma_commit_pair(empty_bar(s));        // frees this stage in BOTH CTAs once the MMAs above retire
+                umma_commit_pair(tfull_bar(acc));
             }
-            umma_commit_pair(tmem_full_bar);
         }
     } else {
-        // ===================== epilogue (each CTA: its own 128 rows) =====================
+        // ===================== epilogue (each CTA: its own 128 rows of every tile) =====================
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        bool row_valid;
-        long long grow;
-        if (p.conv) {
-            const int per_img = p.box_h * p.box_w;
-            const int bi = r / per_img;
-            const int rem = r - bi * per_img;
-            const int bh = rem / p.box_w;
-            const int bw = rem - bh * p.box_w;
-            const int img = img0 + bi, oh = oh0 + bh, ow = ow0 + bw;
-            row_valid = (bi < p.box_i) && (img < p.img_n) && (oh < p.out_h) && (ow < p.out_w);
-            grow = ((long long)img * p.out_h + oh) * p.out_w + ow;
-        } else {
-            grow = m0 + r;
-            row_valid = grow < p.M;
-        }
-        const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
-        const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
-        const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
-        const int ncols_tile = min(BN, p.N - n0);
         __shared__ __align__(16) float s_bias[BN + 8];
-        const float* sb = nullptr;
-        if (p.bias) {
-            const long long tile_row0 = p.conv ? (((long long)img0 * p.out_h + oh0) * p.out_w + ow0) : (long long)m0;
-            const long long brow0 = p.bias_row_div > 0 ? tile_row0 / p.bias_row_div : 0;
-            for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = i < ncols_tile ? p.bias[brow0 * p.ldbias + n0 + i] : 0.f;
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (brow == brow0) sb = s_bias;
-        }
-        const bool r_fast = p.R && p.vec_ok && !p.d_transposed && row_valid;
-        const long long r_row = r_off + grow * p.ldr + n0;
-        ResidualChunk rc_cur, rc_next;
-        if (r_fast && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        int lt = 0;
+        for (int t = cid; t < total_tiles; t += nclusters, ++lt) {
+            const int acc = lt & 1;
+            int bz, m_tile, n0, m0, ow0, oh0, img0;
+            tile_coords(t, bz, m_tile, n0);
+            tile_origin(m_tile, m0, ow0, oh0, img0);
+            const int zi = bz % p.batch_inner, zo = bz / p.batch_inner;
+            bool row_valid;
+            long long grow;
+            if (p.conv) {
+                const int per_img = p.box_h * p.box_w;
+                const int bi = r / per_img;
+                const int rem = r - bi * per_img;
+                const int bh = rem / p.box_w;
+                const int bw = rem - bh * p.box_w;
+                const int img = img0 + bi, oh = oh0 + bh, ow = ow0 + bw;
+                row_valid = (bi < p.box_i) && (img < p.img_n) && (oh < p.out_h) && (ow < p.out_w);
+                grow = ((long long)img * p.out_h + oh) * p.out_w + ow;
+            } else {
+                grow = m0 + r;
+                row_valid = grow < p.M;
+            }
+            const long long brow = p.bias_row_div > 0 ? grow / p.bias_row_div : 0;
+            const long long d_off = (long long)zo * p.d_bs2 + (long long)zi * p.d_bs;
+            const long long r_off = (long long)zo * p.r_bs2 + (long long)zi * p.r_bs;
+            const int ncols_tile = min(BN, p.N - n0);
+            const float* sb = nullptr;
+            if (p.bias) {
+                const long long tile_row0 = p.conv ? (((long long)img0 * p.out_h + oh0) * p.out_w + ow0) : (long long)m0;
+                const long long brow0 = p.bias_row_div > 0 ? tile_row0 / p.bias_row_div : 0;
+                for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = i < ncols_tile ? p.bias[brow0 * p.ldbias + n0 + i] : 0.f;
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (brow == brow0) sb = s_bias;
+            }
+            const bool r_fast = p.R && p.vec_ok && !p.d_transposed && row_valid;
+            const long long r_row = r_off + grow * p.ldr + n0;
+            ResidualChunk rc_cur, rc_next;
+            if (r_fast && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);
+            mbar_wait(tfull_bar(acc), ((unsigned)lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(acc * Cfg::kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c * 32 < ncols_tile; ++c) {
-            uint32_t acc[32];
-            tmem_ld_32x32(trow + c * 32, acc);
-            const bool pre = r_fast && ncols_tile - c * 32 >= 32;
-            if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
-            tmem_ld_wait();
-            if (row_valid && p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
-                float f[32];
+            for (int c = 0; c * 32 < ncols_tile; ++c) {
+                uint32_t av[32];
+                tmem_ld_32x32(trow + c * 32, av);
+                const bool pre = r_fast && ncols_tile - c * 32 >= 32;
+                if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
+                tmem_ld_wait();
+                if (c * 32 + 32 >= ncols_tile) {
+                    // last TMEM read of this accumulator: hand it back to the MMA issuer before the stores drain
+                    tc_fence_before();
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (threadIdx.x == 64) mbar_arrive_cluster(tempty_bar(acc), 0);
+                }
+                if (row_valid && p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
+                    float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
-                epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
-            } else if (row_valid) {
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(av[j]) * p.alpha;
+                    epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                } else if (row_valid) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int nc = min(8, ncols_tile - c * 32 - g * 8);
-                    if (nc > 0) {
-                        float f[8];
+                    for (int g = 0; g < 4; ++g) {
+                        const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                        if (nc > 0) {
+                            float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
-                        epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(av[g * 8 + j]) * p.alpha;
+                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                        }
                     }
                 }
+                rc_cur = rc_next;
             }
-            rc_cur = rc_next;
+            if (p.bias) asm volatile("bar.sync 2, 128;" ::: "memory");      // s_bias is rewritten for the next tile
         }
     }
     __syncwarp();
@@ -880,8 +925,9 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
 }
 
 template <int BN, bool B_MN>
-static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
-    constexpr int kSt = BN == 256 ? 6 : 6;
+static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
+                       int batch, cudaStream_t st) {
+    constexpr int kSt = 6;
     using Cfg = PairCfg<BN, kSt>;
     static bool attr_done = false;
     auto kern = cb_gemm_pair_kernel<BN, B_MN, kSt>;
@@ -889,7 +935,11 @@ static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
+    const long long total = (long long)n_mpairs * n_ntiles * batch;
+    CB_REQUIRE(total < (1ll << 30), CB_ERR_ARG, "cb_gemm(pair): too many tiles");
+    const int clusters = (int)std::min<long long>(total, device_sm_count() / 2);
+    dim3 grid((unsigned)(2 * clusters));
+    CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p, n_ntiles, n_mpairs, (int)total);
     CB_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
@@ -1151,9 +1201,9 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     if (pair) {
         p.splits = 1;
         p.kiters_per_split = p.taps * p.kchunks;
-        dim3 pgrid((unsigned)(2 * ceil_div(m_tiles, 2)), (unsigned)ceil_div(d.N, BN), (unsigned)d.batch);
-        if (b_mn) return BN == 128 ? launch_pair<128, true>(tA, tB, p, pgrid, st) : launch_pair<256, true>(tA, tB, p, pgrid, st);
-        return BN == 128 ? launch_pair<128, false>(tA, tB, p, pgrid, st) : launch_pair<256, false>(tA, tB, p, pgrid, st);
+        const int mp = ceil_div(m_tiles, 2), nt = ceil_div(d.N, BN);
+        if (b_mn) return BN == 128 ? launch_pair<128, true>(tA, tB, p, mp, nt, d.batch, st) : launch_pair<256, true>(tA, tB, p, mp, nt, d.batch, st);
+        return BN == 128 ? launch_pair<128, false>(tA, tB, p, mp, nt, d.batch, st) : launch_pair<256, false>(tA, tB, p, mp, nt, d.batch, st);
     }
     dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)(d.batch * p.splits));
     if (!a_mn && !b_mn) {
