@@ -42,7 +42,7 @@ def gn(hw, c):
     work.append(f)
     work.append(lambda: ops.groupnorm_bwd(dy, x, ops.Geo(1, hw, hw), gm, bt, st["s"], silu=True))
 
-conv(1, 64, 320, 320); conv(1, 128, 512, 512); conv(1, 16, 1280, 1280); lin(4096, 2560, 320); lin(77, 768, 768)
+conv(1, 64, 320, 320); conv(1, 128, 512, 512); conv(1, 16, 1280, 1280); conv(1, 64, 640, 640); lin(4096, 2560, 320); lin(77, 768, 768)
 attn(4096, 40); attn(1024, 80)
 gn(64, 320); gn(32, 640)
 for _ in range(2):
