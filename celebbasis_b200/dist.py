@@ -80,12 +80,15 @@ def gather_identity_state(local_coeffs, owned_ids, num_ids):
     local_coeffs: (num_ids, ...) tensor where only rows `owned_ids` are meaningful on this rank."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):
         return local_coeffs
-    world = dist.get_world_size()
     mask = torch.zeros(num_ids, dtype=local_coeffs.dtype, device=local_coeffs.device)
     mask[owned_ids] = 1
-    contrib = local_coeffs * mask.view(-1, *([1] * (local_coeffs.dim() - 1)))
-    dist.all_reduce(contrib, op=dist.ReduceOp.SUM)    # rows are owned by exactly one rank => sum == gather
-    return contrib
+    shape = (-1, *([1] * (local_coeffs.dim() - 1)))
+    contrib = local_coeffs * mask.view(shape)
+    owners = mask.clone()
+    dist.all_reduce(contrib, op=dist.ReduceOp.SUM)    # a row owned by exactly one rank: sum == that rank's row
+    dist.all_reduce(owners, op=dist.ReduceOp.SUM)
+    # identities nobody trained keep their (identical on every rank) initial value; shared ones are averaged
+    return torch.where(owners.view(shape) > 0, contrib / owners.clamp_min(1).view(shape), local_coeffs)
 
 
 def barrier():

@@ -111,6 +111,12 @@ def _dp_worker(rank, world, port, out_dir):
     for i in owned:
         coeff[i] = i + 1
     full = cbd.gather_identity_state(coeff, owned, 10)
+    # identities that NO rank trained keep their initial value (identical on all ranks)
+    init = torch.full((10, 2, 1, 4), 7.0)
+    part = init.clone()
+    part[rank] = 100.0 + rank
+    kept = cbd.gather_identity_state(part, [rank], 10)
+    assert float(kept[0, 0, 0, 0]) == 100.0 and float(kept[1, 0, 0, 0]) == 101.0 and bool((kept[2:] == 7.0).all())
     torch.save({"g0": g[0].item(), "gl": g[-1].item(), "owned": owned, "full": full, "lr": cbd.scaled_lr(5e-3, 1)},
                os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
