@@ -39,6 +39,9 @@ struct GemmParams {
     void* D2;          // optional second destination (same value, own dtype / row pitch)
     int d2_dtype;
     long long ldd2;
+    const float* act_param;    // CB_ACT_PRELU: per-column negative slope
+    const float* d2_scale;     // optional per-column affine applied to the D2 copy only: D2 = v * scale[col] + shift[col]
+    const float* d2_shift;
     int batch_inner;
     int d_transposed;
     int vec_ok;
@@ -85,6 +88,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         case CB_ACT_QUICK_GELU: return quick_gelu_f(v);
         default: return v;
     }
+}
+
+// activation of 8 consecutive columns starting at `col` (PReLU reads its per-column slopes)
+__device__ __forceinline__ void apply_act8(float (&f)[8], int act, const float* act_param, int col, int ncols = 8) {
+    if (act == CB_ACT_PRELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < ncols) f[j] = f[j] > 0.f ? f[j] : f[j] * __ldg(act_param + col + j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], act);
+    }
+}
+// second destination: optional per-column affine (eval BatchNorm of the consumer folded into the producer's epilogue)
+__device__ __forceinline__ void d2_affine8(float (&g)[8], const float (&f)[8], const float* sc, const float* sh, int col,
+                                           int ncols = 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = (sc && j < ncols) ? f[j] * __ldg(sc + col + j) + __ldg(sh + col + j) : f[j];
 }
 
 template <typename T>
@@ -232,10 +253,7 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             for (int j = 0; j < ncols; ++j) f[j] += p.bias[brow * p.ldbias + col + j];
         }
     }
-    if (p.act != CB_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
-    }
+    if (p.act != CB_ACT_NONE) apply_act8(f, p.act, p.act_param, col, ncols);
     if (ncols == 8 && p.vec_ok && !p.d_transposed) {
         if (rpre) {
 #pragma unroll
@@ -253,7 +271,11 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
         if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
         else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
         else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
-        if (p.D2) store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col, f);
+        if (p.D2) {
+            float g2[8];
+            d2_affine8(g2, f, p.d2_scale, p.d2_shift, col);
+            store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col, g2);
+        }
     } else {
         for (int j = 0; j < ncols; ++j) {
             float v = f[j];
@@ -261,7 +283,8 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             const long long didx = p.d_transposed ? (d_off + (long long)(col + j) * p.ldd + grow)
                                                   : (d_off + grow * p.ldd + col + j);
             store_any(p.D, p.d_dtype, didx, v);
-            if (p.D2) store_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + j, v);
+            if (p.D2) store_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + j,
+                                p.d2_scale ? v * p.d2_scale[col + j] + p.d2_shift[col + j] : v);
         }
     }
 }
@@ -287,10 +310,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += b[j];
         }
-        if (p.act != CB_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
-        }
+        if (p.act != CB_ACT_NONE) apply_act8(f, p.act, p.act_param, col + g * 8);
         if (rc) {
             float r[8];
             residual_unpack8(p, *rc, g, r);
@@ -305,7 +325,11 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += r[j];
         }
-        if (p.D2) store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + g * 8, f);
+        if (p.D2) {
+            float g2[8];
+            d2_affine8(g2, f, p.d2_scale, p.d2_shift, col + g * 8);
+            store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + g * 8, g2);
+        }
         if (p.d_dtype == CB_F32) {
             float* dst = reinterpret_cast<float*>(p.D) + didx + g * 8;
             const uint4 a = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
@@ -1124,6 +1148,11 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         CB_REQUIRE((reinterpret_cast<uintptr_t>(d.D2) & 15u) == 0 && (d.ldd2 * es2) % 16 == 0 && d.ldd2 >= d.N, CB_ERR_ALIGN,
                    "cb_gemm: D2 must be 16-byte aligned with a 16-byte multiple row pitch >= N");
     }
+    p.act_param = d.act_param;
+    p.d2_scale = d.d2_scale;
+    p.d2_shift = d.d2_shift;
+    CB_REQUIRE(d.act != CB_ACT_PRELU || d.act_param != nullptr, CB_ERR_ARG, "cb_gemm: CB_ACT_PRELU needs act_param (slopes)");
+    CB_REQUIRE((d.d2_scale == nullptr) == (d.d2_shift == nullptr), CB_ERR_ARG, "cb_gemm: d2_scale and d2_shift go together");
     p.bias = d.bias;
     p.bias_row_div = d.bias_row_div;
     p.ldbias = d.ldbias;

@@ -59,9 +59,43 @@ class IResNetEngine:
         self.fc_w = ops.to_device(Wr.permute(0, 2, 1).reshape(nf, 49 * 512), self.dev, self.dt)  # column = pix*512 + c
         self.fc_b = f32(bias)
 
+    FUSE_EPILOGUES = True    # PReLU and the next block's bn1 inside the conv epilogues (no channel_affine_act launches)
+
     @torch.no_grad()
     def forward(self, x, geo):
         """x: [F*112*112][8] channels-last (RGB + zero pad), geo=(F,112,112) -> features [F][512] fp32."""
+        if not self.FUSE_EPILOGUES:
+            return self._forward_unfused(x, geo)
+        from .lib import CB_ACT_PRELU
+        # The residual stream is fp32 (100 blocks deep); tensor-core operands are fp16.  Every IBasicBlock
+        # (iresnet.py:26-64) is two launches: conv1 (+bn2 folded, PReLU in the epilogue) and conv2 (+bn3 folded, + shortcut)
+        # whose epilogue ALSO writes bn1 of the NEXT block applied to the result as the 16-bit operand that block reads.
+        blocks = self.blocks
+        nb = len(blocks)
+
+        def t_buf(g, c):
+            return torch.empty(g.rows, c, dtype=self.dt, device=self.dev)
+        t = t_buf(geo, 64)
+        h, _ = ops.conv2d(x, geo, self.stem_w, 64, bias=self.stem_b, out_dtype=torch.float32, act=CB_ACT_PRELU,
+                          act_param=self.stem_slope, out2=t, out2_affine=(blocks[0]["s1"], blocks[0]["sh1"]))
+        for i, b in enumerate(blocks):
+            u, _ = ops.conv2d(t, geo, b["w1"], b["cout"], bias=b["b1"], out_dtype=self.dt, act=CB_ACT_PRELU,
+                              act_param=b["slope"])
+            if "wd" in b:
+                idn, ogeo = ops.conv2d(ops.cast(h, self.dt), geo, b["wd"], b["cout"], bias=b["bd"], ksize=1, stride=2,
+                                       pad=(0, 0, 0, 0), out_dtype=torch.float32)
+            else:
+                idn, ogeo = h, geo
+            t = t_buf(ogeo, b["cout"])
+            aff = (blocks[i + 1]["s1"], blocks[i + 1]["sh1"]) if i + 1 < nb else None     # last block: plain 16-bit copy
+            h, geo = ops.conv2d(u, geo, b["w2"], b["cout"], bias=b["b2"], stride=b["stride"], out_dtype=torch.float32,
+                                residual=idn, out2=t, out2_affine=aff)
+            assert (geo.h, geo.w) == (ogeo.h, ogeo.w)
+        flat = t.view(geo.n, geo.hw * t.shape[1])
+        return ops.linear(flat, self.fc_w, self.fc_b, out_dtype=torch.float32)
+
+    @torch.no_grad()
+    def _forward_unfused(self, x, geo):
         # the residual stream is fp32 (100 blocks deep); tensor-core operands are fp16
         h, _ = ops.conv2d(x, geo, self.stem_w, 64, bias=self.stem_b, out_dtype=torch.float32)
         ops.channel_affine_act(h, slope=self.stem_slope, out=h)

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcelebbasis_b200.so")
 
 CB_F16, CB_BF16, CB_F32 = 0, 1, 2
-CB_ACT_NONE, CB_ACT_SILU, CB_ACT_GELU, CB_ACT_QUICK_GELU = 0, 1, 2, 3
+CB_ACT_NONE, CB_ACT_SILU, CB_ACT_GELU, CB_ACT_QUICK_GELU, CB_ACT_PRELU = 0, 1, 2, 3, 4
 CB_MAJOR_K, CB_MAJOR_MN = 0, 1
 
 
@@ -41,6 +41,7 @@ class GemmDesc(ctypes.Structure):
         ("debug_timeline", ctypes.c_void_p),
         ("tile_n", ctypes.c_int32), ("splits", ctypes.c_int32), ("stages", ctypes.c_int32), ("cta_pair", ctypes.c_int32),
         ("D2", ctypes.c_void_p), ("ldd2", ctypes.c_int64), ("d2_dtype", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("act_param", ctypes.c_void_p), ("d2_scale", ctypes.c_void_p), ("d2_shift", ctypes.c_void_p),
     ]
 
 

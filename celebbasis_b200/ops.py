@@ -9,7 +9,7 @@ import os
 import torch
 
 from . import lib as _lib
-from .lib import (CB_ACT_GELU, CB_ACT_NONE, CB_ACT_QUICK_GELU, CB_ACT_SILU, CB_BF16, CB_F16, CB_F32,
+from .lib import (CB_ACT_GELU, CB_ACT_NONE, CB_ACT_PRELU, CB_ACT_QUICK_GELU, CB_ACT_SILU, CB_BF16, CB_F16, CB_F32,
                   CB_MAJOR_K, CB_MAJOR_MN, GemmDesc)
 
 _DT = {torch.float16: CB_F16, torch.bfloat16: CB_BF16, torch.float32: CB_F32}
@@ -81,13 +81,20 @@ TUNE_LOG = None     # set to a list to collect (key, table of candidate times)
 def _tune_key(d):
     return (d.M, d.N, d.K, d.batch, d.batch_inner, d.ab_dtype, d.a_major, d.b_major, d.conv, d.img_n, d.img_h, d.img_w,
             d.out_h, d.out_w, d.kh, d.kw, d.stride, d.flip_taps, d.d_dtype, d.d_transposed, 1 if d.R else 0, d.r_dtype,
-            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd, (d.d2_dtype + 1) if d.D2 else 0)
+            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd, (d.d2_dtype + 1) if d.D2 else 0, 1 if d.d2_scale else 0)
 
 
-def _set_out2(d, out2):
+def _set_out2(d, out2, out2_affine=None, act_param=None):
     if out2 is not None:
         assert out2.dim() == 2 and out2.stride(1) == 1
         d.D2, d.d2_dtype, d.ldd2 = out2.data_ptr(), _dt(out2), out2.stride(0)
+        if out2_affine is not None:
+            sc, sh = out2_affine
+            assert sc.dtype == torch.float32 and sh.dtype == torch.float32 and sc.numel() >= d.N and sh.numel() >= d.N
+            d.d2_scale, d.d2_shift = sc.data_ptr(), sh.data_ptr()
+    if act_param is not None:
+        assert act_param.dtype == torch.float32 and act_param.numel() >= d.N
+        d.act_param = act_param.data_ptr()
 
 
 def _autotune(d, key):
@@ -302,7 +309,8 @@ def linear_dgrad(dy, w, *, out_dtype=None, out=None, residual=None, alpha=1.0):
 
 
 def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1), out_dtype=None, out=None,
-           residual=None, bias_per_image=False, ldbias=None, act=CB_ACT_NONE, cout_rows=None, out2=None):
+           residual=None, bias_per_image=False, ldbias=None, act=CB_ACT_NONE, cout_rows=None, out2=None, out2_affine=None,
+           act_param=None):
     """Implicit-GEMM convolution on an NHWC activation matrix.
 
     x: [geo.rows][Cin]; wpack: [k*k*cout_rows][Cin] from pack_conv_weight; pad=(top,bottom,left,right).
@@ -333,7 +341,7 @@ def conv2d(x, geo, wpack, cout, bias=None, *, ksize=3, stride=1, pad=(1, 1, 1, 1
     if residual is not None:
         d.R, d.r_dtype, d.ldr = residual.data_ptr(), _dt(residual), residual.stride(0)
     d.alpha, d.act = 1.0, act
-    _set_out2(d, out2)
+    _set_out2(d, out2, out2_affine, act_param)
     _gemm(d, "cb_gemm(conv2d)")
     return out, ogeo
 

@@ -32,7 +32,7 @@ extern "C" {
 /* element types */
 enum { CB_F16 = 0, CB_BF16 = 1, CB_F32 = 2 };
 /* activation fused into the GEMM epilogue */
-enum { CB_ACT_NONE = 0, CB_ACT_SILU = 1, CB_ACT_GELU = 2, CB_ACT_QUICK_GELU = 3 };
+enum { CB_ACT_NONE = 0, CB_ACT_SILU = 1, CB_ACT_GELU = 2, CB_ACT_QUICK_GELU = 3, CB_ACT_PRELU = 4 };
 /* operand majorness: K-major = reduction dim contiguous; MN-major = M (or N) contiguous */
 enum { CB_MAJOR_K = 0, CB_MAJOR_MN = 1 };
 
@@ -155,6 +155,12 @@ typedef struct cb_gemm_desc {
     int64_t ldd2;
     int32_t d2_dtype;
     int32_t reserved1;
+    /* CB_ACT_PRELU: per-column negative slopes [N] (iresnet.py:41-58 PReLU after conv1 + bn2);
+     * d2_scale / d2_shift (optional, [N] each): the D2 copy is v * scale[col] + shift[col] -- the eval BatchNorm that the
+     * NEXT layer applies to its input (IBasicBlock.bn1, iresnet.py:47) folded into this layer's epilogue. */
+    const float* act_param;
+    const float* d2_scale;
+    const float* d2_shift;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

@@ -508,3 +508,46 @@ def test_gemm_cta_pair(dev, bn):
         assert rel(dxc, xr.grad.permute(0, 2, 3, 1).reshape(g.rows, 128)) < 2e-3
     finally:
         ops._gemm = orig
+
+
+def test_gemm_prelu_epilogue_and_d2_affine(dev):
+    """CB_ACT_PRELU (per-column slopes) and the per-column affine of the second destination: an IBasicBlock's PReLU and
+    the next block's bn1 inside the conv epilogues (iresnet.py:41-58)."""
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import CB_ACT_PRELU
+    g = ops.Geo(2, 14, 14)
+    xi = rnd(g.rows, 64)
+    wc = torch.randn(72, 64, 3, 3, device="cuda") * 0.05                       # N = 72: fast path + ragged tail
+    bias = rnd(72, dtype=torch.float32)
+    slope = torch.rand(72, device="cuda") * 0.5
+    sc, sh = torch.rand(72, device="cuda") + 0.5, rnd(72, dtype=torch.float32)
+    res = rnd(g.rows, 72, dtype=torch.float32)
+    d2 = torch.empty(g.rows, 72, dtype=torch.float16, device="cuda")
+    y, _ = ops.conv2d(xi, g, ops.pack_conv_weight(wc, torch.float16), 72, bias=bias, out_dtype=torch.float32, act=CB_ACT_PRELU,
+                      act_param=slope, residual=res, out2=d2, out2_affine=(sc, sh))
+    ref = F.conv2d(xi.float().view(2, 14, 14, 64).permute(0, 3, 1, 2), wc.half().float(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(g.rows, 72) + bias
+    ref = torch.where(ref > 0, ref, ref * slope) + res
+    assert rel(y, ref) < 2e-3 and rel(d2, ref * sc + sh) < 2e-3
+
+
+def test_iresnet_fused_epilogues_equal_unfused(dev):
+    from celebbasis_b200 import synth
+    from celebbasis_b200.iresnet_engine import IResNetEngine
+    from oracle import torch_ref
+    net = torch_ref.IResNet().eval()
+    pre = "embedding_manager.meta_id_net.id_model."
+    sd = synth.synth_state_dict(net, seed=0, prefix=pre)
+    net.load_state_dict(sd)
+    eng = IResNetEngine({pre + k: v for k, v in sd.items()}, "cuda", prefix=pre)
+    x = rnd(2 * 112 * 112, 8)
+    x[:, 3:] = 0
+    from celebbasis_b200 import ops
+    geo = ops.Geo(2, 112, 112)
+    a = eng.forward(x, geo)
+    eng.FUSE_EPILOGUES = False
+    b = eng.forward(x, geo)
+    assert rel(a, b) < 5e-3, rel(a, b)
+    with torch.no_grad():
+        ref = net.cuda()(x[:, :3].float().view(2, 112, 112, 3).permute(0, 3, 1, 2).contiguous())
+    assert rel(a, ref) < 5e-3, rel(a, ref)
