@@ -237,6 +237,10 @@ __device__ __forceinline__ void residual_unpack8(const GemmParams& p, const Resi
     }
 }
 
+// kExt: the instantiation that carries the rarely used epilogue features (second destination, PReLU slopes, D2 affine).
+// They are compiled OUT of the common instantiation: the epilogue runs once per CTA and its cost is cold instruction
+// fetch, so every extra line of straight-line code is paid by all 700+ GEMM launches of the step.
+template <bool kExt>
 __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[8], long long grow, long long brow, int col,
                                              long long d_off, long long r_off, int ncols, const float* rpre = nullptr,
                                              const float* sbias = nullptr) {
@@ -253,7 +257,14 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             for (int j = 0; j < ncols; ++j) f[j] += p.bias[brow * p.ldbias + col + j];
         }
     }
-    if (p.act != CB_ACT_NONE) apply_act8(f, p.act, p.act_param, col, ncols);
+    if (p.act != CB_ACT_NONE) {
+        if constexpr (kExt) {
+            apply_act8(f, p.act, p.act_param, col, ncols);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+        }
+    }
     if (ncols == 8 && p.vec_ok && !p.d_transposed) {
         if (rpre) {
 #pragma unroll
@@ -271,10 +282,12 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
         if (p.d_dtype == CB_F32) store8<float>(reinterpret_cast<float*>(p.D) + didx, f);
         else if (p.d_dtype == CB_F16) store8<__half>(reinterpret_cast<__half*>(p.D) + didx, f);
         else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.D) + didx, f);
-        if (p.D2) {
-            float g2[8];
-            d2_affine8(g2, f, p.d2_scale, p.d2_shift, col);
-            store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col, g2);
+        if constexpr (kExt) {
+            if (p.D2) {
+                float g2[8];
+                d2_affine8(g2, f, p.d2_scale, p.d2_shift, col);
+                store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col, g2);
+            }
         }
     } else {
         for (int j = 0; j < ncols; ++j) {
@@ -283,14 +296,17 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
             const long long didx = p.d_transposed ? (d_off + (long long)(col + j) * p.ldd + grow)
                                                   : (d_off + grow * p.ldd + col + j);
             store_any(p.D, p.d_dtype, didx, v);
-            if (p.D2) store_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + j,
-                                p.d2_scale ? v * p.d2_scale[col + j] + p.d2_shift[col + j] : v);
+            if constexpr (kExt) {
+                if (p.D2) store_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + j,
+                                    p.d2_scale ? v * p.d2_scale[col + j] + p.d2_shift[col + j] : v);
+            }
         }
     }
 }
 
 // Full 32-column chunk of one output row on the aligned fast path: bias / activation / residual on registers, then
 // 256-bit stores (one full 32-byte sector per lane and instruction) when the rows are 32-byte aligned.
+template <bool kExt>
 __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const float (&fin)[32], long long grow, long long brow,
                                                  int col, long long d_off, long long r_off, const ResidualChunk* rc,
                                                  const float* sbias) {
@@ -310,7 +326,14 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += b[j];
         }
-        if (p.act != CB_ACT_NONE) apply_act8(f, p.act, p.act_param, col + g * 8);
+        if (p.act != CB_ACT_NONE) {
+            if constexpr (kExt) {
+                apply_act8(f, p.act, p.act_param, col + g * 8);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+            }
+        }
         if (rc) {
             float r[8];
             residual_unpack8(p, *rc, g, r);
@@ -325,10 +348,12 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += r[j];
         }
-        if (p.D2) {
-            float g2[8];
-            d2_affine8(g2, f, p.d2_scale, p.d2_shift, col + g * 8);
-            store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + g * 8, g2);
+        if constexpr (kExt) {
+            if (p.D2) {
+                float g2[8];
+                d2_affine8(g2, f, p.d2_scale, p.d2_shift, col + g * 8);
+                store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + col + g * 8, g2);
+            }
         }
         if (p.d_dtype == CB_F32) {
             float* dst = reinterpret_cast<float*>(p.D) + didx + g * 8;
@@ -357,7 +382,7 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
 
 // kStages = 3: two CTAs per SM share the smem (large grids); kStages = 6: one CTA per SM with a deeper ring
 // (grids of <= one CTA per SM, where a single CTA must cover the whole TMA latency by itself).
-template <int BN, bool A_MN, bool B_MN, int kStages>
+template <int BN, bool A_MN, bool B_MN, int kStages, bool kExt>
 __global__ void __launch_bounds__(kThreads, kStages <= 3 ? 2 : 1)
 cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
@@ -539,7 +564,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(acc[j]) * p.alpha;
-                    epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                    epilogue_chunk32<kExt>(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
                 } else if (row_valid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -548,7 +573,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[g * 8 + j]) * p.alpha;
-                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                            epilogue_group8<kExt>(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
                         }
                     }
                 }
@@ -601,7 +626,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 f[4 * j] = v[j].x * p.alpha; f[4 * j + 1] = v[j].y * p.alpha;
                                 f[4 * j + 2] = v[j].z * p.alpha; f[4 * j + 3] = v[j].w * p.alpha;
                             }
-                            epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                            epilogue_chunk32<kExt>(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
                         } else {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
@@ -610,7 +635,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const float4 lo = v[2 * g], hi = v[2 * g + 1];
                                     float f[8] = {lo.x * p.alpha, lo.y * p.alpha, lo.z * p.alpha, lo.w * p.alpha,
                                                   hi.x * p.alpha, hi.y * p.alpha, hi.z * p.alpha, hi.w * p.alpha};
-                                    epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                                    epilogue_group8<kExt>(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
                                 }
                             }
                         }
@@ -655,7 +680,7 @@ struct PairCfg {
 // (batch, m-pair, n-tile) space with n fastest (consecutive clusters share the same A rows in L2).  The shared-memory
 // ring and its phases run on across tiles; the accumulator alternates between two TMEM regions so the MMAs of tile i+1
 // start while the epilogue warps of both CTAs still drain tile i (tmem_full[acc] / tmem_empty[acc] barriers).
-template <int BN, bool B_MN, int kStages>
+template <int BN, bool B_MN, int kStages, bool kExt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ GemmParams p, int n_ntiles, int n_mpairs, int total_tiles) {
@@ -852,7 +877,7 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(av[j]) * p.alpha;
-                    epilogue_chunk32(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+                    epilogue_chunk32<kExt>(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
                 } else if (row_valid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -861,7 +886,7 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(av[g * 8 + j]) * p.alpha;
-                            epilogue_group8(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                            epilogue_group8<kExt>(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
                         }
                     }
                 }
@@ -919,11 +944,13 @@ int make_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint
     return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int kStages>
-static int launch_s(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+static inline bool needs_ext(const GemmParams& p) { return p.D2 != nullptr || p.act == CB_ACT_PRELU; }
+
+template <int BN, bool A_MN, bool B_MN, int kStages, bool kExt>
+static int launch_se(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
     using Cfg = TileCfg<BN, kStages>;
     static bool attr_done = false;
-    auto kern = cb_gemm_kernel<BN, A_MN, B_MN, kStages>;
+    auto kern = cb_gemm_kernel<BN, A_MN, B_MN, kStages, kExt>;
     if (!attr_done) {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
@@ -932,6 +959,12 @@ CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
     CB_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int kStages>
+static int launch_s(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    return needs_ext(p) ? launch_se<BN, A_MN, B_MN, kStages, true>(tA, tB, p, grid, st)
+                        : launch_se<BN, A_MN, B_MN, kStages, false>(tA, tB, p, grid, st);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -948,13 +981,13 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
     }
 }
 
-template <int BN, bool B_MN>
-static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
-                       int batch, cudaStream_t st) {
+template <int BN, bool B_MN, bool kExt>
+static int launch_pair_e(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
+                         int batch, cudaStream_t st) {
     constexpr int kSt = 6;
     using Cfg = PairCfg<BN, kSt>;
     static bool attr_done = false;
-    auto kern = cb_gemm_pair_kernel<BN, B_MN, kSt>;
+    auto kern = cb_gemm_pair_kernel<BN, B_MN, kSt, kExt>;
     if (!attr_done) {
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
@@ -967,6 +1000,13 @@ static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmP
     CB_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
+}
+
+template <int BN, bool B_MN>
+static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
+                       int batch, cudaStream_t st) {
+    return needs_ext(p) ? launch_pair_e<BN, B_MN, true>(tA, tB, p, n_mpairs, n_ntiles, batch, st)
+                        : launch_pair_e<BN, B_MN, false>(tA, tB, p, n_mpairs, n_ntiles, batch, st);
 }
 
 // Measured on B200 (tools/gemm_timeline.py): one SM pulls ~80 GB/s of operand tiles out of L2, i.e. a k-iteration of a
