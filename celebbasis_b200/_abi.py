@@ -11,8 +11,8 @@ SIGS = {
     "cb_axpby2d": [_p, _i, _l, _f, _p, _i, _l, _f, _p, _i, _l, _l, _i, _p],
     "cb_act_fwd": [_p, _i, _p, _i, _l, _i, _p],
     "cb_act_bwd": [_p, _i, _p, _i, _p, _i, _l, _i, _p],
-    "cb_geglu_fwd": [_p, _p, _i, _l, _i, _p],
-    "cb_geglu_bwd": [_p, _p, _p, _i, _i, _l, _i, _p],
+    "cb_geglu_fwd": [_p, _p, _i, _l, _i, _i, _p],
+    "cb_geglu_bwd": [_p, _p, _p, _i, _i, _l, _i, _i, _p],
     "cb_softmax_fwd": [_p, _p, _i, _l, _i, _i, _i, _p],
     "cb_softmax_bwd": [_p, _p, _p, _i, _i, _l, _i, _i, _p],
     "cb_upsample2x_fwd": [_p, _p, _i, _i, _i, _i, _i, _p],

@@ -117,7 +117,7 @@ __global__ void act_bwd_kernel(const void* dy, int gdt, const void* x, int xdt, 
 
 // ---- GEGLU: out[m][f] = in[m][f] * gelu(in[m][F+f])  (ldm/modules/attention.py:37-45) ------------------------
 template <typename T>
-__global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, long long M, int F) {
+__global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, long long M, int F, int il) {
     pdl_sync();
     const int f4 = F >> 2;
     const long long total = M * f4;
@@ -126,8 +126,10 @@ __global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, 
         const long long m = i / f4;
         const int c = (int)(i - m * f4) * 4;
         float a[4], g[4], o[4];
-        V4<T>::ld(in + m * 2 * F + c, a);
-        V4<T>::ld(in + m * 2 * F + F + c, g);
+        const int ao = il ? ((c >> 5) << 6) + (c & 31) : c;       // interleaved: 64-column groups of 32 values + 32 gates
+        const int go = il ? ao + 32 : F + c;
+        V4<T>::ld(in + m * 2 * F + ao, a);
+        V4<T>::ld(in + m * 2 * F + go, g);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = a[k] * gelu_f(g[k]);
         V4<T>::st(out + m * F + c, o);
@@ -135,7 +137,7 @@ __global__ void geglu_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, 
 }
 template <typename T, typename TG>
 __global__ void geglu_bwd_kernel(const TG* __restrict__ dout, const T* __restrict__ in, TG* __restrict__ din,
-                                 long long M, int F) {
+                                 long long M, int F, int il) {
     pdl_sync();
     const int f4 = F >> 2;
     const long long total = M * f4;
@@ -144,16 +146,18 @@ __global__ void geglu_bwd_kernel(const TG* __restrict__ dout, const T* __restric
         const long long m = i / f4;
         const int c = (int)(i - m * f4) * 4;
         float a[4], g[4], d[4], da[4], dg[4];
-        V4<T>::ld(in + m * 2 * F + c, a);
-        V4<T>::ld(in + m * 2 * F + F + c, g);
+        const int ao = il ? ((c >> 5) << 6) + (c & 31) : c;
+        const int go = il ? ao + 32 : F + c;
+        V4<T>::ld(in + m * 2 * F + ao, a);
+        V4<T>::ld(in + m * 2 * F + go, g);
         V4<TG>::ld(dout + m * F + c, d);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             da[k] = d[k] * gelu_f(g[k]);
             dg[k] = d[k] * a[k] * act_grad(g[k], CB_ACT_GELU);
         }
-        V4<TG>::st(din + m * 2 * F + c, da);
-        V4<TG>::st(din + m * 2 * F + F + c, dg);
+        V4<TG>::st(din + m * 2 * F + ao, da);
+        V4<TG>::st(din + m * 2 * F + go, dg);
     }
 }
 
@@ -501,20 +505,20 @@ CB_LAUNCH((act_bwd_kernel), grid_for(n, 256), 256, 0, reinterpret_cast<cudaStrea
     return 0;
 }
 
-extern "C" int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, void* stream) {
+extern "C" int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, int interleave, void* stream) {
     CB_REQUIRE(M > 0 && F > 0 && F % 4 == 0, CB_ERR_ARG, "geglu_fwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CB_DISPATCH16(dtype, T,CB_LAUNCH((geglu_fwd_kernel<T>), grid_for(M * (F / 4), 256), 256, 0, st, (const T*)in, (T*)out, M, F));
+    CB_DISPATCH16(dtype, T,CB_LAUNCH((geglu_fwd_kernel<T>), grid_for(M * (F / 4), 256), 256, 0, st, (const T*)in, (T*)out, M, F, interleave));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;
 }
 extern "C" int cb_geglu_bwd(const void* dout, const void* in, void* din, int dtype, int g_dtype, long long M, int F,
-                            void* stream) {
+                            int interleave, void* stream) {
     CB_REQUIRE(M > 0 && F > 0 && F % 4 == 0, CB_ERR_ARG, "geglu_bwd: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CB_DISPATCH16(dtype, T, CB_DISPATCH16(g_dtype, TG,
-CB_LAUNCH((geglu_bwd_kernel<T, TG>), grid_for(M * (F / 4), 256), 256, 0, st, (const TG*)dout, (const T*)in, (TG*)din, M, F)));
+CB_LAUNCH((geglu_bwd_kernel<T, TG>), grid_for(M * (F / 4), 256), 256, 0, st, (const TG*)dout, (const T*)in, (TG*)din, M, F, interleave)));
     CB_CUDA(cudaGetLastError());
     cb::count_launches(1);
     return 0;

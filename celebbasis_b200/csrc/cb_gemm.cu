@@ -39,6 +39,7 @@ struct GemmParams {
     void* D2;          // optional second destination (same value, own dtype / row pitch)
     int d2_dtype;
     long long ldd2;
+    int glu;                   // GEGLU epilogue: column chunks come in (value, gate) pairs; D2 = value * gelu(gate)
     const float* act_param;    // CB_ACT_PRELU: per-column negative slope
     const float* d2_scale;     // optional per-column affine applied to the D2 copy only: D2 = v * scale[col] + shift[col]
     const float* d2_shift;
@@ -304,6 +305,48 @@ __device__ __forceinline__ void epilogue_group8(const GemmParams& p, float (&f)[
     }
 }
 
+// GEGLU (attention.py:37-45) inside the FF-in projection's epilogue.  The weight rows are interleaved at load time so that
+// every 64-column group of the GEMM output holds 32 value columns followed by their 32 gate columns; this thread's row of
+// such a group arrives as two accumulator chunks.  D (optional) keeps the pre-activations for the backward pass, D2
+// receives value * gelu(gate) at column (group * 32).
+__device__ __forceinline__ void epilogue_glu64(const GemmParams& p, float (&fv)[32], float (&fg)[32], long long grow, int col,
+                                               const float* sbias) {
+    uint4 pk[4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float(&f)[32] = half ? fg : fv;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float b[8];
+            if (sbias) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = sbias[half * 32 + g * 8 + j];
+            } else if (p.bias) {
+                load8<float>(p.bias + col + half * 32 + g * 8, b);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[g * 8 + j] += b[j];
+            if (p.D) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = f[g * 8 + j];
+                store8_any(p.D, p.d_dtype, grow * p.ldd + col + half * 32 + g * 8, t);
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = fv[g * 8 + j] * gelu_f(fg[g * 8 + j]);
+        store8_any(p.D2, p.d2_dtype, grow * p.ldd2 + (col >> 1) + g * 8, u);
+    }
+    (void)pk;
+}
+
 // Full 32-column chunk of one output row on the aligned fast path: bias / activation / residual on registers, then
 // 256-bit stores (one full 32-byte sector per lane and instruction) when the rows are 32-byte aligned.
 template <bool kExt>
@@ -556,6 +599,22 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int c = 0; c * 32 < ncols_tile; ++c) {
                 uint32_t acc[32];
+                if constexpr (kExt) {
+                    if (p.glu) {
+                        uint32_t acc2[32];
+                        tmem_ld_32x32(trow + c * 32, acc);
+                        tmem_ld_32x32(trow + c * 32 + 32, acc2);
+                        tmem_ld_wait();
+                        if (row_valid) {
+                            float fv[32], fg[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { fv[j] = __uint_as_float(acc[j]) * p.alpha; fg[j] = __uint_as_float(acc2[j]) * p.alpha; }
+                            epilogue_glu64(p, fv, fg, grow, n0 + c * 32, sb ? sb + c * 32 : nullptr);
+                        }
+                        ++c;
+                        continue;
+                    }
+                }
                 tmem_ld_32x32(trow + c * 32, acc);      // one TMEM round trip per 32 columns
                 const bool pre = r_fast && ncols_tile - c * 32 >= 32;
                 if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
@@ -863,6 +922,27 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
             for (int c = 0; c * 32 < ncols_tile; ++c) {
                 uint32_t av[32];
+                if constexpr (kExt) {
+                    if (p.glu) {
+                        uint32_t av2[32];
+                        tmem_ld_32x32(trow + c * 32, av);
+                        tmem_ld_32x32(trow + c * 32 + 32, av2);
+                        tmem_ld_wait();
+                        if (c * 32 + 64 >= ncols_tile) {
+                            tc_fence_before();
+                            asm volatile("bar.sync 3, 128;" ::: "memory");
+                            if (threadIdx.x == 64) mbar_arrive_cluster(tempty_bar(acc), 0);
+                        }
+                        if (row_valid) {
+                            float fv[32], fg[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { fv[j] = __uint_as_float(av[j]) * p.alpha; fg[j] = __uint_as_float(av2[j]) * p.alpha; }
+                            epilogue_glu64(p, fv, fg, grow, n0 + c * 32, sb ? sb + c * 32 : nullptr);
+                        }
+                        ++c;
+                        continue;
+                    }
+                }
                 tmem_ld_32x32(trow + c * 32, av);
                 const bool pre = r_fast && ncols_tile - c * 32 >= 32;
                 if (r_fast && ncols_tile - (c + 1) * 32 >= 32) residual_prefetch(p, r_row + (c + 1) * 32, rc_next);
@@ -944,7 +1024,7 @@ int make_tmap(CUtensorMap* out, int dtype, int rank, const void* ptr, const uint
     return 0;
 }
 
-static inline bool needs_ext(const GemmParams& p) { return p.D2 != nullptr || p.act == CB_ACT_PRELU; }
+static inline bool needs_ext(const GemmParams& p) { return p.D2 != nullptr || p.act == CB_ACT_PRELU || p.glu; }
 
 template <int BN, bool A_MN, bool B_MN, int kStages, bool kExt>
 static int launch_se(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, dim3 grid, cudaStream_t st) {
@@ -1058,7 +1138,12 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     CB_REQUIRE(dp != nullptr, CB_ERR_ARG, "cb_gemm: null desc");
     const cb_gemm_desc& d = *dp;
     CB_REQUIRE(d.ab_dtype == CB_F16 || d.ab_dtype == CB_BF16, CB_ERR_ARG, "cb_gemm: ab_dtype must be f16/bf16");
-    CB_REQUIRE(d.A && d.B && d.D, CB_ERR_ARG, "cb_gemm: null A/B/D");
+    CB_REQUIRE(d.A && d.B && (d.D || (d.glu && d.D2)), CB_ERR_ARG, "cb_gemm: null A/B/D");
+    if (d.glu) {
+        CB_REQUIRE(d.D2 && d.N % 64 == 0 && d.batch == 1 && !d.d_transposed && !d.R && d.act == CB_ACT_NONE &&
+                       d.bias_row_div == 0,
+                   CB_ERR_ARG, "cb_gemm(glu): needs D2, N %% 64 == 0, batch 1, no residual / activation / per-image bias");
+    }
     CB_REQUIRE(d.N > 0 && d.K > 0 && d.batch > 0, CB_ERR_ARG, "cb_gemm: bad N/K/batch");
     CB_REQUIRE(d.d_dtype >= CB_F16 && d.d_dtype <= CB_F32, CB_ERR_ARG, "cb_gemm: bad d_dtype");
     const int es = 2;
@@ -1148,7 +1233,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
 
     // CTA-pair variant on request (desc.cta_pair = 1; the host autotuner decides): 256 x BN tiles, K-major A, no split-K
     const bool pair = d.cta_pair == 1 && !a_mn && m_tiles >= 2 && d.N >= 64;
-    const int BN = pair ? ((d.tile_n == 128 || d.N <= 128) ? 128 : 256) : pick_bn(d, m_tiles, p.taps * p.kchunks);
+    int BN = pair ? ((d.tile_n == 128 || d.N <= 128) ? 128 : 256) : pick_bn(d, m_tiles, p.taps * p.kchunks);
+    if (d.glu && BN % 64 != 0) BN = 128;        // (value, gate) column pairs live in 64-column groups
     const int b_box_rows = pair ? BN / 2 : BN;
     p.b_bytes = (unsigned)b_box_rows * BK * es;
     {
@@ -1188,6 +1274,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         CB_REQUIRE((reinterpret_cast<uintptr_t>(d.D2) & 15u) == 0 && (d.ldd2 * es2) % 16 == 0 && d.ldd2 >= d.N, CB_ERR_ALIGN,
                    "cb_gemm: D2 must be 16-byte aligned with a 16-byte multiple row pitch >= N");
     }
+    p.glu = d.glu;
     p.act_param = d.act_param;
     p.d2_scale = d.d2_scale;
     p.d2_shift = d.d2_shift;
@@ -1242,7 +1329,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         const long long counters_bytes = 65536;
         const long long avail = d.splitk_ws_bytes - counters_bytes;
         const bool ws_ok = d.splitk_ws != nullptr && tiles <= counters_bytes / 4 && tiles * (long long)(BM * BN * 4) <= avail;
-        if (ws_ok && (d.splits > 0 || (tiles < sms && kiters >= 8))) {
+        if (ws_ok && !d.glu && (d.splits > 0 || (tiles < sms && kiters >= 8))) {
             const double out_elems = (double)p.M * d.batch * d.N;
             double best_t = tile_time_us(BN, tiles, kiters, sms);
             int best_sp = 1;

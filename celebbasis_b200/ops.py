@@ -81,7 +81,8 @@ TUNE_LOG = None     # set to a list to collect (key, table of candidate times)
 def _tune_key(d):
     return (d.M, d.N, d.K, d.batch, d.batch_inner, d.ab_dtype, d.a_major, d.b_major, d.conv, d.img_n, d.img_h, d.img_w,
             d.out_h, d.out_w, d.kh, d.kw, d.stride, d.flip_taps, d.d_dtype, d.d_transposed, 1 if d.R else 0, d.r_dtype,
-            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd, (d.d2_dtype + 1) if d.D2 else 0, 1 if d.d2_scale else 0)
+            1 if d.bias else 0, d.act, d.lda, d.ldb, d.ldd, (d.d2_dtype + 1) if d.D2 else 0, 1 if d.d2_scale else 0, d.glu,
+            1 if d.D else 0)
 
 
 def _set_out2(d, out2, out2_affine=None, act_param=None):
@@ -135,7 +136,7 @@ def _autotune(d, key):
         _tune_scratch.pop(dev, None)
         sc = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device="cuda")
         _tune_scratch[dev] = sc
-    t.D, t.R = sc.data_ptr(), None
+    t.D, t.R = (sc.data_ptr() if d.D else None), None
     if d.D2:
         off = (nbytes + 255) // 256 * 256
         n2 = int(d.ldd2 * M + d.N + 64) * (4 if d.d2_dtype == CB_F32 else 2)
@@ -507,18 +508,53 @@ def act_bwd(dy, x, act, out_dtype=None):
     return dx
 
 
-def geglu(x):
+def geglu(x, interleaved=False):
     M, F2 = x.shape
     y = torch.empty(M, F2 // 2, dtype=x.dtype, device=x.device)
-    _lib.check(_L().cb_geglu_fwd(_p(x), _p(y), _dt(x), M, F2 // 2, _st()), "cb_geglu_fwd")
+    _lib.check(_L().cb_geglu_fwd(_p(x), _p(y), _dt(x), M, F2 // 2, 1 if interleaved else 0, _st()), "cb_geglu_fwd")
     return y
 
 
-def geglu_bwd(dy, x):
+def geglu_bwd(dy, x, interleaved=False):
     M, F2 = x.shape
     dx = torch.empty(M, F2, dtype=dy.dtype, device=x.device)
-    _lib.check(_L().cb_geglu_bwd(_p(dy), _p(x), _p(dx), _dt(x), _dt(dy), M, F2 // 2, _st()), "cb_geglu_bwd")
+    _lib.check(_L().cb_geglu_bwd(_p(dy), _p(x), _p(dx), _dt(x), _dt(dy), M, F2 // 2, 1 if interleaved else 0, _st()),
+               "cb_geglu_bwd")
     return dx
+
+
+def glu_interleave_rows(w):
+    """[2F][...] rows ordered [all values | all gates] -> 64-row groups of 32 value rows followed by their 32 gate rows
+    (F % 32 == 0): the layout the GEGLU epilogue of cb_gemm expects for the FF-in projection (attention.py:37-45)."""
+    F2 = w.shape[0]
+    F = F2 // 2
+    assert F % 32 == 0
+    v = w[:F].reshape(F // 32, 32, *w.shape[1:])
+    g = w[F:].reshape(F // 32, 32, *w.shape[1:])
+    return torch.cat([v, g], dim=1).reshape(w.shape).contiguous()
+
+
+def linear_geglu(x, w_il, bias_il, *, keep_preact=True):
+    """u = (x W_v^T + b_v) * gelu(x W_g^T + b_g) with W = interleaved FF-in weight (glu_interleave_rows): ONE GEMM launch
+    whose epilogue applies the GEGLU.  Returns (u [M][F], pre-activations [M][2F] in the interleaved layout or None)."""
+    M, K = x.shape
+    N = w_il.shape[0]
+    assert w_il.shape[1] == K and N % 64 == 0 and x.is_contiguous()
+    u = torch.empty(M, N // 2, dtype=x.dtype, device=x.device)
+    g = torch.empty(M, N, dtype=x.dtype, device=x.device) if keep_preact else None
+    d = GemmDesc()
+    d.M, d.N, d.K, d.batch, d.ab_dtype = M, N, K, 1, _dt(x)
+    d.A, d.lda, d.a_major = x.data_ptr(), K, CB_MAJOR_K
+    d.B, d.ldb, d.b_major = w_il.data_ptr(), K, CB_MAJOR_K
+    if g is not None:
+        d.D, d.ldd = g.data_ptr(), N
+    d.d_dtype = _dt(u)
+    if bias_il is not None:
+        d.bias, d.bias_row_div, d.ldbias = bias_il.data_ptr(), 0, N
+    d.alpha, d.glu = 1.0, 1
+    d.D2, d.d2_dtype, d.ldd2 = u.data_ptr(), _dt(u), N // 2
+    _gemm(d, "cb_gemm(linear_geglu)")
+    return u, g
 
 
 def softmax_(s, rows, ncols, ld, causal_period=0):

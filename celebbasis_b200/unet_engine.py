@@ -224,7 +224,9 @@ class UNetEngine:
             w["kv_off"] = self._kv_off          # this block's [K | V] columns in the batched context projection
             self._kv_off += 2 * c
             w["wo2"], w["bo2"] = self._w16(g(tb + "attn2.to_out.0.weight")), self._f32(g(tb + "attn2.to_out.0.bias"))
-            w["wff1"], w["bff1"] = self._w16(g(tb + "ff.net.0.proj.weight")), self._f32(g(tb + "ff.net.0.proj.bias"))
+            # GEGLU in the FF-in GEMM's epilogue: rows interleaved into (32 values, 32 gates) groups (ops.linear_geglu)
+            w["wff1"] = self._w16(ops.glu_interleave_rows(g(tb + "ff.net.0.proj.weight")))
+            w["bff1"] = self._f32(ops.glu_interleave_rows(g(tb + "ff.net.0.proj.bias")))
             w["wff2"], w["bff2"] = self._w16(g(tb + "ff.net.2.weight")), self._f32(g(tb + "ff.net.2.bias"))
             w["wpo"], w["bpo"] = self._w16(g(prefix + "proj_out.weight").reshape(c, c)), self._f32(g(prefix + "proj_out.bias"))
             return w
@@ -344,8 +346,7 @@ class UNetEngine:
         h2 = ops.linear(o2, w["wo2"], w["bo2"], out_dtype=torch.float32, residual=h1)
         # GEGLU feed-forward
         l3, s3 = ops.layernorm(h2, w["ln3g"], w["ln3b"], out_dtype=self.dt)
-        g16 = ops.linear(l3, w["wff1"], w["bff1"])
-        u16 = ops.geglu(g16)
+        u16, g16 = ops.linear_geglu(l3, w["wff1"], w["bff1"], keep_preact=tape is not None)
         h3 = ops.linear(u16, w["wff2"], w["bff2"], out_dtype=self.dt, residual=h2)
         out = ops.linear(h3, w["wpo"], w["bpo"], out_dtype=torch.float32, residual=x, out=out, out2=out2)
         if tape is not None:
@@ -365,7 +366,7 @@ class UNetEngine:
         dx16 = torch.empty(dout.shape, dtype=self.dt, device=self.dev) if to_input else None
         # feed-forward
         du = ops.linear_dgrad(ops.cast(dr, self.dt), w["wff2"])
-        dg = ops.geglu_bwd(du, g16)
+        dg = ops.geglu_bwd(du, g16, interleaved=True)
         dl3 = ops.linear_dgrad(dg, w["wff1"])
         dr16 = torch.empty(dr.shape, dtype=self.dt, device=self.dev)      # 16-bit copy of the running gradient, written
         ops.layernorm_bwd(dl3, h2, w["ln3g"], s3, dx=dr, accumulate=True, dx_lp=dr16)   # by the kernel that updates it

@@ -154,7 +154,10 @@ typedef struct cb_gemm_desc {
     void* D2;
     int64_t ldd2;
     int32_t d2_dtype;
-    int32_t reserved1;
+    int32_t glu;         /* 1 = GEGLU epilogue (attention.py:37-45): the N output columns are 64-column groups of 32 value
+                          * columns followed by their 32 gate columns (weight rows interleaved by the caller);
+                          * D2[row][32*group + j] = (value + bias) * gelu(gate + bias); D (may be NULL) keeps the
+                          * pre-activations in that interleaved layout for cb_geglu_bwd(interleave = 1) */
     /* CB_ACT_PRELU: per-column negative slopes [N] (iresnet.py:41-58 PReLU after conv1 + bn2);
      * d2_scale / d2_shift (optional, [N] each): the D2 copy is v * scale[col] + shift[col] -- the eval BatchNorm that the
      * NEXT layer applies to its input (IBasicBlock.bn1, iresnet.py:47) folded into this layer's epilogue. */
@@ -213,9 +216,11 @@ int cb_axpby2d(const void* x, int x_dtype, long long ldx, float a, const void* y
 int cb_act_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long n, int act, void* stream);
 int cb_act_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype, long long n, int act,
                void* stream);
-int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, void* stream);
+/* interleave = 1: `in` / `din` rows are 64-column groups of 32 values followed by their 32 gates (the layout the GEGLU
+ * epilogue of cb_gemm keeps), instead of [all values | all gates] */
+int cb_geglu_fwd(const void* in, void* out, int dtype, long long M, int F, int interleave, void* stream);
 int cb_geglu_bwd(const void* dout, const void* in, void* din, int dtype, int g_dtype, long long M, int F,
-                 void* stream);
+                 int interleave, void* stream);
 int cb_softmax_fwd(const void* s, void* p, int dtype, long long rows, int ncols, int ld, int causal_period,
                    void* stream);
 int cb_softmax_bwd(const void* dp, const void* p, void* ds, int p_dtype, int g_dtype, long long rows, int ncols,

@@ -551,3 +551,30 @@ def test_iresnet_fused_epilogues_equal_unfused(dev):
     with torch.no_grad():
         ref = net.cuda()(x[:, :3].float().view(2, 112, 112, 3).permute(0, 3, 1, 2).contiguous())
     assert rel(a, ref) < 5e-3, rel(a, ref)
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (256, 1280), (70, 64)])
+def test_linear_geglu_epilogue(dev, M, C):
+    """GEGLU (attention.py:37-45: x, gate = proj(x).chunk(2); x * gelu(gate)) inside the FF-in GEMM's epilogue on the
+    interleaved weight layout; the kept pre-activations feed cb_geglu_bwd(interleave=1)."""
+    from celebbasis_b200 import ops
+    x = rnd(M, C)
+    w = rnd(8 * C, C, scale=C ** -0.5)
+    b = rnd(8 * C, dtype=torch.float32) * 0.1
+    w_il = ops.glu_interleave_rows(w).contiguous()
+    b_il = ops.glu_interleave_rows(b).contiguous()
+    u, g = ops.linear_geglu(x, w_il, b_il, keep_preact=True)
+    pre = x.float() @ w.float().t() + b
+    a_ref, g_ref = pre.chunk(2, -1)
+    u_ref = a_ref * F.gelu(g_ref)
+    assert rel(u, u_ref) < 3e-3, rel(u, u_ref)
+    assert rel(g, ops.glu_interleave_rows(pre.t()).t()) < 2e-3
+    u2, g2 = ops.linear_geglu(x, w_il, b_il, keep_preact=False)        # inference: no pre-activation store
+    assert g2 is None and rel(u2, u_ref) < 3e-3
+    assert rel(ops.geglu(g, interleaved=True), u_ref) < 3e-3
+    du = rnd(M, 4 * C)
+    dg = ops.geglu_bwd(du, g, interleaved=True)
+    pr = pre.clone().requires_grad_(True)
+    a2, g2r = pr.chunk(2, -1)
+    (a2 * F.gelu(g2r)).backward(du.float())
+    assert rel(dg, ops.glu_interleave_rows(pr.grad.t()).t()) < 5e-3
