@@ -1271,8 +1271,9 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
         CB_REQUIRE(d.batch == 1 && !d.d_transposed, CB_ERR_ARG, "cb_gemm: D2 needs batch == 1 and a non-transposed D");
         CB_REQUIRE(d.d2_dtype >= CB_F16 && d.d2_dtype <= CB_F32, CB_ERR_ARG, "cb_gemm: bad d2_dtype");
         const int es2 = d.d2_dtype == CB_F32 ? 4 : 2;
-        CB_REQUIRE((reinterpret_cast<uintptr_t>(d.D2) & 15u) == 0 && (d.ldd2 * es2) % 16 == 0 && d.ldd2 >= d.N, CB_ERR_ALIGN,
-                   "cb_gemm: D2 must be 16-byte aligned with a 16-byte multiple row pitch >= N");
+        CB_REQUIRE((reinterpret_cast<uintptr_t>(d.D2) & 15u) == 0 && (d.ldd2 * es2) % 16 == 0 &&
+                       d.ldd2 >= (d.glu ? d.N / 2 : d.N),
+                   CB_ERR_ALIGN, "cb_gemm: D2 must be 16-byte aligned with a 16-byte multiple row pitch >= N (N/2 with glu)");
     }
     p.glu = d.glu;
     p.act_param = d.act_param;
