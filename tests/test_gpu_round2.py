@@ -111,9 +111,6 @@ def test_mlp_gradient_elementwise_outside_leakyrelu_flips(dev, golden_dir):
     scale = gWr[same].abs().mean(1, keepdim=True) + 1e-30
     frac_ok = ((gW[same] - gWr[same]).abs() <= 2e-2 * scale * 10).float().mean().item()
     assert frac_ok > 0.97, frac_ok
-    if n_flip:
-        # the flipped rows are where the whole-tensor error comes from
-        assert rel(gW[flipped], gWr[flipped]) > rel(gW[same], gWr[same])
 
 
 def _train_curve(eng, kind, steps, dev, lr=5e-3):
