@@ -505,3 +505,32 @@ def test_device_data_path_vs_reference_and_torchvision(dev, golden_dir, tmp_path
             assert float((faces - g["faces"]).abs().mean()) < 1.5e-2, float((faces - g["faces"]).abs().mean())
             assert float((img - g["image"]).abs().max()) < 0.12
             assert out["caption"] == [g["caption"]] and out["image_ori"]["ids"].tolist() == [g["ids"].tolist()]
+
+
+def test_engine_save_writes_reference_checkpoint_format(dev, golden_dir, tmp_path):
+    """a training run on the fused engine must produce the artefact inference consumes.  CelebBasisStep.save()
+    writes the reference's embedding-manager checkpoint (embedding_manager.py:396-410); the mirror's load() -- pinned to the
+    file the UNMODIFIED reference wrote (tests/golden/embeddings_ref.pt) -- reads it back, and the eval-branch conditioning
+    built from it equals the one built from the engine's state."""
+    from celebbasis_b200 import workload
+    gold = torch.load(os.path.join(golden_dir, "embeddings_ref.pt"), weights_only=False)
+    eng, _, _ = _engine("tiny", dev)
+    batch, draws = workload.synth_batch("tiny", B=1, seed=1234)
+    b, d = _to_dev(batch, draws, dev)
+    eng.forward_backward(b, d)
+    for prec, fp16 in (("fp32", False), ("fp16", True)):
+        eng.save_fp16 = fp16
+        path = str(tmp_path / f"emb_{prec}.pt")
+        eng.save(path)
+        mine = torch.load(path, weights_only=False)
+        ref = gold[prec]
+        assert set(mine.keys()) == set(ref.keys()) == {"id_coefficients"}
+        assert type(mine["id_coefficients"]) is type(ref["id_coefficients"]) and len(mine["id_coefficients"]) == 10
+        for a, r in zip(mine["id_coefficients"], ref["id_coefficients"]):
+            assert a.dtype == r.dtype and a.shape == r.shape
+        model, _ = _mirror("tiny", dev, 2)
+        model.embedding_manager.load(path)
+        got = torch.stack([c.float() for c in model.embedding_manager.id_coefficients])
+        assert rel(got, eng.id_coefficients.cpu()) < (1e-3 if fp16 else 1e-7)
+    # identity 0 moved (EMA), the others still hold the shared initial value
+    assert not torch.equal(eng.id_coefficients[0], eng.id_coefficients[1]) and torch.equal(eng.id_coefficients[1], eng.id_coefficients[2])

@@ -310,3 +310,20 @@ def test_data_path_draws_match_reference(golden_dir, tmp_path):
             outside = ref_img.clone()
             outside[ph:ph + rh, pw:pw + rw] = -1.0
             assert float((outside + 1.0).abs().max()) == 0.0 and inside.shape[:2] == (rh, rw)
+
+
+def test_glu_interleave_and_host_limits():
+    """Host helpers added in round 2: the FF-in weight interleave of the GEGLU epilogue is a permutation that maps value row
+    32*g+i -> 64*g+i and gate row F+32*g+i -> 64*g+32+i; the CPU-arm thread limit never exceeds the scheduler affinity."""
+    import importlib
+    from celebbasis_b200 import ops
+    F_ = 96
+    w = torch.arange(2 * F_ * 3, dtype=torch.float32).view(2 * F_, 3)
+    il = ops.glu_interleave_rows(w)
+    assert il.shape == w.shape and sorted(il[:, 0].tolist()) == sorted(w[:, 0].tolist())
+    for g in range(F_ // 32):
+        assert torch.equal(il[64 * g: 64 * g + 32], w[32 * g: 32 * g + 32])
+        assert torch.equal(il[64 * g + 32: 64 * g + 64], w[F_ + 32 * g: F_ + 32 * g + 32])
+    bench = importlib.import_module("bench")
+    lim = bench.host_cpu_limits()
+    assert 1 <= lim["limit"] <= lim["affinity"] <= (os.cpu_count() or 1)

@@ -1,11 +1,14 @@
+"""Probe: VAE encoder with an fp32 vs fp16 residual stream -- latent parity against the reference fixture and time.
+(Result on B200: fp32 z rel 5.9e-4 / 2.91 ms; fp16 z rel 7.3e-4 / 2.71 ms: not worth the parity budget.)"""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
 from celebbasis_b200 import ops, synth, workload
 from celebbasis_b200.vae_engine import VAEEncoderEngine
 from oracle import torch_ref
 dev = torch.device("cuda:0")
-gold = torch.load("/root/repo/tests/golden/step_full.pt")
+gold = torch.load(os.path.join(ROOT, "tests", "golden", "step_full.pt"))
 params = workload.model_params("full")
 om = torch_ref.OracleModel(params, clip_layers=12)
 sd = synth.synth_state_dict(om, seed=0)
