@@ -63,6 +63,7 @@ struct GemmParams {
     int splits, kiters_per_split;
     float* ws;
     unsigned* counters;
+    int ws_tr;                // accumulator-tile layout in ws: 1 = float4-group-major (coalesced warp requests), 0 = row-major
     int dbg_mode;             // tuning aid (env CB_GEMM_DBG_MODE): 1 exit after setup, 2 skip epilogue, 3 exit at once
     unsigned long long* dbg;  // optional per-CTA timeline (8 x u64 globaltimer ns per CTA), NULL in production
 };
@@ -423,6 +424,85 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const floa
     }
 }
 
+// ---- split-K hand-off (epilogue warps, 128 threads; shared by the single-CTA and the CTA-pair kernels): every CTA adds its
+//      fp32 partial tile into one L2-resident accumulator tile with vector reductions (red.global.add.v4.f32, spread over
+//      all L2 slices); the last CTA to arrive (per-tile counter) reads the sum, runs the epilogue and re-zeroes tile +
+//      counter for the next launch.  `tmem_done()` runs once this thread's last TMEM read has completed.
+//      accumulator-tile layout (p.ws_tr): float4 group g (= 4 columns) of row r lives at ((g * BM) + r) * 4 floats, so the
+//      32 lanes of a warp (32 consecutive rows) touch 512 contiguous bytes per reduction / load / store -- four full
+//      128-byte lines instead of 32 half-sectors of 32 different lines (L2 reduction throughput is per request);
+//      ws_tr = 0 keeps the row-major tile (row pitch BN floats).
+template <int BN, bool kExt, typename TmemDone>
+__device__ __forceinline__ void splitk_reduce_epilogue(const GemmParams& p, unsigned tile_id, uint32_t trow, int r,
+                                                       bool row_valid, long long grow, long long brow, int n0, int ncols_tile,
+                                                       long long d_off, long long r_off, const float* sb, bool r_fast,
+                                                       long long r_row, TmemDone tmem_done) {
+    const int rs = p.ws_tr ? 4 : BN;             // floats between consecutive rows of one float4 group
+    const int gs = p.ws_tr ? BM * 4 : 4;         // floats between consecutive float4 groups of one row
+    float* mine = p.ws + static_cast<size_t>(tile_id) * (BM * BN) + static_cast<size_t>(r) * rs;
+    ResidualChunk rc_cur;
+#pragma unroll 1
+    for (int c = 0; c * 32 < ncols_tile; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(trow + c * 32, acc);
+        tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + (c * 8 + (j >> 2)) * gs),
+                             "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
+                             "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
+                             : "memory");
+        }
+    }
+    tmem_done();
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 64) {
+        const unsigned prev = atomicAdd(p.counters + tile_id, 1u);
+        s_last = (prev == static_cast<unsigned>(p.splits) - 1u) ? 1u : 0u;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const bool last = s_last != 0u;
+    asm volatile("bar.sync 1, 128;" ::: "memory");      // s_last is rewritten by the next tile of a persistent CTA
+    if (!last) return;
+    __threadfence();
+    if (row_valid) {
+#pragma unroll 1
+        for (int c = 0; c * 32 < ncols_tile; ++c) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + (c * 8 + j) * gs));   // 8 loads in flight
+            const bool pre = r_fast && ncols_tile - c * 32 >= 32;
+            if (pre) residual_prefetch(p, r_row + c * 32, rc_cur);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) __stcg(reinterpret_cast<float4*>(mine + (c * 8 + j) * gs), make_float4(0.f, 0.f, 0.f, 0.f));
+            if (p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    f[4 * j] = v[j].x * p.alpha; f[4 * j + 1] = v[j].y * p.alpha;
+                    f[4 * j + 2] = v[j].z * p.alpha; f[4 * j + 3] = v[j].w * p.alpha;
+                }
+                epilogue_chunk32<kExt>(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int nc = min(8, ncols_tile - c * 32 - g * 8);
+                    if (nc > 0) {
+                        const float4 lo = v[2 * g], hi = v[2 * g + 1];
+                        float f[8] = {lo.x * p.alpha, lo.y * p.alpha, lo.z * p.alpha, lo.w * p.alpha,
+                                      hi.x * p.alpha, hi.y * p.alpha, hi.z * p.alpha, hi.w * p.alpha};
+                        epilogue_group8<kExt>(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
+                    }
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
+}
+
 // kStages = 3: two CTAs per SM share the smem (large grids); kStages = 6: one CTA per SM with a deeper ring
 // (grids of <= one CTA per SM, where a single CTA must cover the whole TMA latency by itself).
 template <int BN, bool A_MN, bool B_MN, int kStages, bool kExt>
@@ -639,69 +719,9 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 rc_cur = rc_next;
             }
         } else {
-            // ---- split-K: every CTA adds its fp32 partial tile into one L2-resident accumulator tile with vector
-            //      reductions (red.global.add.v4.f32, spread over all L2 slices); the last CTA to arrive (per-tile
-            //      counter) reads the sum, runs the epilogue and re-zeroes tile + counter for the next launch.
             const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
-            float* mine = p.ws + static_cast<size_t>(tile_id) * (BM * BN) + static_cast<size_t>(r) * BN;
-#pragma unroll 1
-            for (int c = 0; c * 32 < ncols_tile; ++c) {
-                uint32_t acc[32];
-                tmem_ld_32x32(trow + c * 32, acc);
-                tmem_ld_wait();
-                if (row_valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mine + c * 32 + j),
-                                     "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
-                                     "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
-                                     : "memory");
-                }
-            }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            __shared__ unsigned s_last;
-            if (threadIdx.x == 64) {
-                const unsigned prev = atomicAdd(p.counters + tile_id, 1u);
-                s_last = (prev == static_cast<unsigned>(p.splits) - 1u) ? 1u : 0u;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_last) {
-                __threadfence();
-                if (row_valid) {
-#pragma unroll 1
-                    for (int c = 0; c * 32 < ncols_tile; ++c) {
-                        float4 v[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + c * 32 + j * 4));   // 8 loads in flight
-                        const bool pre = r_fast && ncols_tile - c * 32 >= 32;
-                        if (pre) residual_prefetch(p, r_row + c * 32, rc_cur);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) __stcg(reinterpret_cast<float4*>(mine + c * 32 + j * 4), make_float4(0.f, 0.f, 0.f, 0.f));
-                        if (p.vec_ok && !p.d_transposed && ncols_tile - c * 32 >= 32) {
-                            float f[32];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                f[4 * j] = v[j].x * p.alpha; f[4 * j + 1] = v[j].y * p.alpha;
-                                f[4 * j + 2] = v[j].z * p.alpha; f[4 * j + 3] = v[j].w * p.alpha;
-                            }
-                            epilogue_chunk32<kExt>(p, f, grow, brow, n0 + c * 32, d_off, r_off, pre ? &rc_cur : nullptr, sb ? sb + c * 32 : nullptr);
-                        } else {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const int nc = min(8, ncols_tile - c * 32 - g * 8);
-                                if (nc > 0) {
-                                    const float4 lo = v[2 * g], hi = v[2 * g + 1];
-                                    float f[8] = {lo.x * p.alpha, lo.y * p.alpha, lo.z * p.alpha, lo.w * p.alpha,
-                                                  hi.x * p.alpha, hi.y * p.alpha, hi.z * p.alpha, hi.w * p.alpha};
-                                    epilogue_group8<kExt>(p, f, grow, brow, n0 + c * 32 + g * 8, d_off, r_off, nc, nullptr, sb ? sb + c * 32 + g * 8 : nullptr);
-                                }
-                            }
-                        }
-                    }
-                }
-                if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
-            }
+            splitk_reduce_epilogue<BN, kExt>(p, tile_id, trow, r, row_valid, grow, brow, n0, ncols_tile, d_off, r_off, sb,
+                                             r_fast, r_row, [] {});
         }
     }
 
@@ -723,7 +743,9 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // of the tensor peak on the large-M GEMMs (VAE 512^2/256^2 convolutions, CFG-batched inference).
 //   * TMA loads of both CTAs credit their bytes to the LEADER's full[] barrier (.cta_group::2, peer bit cleared);
 //   * tcgen05.commit.multicast frees the stage in both CTAs and publishes the accumulator to both epilogues;
-//   * each CTA's epilogue reads its own 128 TMEM lanes.  No split-K in this variant.
+//   * each CTA's epilogue reads its own 128 TMEM lanes;
+//   * split-K (desc.splits > 1): the work items are (tile, k-slice) with the slice fastest, so the slices of one tile run
+//     on neighbouring clusters at the same time; each CTA of a pair reduces its 128 rows into its own workspace tile.
 // ---------------------------------------------------------------------------------------------
 template <int BN, int kStages>
 struct PairCfg {
@@ -742,7 +764,7 @@ struct PairCfg {
 template <int BN, bool B_MN, int kStages, bool kExt>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ GemmParams p, int n_ntiles, int n_mpairs, int total_tiles) {
+                    const __grid_constant__ GemmParams p, int n_ntiles, int n_mpairs, int total_items) {
     using Cfg = PairCfg<BN, kStages>;
     constexpr int HN = BN / 2;
     extern __shared__ uint8_t smem_raw[];
@@ -810,13 +832,15 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             // ===================== TMA producer (both CTAs) =====================
             int git = 0;
-            for (int t = cid; t < total_tiles; t += nclusters) {
+            for (int w = cid; w < total_items; w += nclusters) {
+                const int t = w / p.splits, sp = w - t * p.splits;
+                const int it0 = sp * p.kiters_per_split, it1 = min(kiters, it0 + p.kiters_per_split);
                 int bz, m_tile, n0, m0, ow0, oh0, img0;
                 tile_coords(t, bz, m_tile, n0);
                 tile_origin(m_tile, m0, ow0, oh0, img0);
                 const int zi = bz % p.batch_inner, zo = bz / p.batch_inner;
                 const int nh = n0 + (int)rank * HN;          // this CTA's half of the B tile
-                for (int it = 0; it < kiters; ++it, ++git) {
+                for (int it = it0; it < it1; ++it, ++git) {
                     const int s = git % kStages;
                     const uint32_t ph = (git / kStages) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1u);
@@ -848,12 +872,14 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0 && leader) {
             // ===================== MMA issuer (leader CTA only) =====================
             int git = 0, lt = 0;
-            for (int t = cid; t < total_tiles; t += nclusters, ++lt) {
+            for (int w = cid; w < total_items; w += nclusters, ++lt) {
+                const int sp = w % p.splits;
+                const int it0 = sp * p.kiters_per_split, it1 = min(kiters, it0 + p.kiters_per_split);
                 const int acc = lt & 1;
                 mbar_wait(tempty_bar(acc), (((unsigned)lt >> 1) & 1u) ^ 1u);      // both epilogues drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
-                for (int it = 0; it < kiters; ++it, ++git) {
+                for (int it = it0; it < it1; ++it, ++git) {
                     const int s = git % kStages;
                     const uint32_t ph = (git / kStages) & 1;
                     mbar_wait(full_bar(s), ph);
@@ -866,7 +892,7 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t adesc = umma_smem_desc_sw128(a_src + k * 32, 16, 1024);
                         const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(b_src + k * 2048, 8192, 1024)
                                                     : umma_smem_desc_sw128(b_src + k * 32, 16, 1024);
-                        umma_f16_pair(d_tmem, adesc, bdesc, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_f16_pair(d_tmem, adesc, bdesc, p.idesc, (it > it0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit_pair(empty_bar(s));        // frees this stage in BOTH CTAs once the MMAs above retire
                 }
@@ -879,7 +905,8 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int r = q * 32 + lane;
         __shared__ __align__(16) float s_bias[BN + 8];
         int lt = 0;
-        for (int t = cid; t < total_tiles; t += nclusters, ++lt) {
+        for (int w = cid; w < total_items; w += nclusters, ++lt) {
+            const int t = w / p.splits;
             const int acc = lt & 1;
             int bz, m_tile, n0, m0, ow0, oh0, img0;
             tile_coords(t, bz, m_tile, n0);
@@ -915,10 +942,21 @@ cb_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const bool r_fast = p.R && p.vec_ok && !p.d_transposed && row_valid;
             const long long r_row = r_off + grow * p.ldr + n0;
             ResidualChunk rc_cur, rc_next;
-            if (r_fast && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);
+            if (r_fast && p.splits == 1 && ncols_tile >= 32) residual_prefetch(p, r_row, rc_cur);
             mbar_wait(tfull_bar(acc), ((unsigned)lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(acc * Cfg::kAccCols) + (static_cast<uint32_t>(q * 32) << 16);
+            if (p.splits > 1) {
+                // this CTA's 128 rows of the tile have their own workspace tile and arrival counter
+                splitk_reduce_epilogue<BN, kExt>(p, static_cast<unsigned>(t) * 2u + rank, trow, r, row_valid, grow, brow, n0,
+                                                 ncols_tile, d_off, r_off, sb, r_fast, r_row, [&] {
+                    tc_fence_before();                  // accumulator drained: hand it back before the L2 hand-off
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (threadIdx.x == 64) mbar_arrive_cluster(tempty_bar(acc), 0);
+                });
+                if (p.bias) asm volatile("bar.sync 2, 128;" ::: "memory");
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c * 32 < ncols_tile; ++c) {
                 uint32_t av[32];
@@ -1063,7 +1101,7 @@ static int launch(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams
 
 template <int BN, bool B_MN, bool kExt>
 static int launch_pair_e(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
-                         int batch, cudaStream_t st) {
+                         int batch, int max_ctas, cudaStream_t st) {
     constexpr int kSt = 6;
     using Cfg = PairCfg<BN, kSt>;
     static bool attr_done = false;
@@ -1072,9 +1110,12 @@ static int launch_pair_e(const CUtensorMap& tA, const CUtensorMap& tB, const Gem
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
-    const long long total = (long long)n_mpairs * n_ntiles * batch;
+    const long long total = (long long)n_mpairs * n_ntiles * batch * p.splits;       // work items: (tile, k-slice)
     CB_REQUIRE(total < (1ll << 30), CB_ERR_ARG, "cb_gemm(pair): too many tiles");
-    const int clusters = (int)std::min<long long>(total, device_sm_count() / 2);
+    // persistent grid: one cluster per SM pair, or fewer on request (desc.cta_pair = n >= 2: a throughput-bound producer
+    // that shares the device with a latency-bound chain leaves the other SMs to it)
+    const int cap = max_ctas >= 2 ? std::min(max_ctas, device_sm_count()) : device_sm_count();
+    const int clusters = (int)std::min<long long>(total, cap / 2);
     dim3 grid((unsigned)(2 * clusters));
     CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p, n_ntiles, n_mpairs, (int)total);
     CB_CUDA(cudaGetLastError());
@@ -1084,9 +1125,9 @@ static int launch_pair_e(const CUtensorMap& tA, const CUtensorMap& tB, const Gem
 
 template <int BN, bool B_MN>
 static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int n_mpairs, int n_ntiles,
-                       int batch, cudaStream_t st) {
-    return needs_ext(p) ? launch_pair_e<BN, B_MN, true>(tA, tB, p, n_mpairs, n_ntiles, batch, st)
-                        : launch_pair_e<BN, B_MN, false>(tA, tB, p, n_mpairs, n_ntiles, batch, st);
+                       int batch, int max_ctas, cudaStream_t st) {
+    return needs_ext(p) ? launch_pair_e<BN, B_MN, true>(tA, tB, p, n_mpairs, n_ntiles, batch, max_ctas, st)
+                        : launch_pair_e<BN, B_MN, false>(tA, tB, p, n_mpairs, n_ntiles, batch, max_ctas, st);
 }
 
 // Measured on B200 (tools/gemm_timeline.py): one SM pulls ~80 GB/s of operand tiles out of L2, i.e. a k-iteration of a
@@ -1232,7 +1273,7 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     }
 
     // CTA-pair variant on request (desc.cta_pair = 1; the host autotuner decides): 256 x BN tiles, K-major A, no split-K
-    const bool pair = d.cta_pair == 1 && !a_mn && m_tiles >= 2 && d.N >= 64;
+    const bool pair = d.cta_pair >= 1 && !a_mn && m_tiles >= 2 && d.N >= 64;
     int BN = pair ? ((d.tile_n == 128 || d.N <= 128) ? 128 : 256) : pick_bn(d, m_tiles, p.taps * p.kchunks);
     if (d.glu && BN % 64 != 0) BN = 128;        // (value, gate) column pairs live in 64-column groups
     const int b_box_rows = pair ? BN / 2 : BN;
@@ -1320,6 +1361,10 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
 
     // ---- split-K heuristic: fill the 148 SMs when the tile grid alone cannot (bs=1 low-resolution layers) ----
     p.force_stages = (d.stages == 3 || d.stages == 6) ? d.stages : 0;
+    {
+        static const int ws_tr = getenv("CB_GEMM_WS_TR") ? atoi(getenv("CB_GEMM_WS_TR")) : 1;   // A/B aid
+        p.ws_tr = ws_tr;
+    }
     p.splits = 1;
     p.kiters_per_split = p.taps * p.kchunks;
     {
@@ -1356,11 +1401,27 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (pair) {
-        p.splits = 1;
-        p.kiters_per_split = p.taps * p.kchunks;
+        const int kiters = p.taps * p.kchunks;
         const int mp = ceil_div(m_tiles, 2), nt = ceil_div(d.N, BN);
-        if (b_mn) return BN == 128 ? launch_pair<128, true>(tA, tB, p, mp, nt, d.batch, st) : launch_pair<256, true>(tA, tB, p, mp, nt, d.batch, st);
-        return BN == 128 ? launch_pair<128, false>(tA, tB, p, mp, nt, d.batch, st) : launch_pair<256, false>(tA, tB, p, mp, nt, d.batch, st);
+        p.splits = 1;
+        p.kiters_per_split = kiters;
+        p.ws = nullptr;
+        p.counters = nullptr;
+        if (d.splits > 1 && !d.glu && d.splitk_ws != nullptr) {      // caller-tuned k-slices (the host autotuner)
+            const long long counters_bytes = 65536;
+            const long long cta_tiles = 2ll * mp * nt * d.batch;       // one workspace tile + counter per CTA of a pair
+            if (cta_tiles <= counters_bytes / 4 && cta_tiles * (long long)(BM * BN * 4) <= d.splitk_ws_bytes - counters_bytes) {
+                const int want = d.splits < kiters ? d.splits : kiters;
+                const int per = ceil_div(kiters, want);
+                p.splits = ceil_div(kiters, per);
+                p.kiters_per_split = per;
+                p.counters = reinterpret_cast<unsigned*>(d.splitk_ws);
+                p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(d.splitk_ws) + counters_bytes);
+            }
+        }
+        const int cap = d.cta_pair;      // 1 = whole device, n >= 2 = at most n CTAs
+        if (b_mn) return BN == 128 ? launch_pair<128, true>(tA, tB, p, mp, nt, d.batch, cap, st) : launch_pair<256, true>(tA, tB, p, mp, nt, d.batch, cap, st);
+        return BN == 128 ? launch_pair<128, false>(tA, tB, p, mp, nt, d.batch, cap, st) : launch_pair<256, false>(tA, tB, p, mp, nt, d.batch, cap, st);
     }
     dim3 grid((unsigned)ceil_div(d.N, BN), (unsigned)m_tiles, (unsigned)(d.batch * p.splits));
     if (!a_mn && !b_mn) {

@@ -826,6 +826,9 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     // flags: bit 0 = fuse SiLU, bit 1 = CB_GN_NO_GRID_BARRIER (never launch the single-kernel variant whose CTAs spin on a
     // grid-wide arrival counter: required on any stream that runs concurrently with another GroupNorm stream)
     const bool allow_fused = (act_silu & CB_GN_NO_GRID_BARRIER) == 0;
+    // bits 8..23: upper bound on the CTAs of the streaming two-kernel path (0 = two per SM): a front end that shares the
+    // device with a latency-bound chain of small launches leaves the other SMs to it
+    const int cta_cap = (act_silu >> 8) & 0xFFFF;
     act_silu &= 1;
     // ws: CB_GN_WS_BYTES; [0, 2*N*G doubles) group sums of the two-kernel path, or per-CTA partial slots of the fused
     // path; the last 8 bytes hold the grid arrival counter
@@ -863,7 +866,8 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
         const size_t row_bytes = (size_t)C * xes;
         const int rpc = (int)(kGnTmaChunkBytes / row_bytes);
         if (row_bytes % 16 == 0 && rpc >= 1) {
-            const int nb = std::max(1, 2 * device_sm_count() / N);
+            const int ctas = cta_cap > 0 ? std::min(cta_cap, 2 * device_sm_count()) : 2 * device_sm_count();
+            const int nb = std::max(1, ctas / N);
             const int rpbt = ceil_div(HW, nb);
             dim3 gridt(ceil_div(HW, rpbt), N);
             const size_t smem = (size_t)kGnTmaStages * kGnTmaChunkBytes;

@@ -72,6 +72,13 @@ def _splitk_workspace(device):
 # later launches -- including the ones captured into the step graph -- pass the winner in desc.tile_n / desc.splits.
 AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
 CTA_PAIR = os.environ.get("CB_GEMM_CTA_PAIR", "1") != "0"      # let the autotuner try the tcgen05 cta_group::2 kernel
+PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "1") != "0"  # ... and its split-K form on small-M / deep-K layers
+# Front-end SM budget (CB_FE_CTAS = n > 0): the software-pipelined front end (VAE encode of the NEXT batch, lane 2) runs
+# its large GEMMs as persistent CTA-pair kernels on at most n CTAs and its streaming GroupNorm on at most n CTAs, so the
+# latency-bound chain of small launches that trains the CURRENT batch always finds free SMs instead of queueing behind a
+# wave of 8-10 us VAE CTAs (step_graph.py).  0 = every kernel sizes its grid for the whole device.
+FE_CTAS = int(os.environ.get("CB_FE_CTAS", "0"))
+FE_LANES = (2,)
 _TUNE = {}
 _tune_scratch = {}
 _tune_stream = {}
@@ -123,6 +130,14 @@ def _autotune(d, key):
         cands.append((128, 1, 0, 1))
         if d.N >= 256:
             cands.append((256, 1, 0, 1))
+    if CTA_PAIR and PAIR_SPLITK and d.a_major != CB_MAJOR_MN and 256 <= M <= 4096 and d.N >= 256 and not d.d_transposed \
+            and not d.glu and kiters >= 16:
+        # small-M / deep-K layers (16^2 / 32^2 convolutions, FF projections): 256 x 256 pair tiles halve the operand bytes
+        # every SM pulls out of L2 (the per-SM ingest limit is what bounds these launches), k-slices fill the SMs
+        ptiles = ((d.N + 255) // 256) * ((M + 255) // 256) * d.batch
+        for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
+            if ptiles * sp <= 80 and kiters // sp >= 4:
+                cands.append((256, sp, 0, 1))
     t = GemmDesc.from_buffer_copy(bytes(d))
     # scratch output large enough for any addressing the descriptor can produce
     inner = d.batch_inner if d.batch_inner > 0 else d.batch
@@ -200,6 +215,9 @@ def _gemm(d, what):
     d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel()
     if GEMM_DEBUG_TIMELINE is not None:
         d.debug_timeline = GEMM_DEBUG_TIMELINE.data_ptr()
+    if FE_CTAS > 0 and _LANE in FE_LANES and d.cta_pair == 0 and d.a_major != CB_MAJOR_MN and d.N >= 64 \
+            and not d.d_transposed and (d.img_n * d.out_h * d.out_w if d.conv else d.M) >= 2048:
+        d.cta_pair, d.tile_n, d.splits = FE_CTAS, (256 if d.N >= 256 else 128), 1
     if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0 and d.cta_pair == 0:
         key = _tune_key(d)
         win = _TUNE.get(key)
@@ -429,7 +447,8 @@ def _gn_flags(silu):
     """bit 0: fused SiLU; bit 1 (CB_GN_NO_GRID_BARRIER): the single-kernel GroupNorm spins on a grid-wide arrival counter
     and needs all its CTAs co-resident -- only the lane-0 stream may use it (two such kernels on concurrent streams could
     each hold part of the SMs and wait for the rest forever)."""
-    return (1 if silu else 0) | (2 if (_LANE != 0 or GN_NO_GRID_BARRIER) else 0)
+    cap = (FE_CTAS & 0xFFFF) << 8 if (FE_CTAS > 0 and _LANE in FE_LANES) else 0     # CB_GN_CTA_CAP(n)
+    return (1 if silu else 0) | (2 if (_LANE != 0 or GN_NO_GRID_BARRIER) else 0) | cap
 
 
 def groupnorm(x, geo, gamma, beta, *, groups=32, eps=1e-5, silu=False, out_dtype=torch.float16, want_stats=True):

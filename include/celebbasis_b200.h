@@ -144,8 +144,11 @@ typedef struct cb_gemm_desc {
     int32_t tile_n;
     int32_t splits;
     int32_t stages;      /* 0 = auto, 3 = 3-stage ring / 2 CTAs per SM, 6 = 6-stage ring / 1 CTA per SM */
-    int32_t cta_pair;    /* 1 = tcgen05 cta_group::2 variant: a 2-CTA cluster computes a 256 x (128|256) tile, each CTA staging
-                          * its 128 rows of A and half of the B tile (K-major A, no split-K); 0 = single-CTA tiles */
+    int32_t cta_pair;    /* >= 1 = tcgen05 cta_group::2 variant: a 2-CTA cluster computes a 256 x (128|256) tile, each CTA
+                          * staging its 128 rows of A and half of the B tile (K-major A; `splits` > 1 spreads the k-slices of
+                          * a tile over clusters); the kernel is persistent on min(work items, SMs / 2) clusters, or on at
+                          * most n CTAs when cta_pair = n >= 2 (a throughput-bound producer that shares the device with a
+                          * latency-bound chain leaves the other SMs to it); 0 = single-CTA tiles */
 
     /* second destination (optional, batch == 1, not transposed): the same epilogue value is also written to
      * D2[row][col] (row pitch ldd2 elements, dtype d2_dtype).  Used to place a UNet skip activation straight into the
@@ -183,6 +186,7 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
 /* cb_groupnorm_bwd: dx_lp (optional, dtype of dy): the result is also written as a 16-bit copy -- the operand of the
  * dgrad GEMM that consumes dx next (saves a cast launch per ResBlock / transformer block of the backward pass). */
 #define CB_GN_NO_GRID_BARRIER 2 /* OR into act_silu: force the statistics + apply kernel pair (no grid-wide spin barrier) */
+#define CB_GN_CTA_CAP(n) (((n) & 0xFFFF) << 8) /* OR into act_silu (cb_groupnorm_fwd): at most n CTAs on the streaming kernel pair */
 int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
                      int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
                      double* ws, void* stream);

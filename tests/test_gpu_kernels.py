@@ -510,6 +510,86 @@ def test_gemm_cta_pair(dev, bn):
         ops._gemm = orig
 
 
+@pytest.mark.parametrize("splits,cap", [(2, 1), (5, 1), (12, 1), (3, 16)])
+def test_gemm_cta_pair_splitk(dev, splits, cap):
+    """Split-K inside the CTA-pair kernel (desc.cta_pair >= 1, desc.splits > 1): the k-slices of a 256 x 256 tile run on
+    different clusters and meet in the L2 workspace (one tile + counter per CTA of a pair); desc.cta_pair = n >= 2 caps the
+    persistent grid at n CTAs.  Small-M / deep-K shapes of the 16^2 / 32^2 UNet levels, ragged M / N, odd tile counts,
+    bias + residual, MN-major B, repeated launches (the workspace must come back zeroed)."""
+    from celebbasis_b200 import ops
+    orig = ops._gemm
+
+    def forced(d, what):
+        d.cta_pair, d.tile_n, d.splits = cap, 256, splits
+        return orig(d, what)
+    ops._gemm = forced
+    try:
+        x, w = rnd(256, 5120), rnd(1280, 5120) * 0.05
+        bias, res = rnd(1280, dtype=torch.float32), rnd(256, 1280, dtype=torch.float32)
+        ref = x.float() @ w.float().t() + bias + res
+        for _ in range(3):
+            y = ops.linear(x, w, bias, out_dtype=torch.float32, residual=res)
+            assert rel(y, ref) < 2e-3
+        dy = rnd(256, 1280)
+        dx = ops.linear_dgrad(dy, w, out_dtype=torch.float16)                   # MN-major B, K = 1280 -> 20 k-iterations
+        assert rel(dx, dy.float() @ w.float()) < 2e-3
+        x3, w3 = rnd(128 * 2 + 44, 1024), rnd(1000, 1024) * 0.05                # 3 m tiles (odd), ragged M and N
+        y3 = ops.linear(x3, w3, out_dtype=torch.float16)
+        assert rel(y3, x3.float() @ w3.float().t()) < 2e-3
+        g = ops.Geo(1, 16, 16)                                                  # the 16^2 level: M = 256, K = 9 * 640
+        xi = rnd(g.rows, 640)
+        wc = torch.randn(1280, 640, 3, 3, device="cuda") * 0.02
+        pk = ops.pack_conv_weight(wc, torch.float16)
+        bi = rnd(1280, dtype=torch.float32)
+        refc = F.conv2d(xi.float().view(1, 16, 16, 640).permute(0, 3, 1, 2), wc.half().float(), bias=bi, padding=1)
+        refc = refc.permute(0, 2, 3, 1).reshape(g.rows, 1280)
+        for _ in range(2):
+            yc, _ = ops.conv2d(xi, g, pk, 1280, bias=bi, out_dtype=torch.float32)
+            assert rel(yc, refc) < 2e-3
+        dyc = rnd(g.rows, 1280)
+        dxc, _ = ops.conv2d_dgrad(dyc, g, pk, 640, out_dtype=torch.float32)
+        xr = xi.float().view(1, 16, 16, 640).permute(0, 3, 1, 2).requires_grad_(True)
+        F.conv2d(xr, wc.half().float(), padding=1).backward(dyc.float().view(1, 16, 16, 1280).permute(0, 3, 1, 2))
+        assert rel(dxc, xr.grad.permute(0, 2, 3, 1).reshape(g.rows, 640)) < 2e-3
+    finally:
+        ops._gemm = orig
+    # the single-CTA split-K kernel shares the workspace: it must still see zeros
+    x, w = rnd(256, 2560), rnd(640, 2560) * 0.05
+    assert rel(ops.linear(x, w, out_dtype=torch.float32), x.float() @ w.float().t()) < 2e-3
+
+
+def test_front_end_sm_budget(dev):
+    """ops.FE_CTAS (env CB_FE_CTAS): inside the front-end lane the large GEMMs run as persistent CTA-pair kernels on at
+    most n CTAs (stride-2 / asymmetric padding of the VAE downsample included) and the streaming GroupNorm pair on at
+    most n CTAs; results are unchanged."""
+    from celebbasis_b200 import ops
+    old = ops.FE_CTAS
+    ops.FE_CTAS = 24
+    try:
+        with ops.lane(2):
+            for (n, h, cin, cout, stride, pad) in [(1, 128, 128, 128, 2, (0, 1, 0, 1)), (1, 96, 128, 256, 1, (1, 1, 1, 1)),
+                                                   (1, 64, 8, 128, 1, (1, 1, 1, 1))]:
+                x = rnd(n * h * h, cin)
+                wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5)
+                b = rnd(cout, dtype=torch.float32)
+                y, _ = ops.conv2d(x, ops.Geo(n, h, h), ops.pack_conv_weight(wt, torch.float16), cout, bias=b, stride=stride,
+                                  pad=pad, out_dtype=torch.float32)
+                xr = F.pad(x.float().view(n, h, h, cin).permute(0, 3, 1, 2), (pad[2], pad[3], pad[0], pad[1]))
+                ref = F.conv2d(xr, wt.float(), b, stride=stride).permute(0, 2, 3, 1).reshape(-1, cout)
+                assert y.shape == ref.shape and rel(y, ref) < 1e-3
+            xl, wl = rnd(4096, 512), rnd(512, 512) * 0.05
+            res = rnd(4096, 512, dtype=torch.float32)
+            assert rel(ops.linear(xl, wl, out_dtype=torch.float32, residual=res), xl.float() @ wl.float().t() + res) < 1e-3
+            hw, c = 65536, 128
+            xg = rnd(hw, c, dtype=torch.float32, scale=2.0) + 0.5
+            g, b = rnd(c, dtype=torch.float32) * 0.1 + 1, rnd(c, dtype=torch.float32) * 0.1
+            y, _ = ops.groupnorm(xg, ops.Geo(1, 256, 256), g, b, eps=1e-6, silu=True)
+            yr = F.silu(F.group_norm(xg.view(1, hw, c).permute(0, 2, 1), 32, g, b, 1e-6)).permute(0, 2, 1).reshape(hw, c)
+            assert rel(y, yr) < 1e-3
+    finally:
+        ops.FE_CTAS = old
+
+
 def test_gemm_prelu_epilogue_and_d2_affine(dev):
     """CB_ACT_PRELU (per-column slopes) and the per-column affine of the second destination: an IBasicBlock's PReLU and
     the next block's bn1 inside the conv epilogues (iresnet.py:41-58)."""
