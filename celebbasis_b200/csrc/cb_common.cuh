@@ -68,6 +68,26 @@ static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+// same, as thread-block clusters of `cluster` CTAs (runtime cluster shape)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, dim3 cluster, size_t smem,
+                                                cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster.x;
+    at[0].val.clusterDim.y = cluster.y;
+    at[0].val.clusterDim.z = cluster.z;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 #define CB_LAUNCH(kern, grid, block, smem, st, ...) \
     ::cb::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), (st), ##__VA_ARGS__)
 #endif
@@ -287,6 +307,24 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
         "%5, %6}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+// 32 bytes (8 floats) into the shared memory of CTA `cta` of the cluster at the offset `addr` has in this CTA
+__device__ __forceinline__ void st_cluster_f32x8(uint32_t addr, uint32_t cta, const uint32_t* v) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n"
+        "st.shared::cluster.v4.b32 [ra + 16], {%6, %7, %8, %9};\n"
+        "}\n" ::"r"(addr),
+        "r"(cta), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+        : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // arrive (release, cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster

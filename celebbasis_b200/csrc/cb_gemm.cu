@@ -63,6 +63,7 @@ struct GemmParams {
     int splits, kiters_per_split;
     float* ws;
     unsigned* counters;
+    int cluster_sk;           // split-K through distributed shared memory: the `splits` CTAs of a tile form a cluster (1,1,splits)
     int ws_tr;                // accumulator-tile layout in ws: 1 = float4-group-major (coalesced warp requests), 0 = row-major
     int dbg_mode;             // tuning aid (env CB_GEMM_DBG_MODE): 1 exit after setup, 2 skip epilogue, 3 exit at once
     unsigned long long* dbg;  // optional per-CTA timeline (8 x u64 globaltimer ns per CTA), NULL in production
@@ -605,6 +606,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        if (p.cluster_sk) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }   // the two cluster barriers of the epilogue
     } else if (warp == 1) {
         if (lane == 0) {
             // ===================== MMA issuer =====================
@@ -631,6 +633,7 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full_bar);
             if (dbg) dbg[3] = clock64();
         }
+        if (p.cluster_sk) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }
     } else {
         // ===================== epilogue =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -717,6 +720,49 @@ cb_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 rc_cur = rc_next;
+            }
+        } else if (p.cluster_sk) {
+            // ---- split-K inside a thread-block cluster: the `splits` CTAs of this tile are the cluster (1,1,splits), rank =
+            //      k-slice.  The 8-column groups of the tile are dealt round-robin to the CTAs (group g -> CTA g % S); every CTA
+            //      sends each group of its partial accumulator into the owner's shared memory (the TMA ring, idle once all
+            //      MMAs have retired), slot [sender][g / S][row] of 32 bytes, then sums its own groups over the S senders and
+            //      runs the epilogue for them.  Two cluster barriers (~0.2 us each) replace the L2 reductions, the
+            //      __threadfence, the arrival counter and the read-back of the global-workspace path (~4 us of round trips).
+            const int S = p.splits;
+            const int GI = (BN / 8 + S - 1) / S;                 // groups a CTA can own
+            fence_proxy_async_smem();                            // the ring was written / read through the async proxy
+            cluster_sync_all();                                  // #1: every CTA of the cluster has retired its MMAs
+#pragma unroll 1
+            for (int c = 0; c * 32 < ncols_tile; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32(trow + c * 32, acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const int g = c * 4 + gq;
+                    if (g * 8 < ncols_tile)
+                        st_cluster_f32x8(smem_base + static_cast<uint32_t>(((sp * GI + g / S) * BM + r) * 32),
+                                         static_cast<uint32_t>(g % S), &acc[gq * 8]);
+                }
+            }
+            cluster_sync_all();                                  // #2: all partial groups have landed in their owners
+            for (int gi = 0; gi < GI; ++gi) {
+                const int g = gi * S + sp;
+                if (g * 8 >= ncols_tile) break;
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                for (int s2 = 0; s2 < S; ++s2) {
+                    const uint32_t a = smem_base + static_cast<uint32_t>(((s2 * GI + gi) * BM + r) * 32);
+                    const float4 lo = ld_shared_f32x4(a), hi = ld_shared_f32x4(a + 16);
+                    f[0] += lo.x; f[1] += lo.y; f[2] += lo.z; f[3] += lo.w;
+                    f[4] += hi.x; f[5] += hi.y; f[6] += hi.z; f[7] += hi.w;
+                }
+                if (row_valid) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] *= p.alpha;
+                    epilogue_group8<kExt>(p, f, grow, brow, n0 + g * 8, d_off, r_off, min(8, ncols_tile - g * 8), nullptr,
+                                          sb ? sb + g * 8 : nullptr);
+                }
             }
         } else {
             const unsigned tile_id = (static_cast<unsigned>(bz) * gridDim.y + m_tile) * gridDim.x + blockIdx.x;
@@ -1073,6 +1119,22 @@ static int launch_se(const CUtensorMap& tA, const CUtensorMap& tB, const GemmPar
         CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         attr_done = true;
     }
+    if (p.cluster_sk) {
+        // the k-slices of a tile are one cluster (1,1,splits); the exchange buffer lives in the idle TMA ring
+        const int S = p.splits, GI = (BN / 8 + S - 1) / S;
+        CB_REQUIRE(S >= 2 && S <= 16 && grid.z % S == 0, CB_ERR_ARG, "cb_gemm(cluster split-K): %d slices not in [2,16]", S);
+        CB_REQUIRE((long long)S * GI * BM * 32 <= (long long)kStages * Cfg::kStageBytes, CB_ERR_ARG,
+                   "cb_gemm(cluster split-K): exchange buffer (%d slices x %d groups) exceeds the %d-stage ring", S, GI, kStages);
+        static bool np_done = false;
+        if (S > 8 && !np_done) {
+            CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            np_done = true;
+        }
+        CB_CUDA(launch_kernel_cluster(kern, grid, dim3(kThreads), dim3(1, 1, (unsigned)S), (size_t)Cfg::kSmemBytes, st, tA, tB, p));
+        CB_CUDA(cudaGetLastError());
+        count_launches(1);
+        return 0;
+    }
 CB_LAUNCH((kern), grid, kThreads, Cfg::kSmemBytes, st, tA, tB, p);
     CB_CUDA(cudaGetLastError());
     count_launches(1);
@@ -1399,6 +1461,8 @@ extern "C" int cb_gemm(const cb_gemm_desc* dp, void* stream) {
             }
         }
     }
+    // split-K through distributed shared memory instead of the global workspace (desc.splitk_cluster, host autotuner)
+    p.cluster_sk = (d.splitk_cluster == 1 && !pair && p.splits >= 2 && p.splits <= 16 && p.dbg_mode == 0) ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (pair) {
         const int kiters = p.taps * p.kchunks;

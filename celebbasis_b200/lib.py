@@ -42,6 +42,7 @@ class GemmDesc(ctypes.Structure):
         ("tile_n", ctypes.c_int32), ("splits", ctypes.c_int32), ("stages", ctypes.c_int32), ("cta_pair", ctypes.c_int32),
         ("D2", ctypes.c_void_p), ("ldd2", ctypes.c_int64), ("d2_dtype", ctypes.c_int32), ("glu", ctypes.c_int32),
         ("act_param", ctypes.c_void_p), ("d2_scale", ctypes.c_void_p), ("d2_shift", ctypes.c_void_p),
+        ("splitk_cluster", ctypes.c_int32),
     ]
 
 

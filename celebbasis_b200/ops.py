@@ -72,7 +72,8 @@ def _splitk_workspace(device):
 # later launches -- including the ones captured into the step graph -- pass the winner in desc.tile_n / desc.splits.
 AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
 CTA_PAIR = os.environ.get("CB_GEMM_CTA_PAIR", "1") != "0"      # let the autotuner try the tcgen05 cta_group::2 kernel
-PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "1") != "0"  # ... and its split-K form on small-M / deep-K layers
+PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "0") != "0"  # ... and its split-K form (measured: never wins)
+CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "1") != "0"    # split-K slices as a thread-block cluster reducing through DSMEM
 # Front-end SM budget (CB_FE_CTAS = n > 0): the software-pipelined front end (VAE encode of the NEXT batch, lane 2) runs
 # its large GEMMs as persistent CTA-pair kernels on at most n CTAs and its streaming GroupNorm on at most n CTAs, so the
 # latency-bound chain of small launches that trains the CURRENT batch always finds free SMs instead of queueing behind a
@@ -113,23 +114,29 @@ def _autotune(d, key):
     bns = [64] if d.N <= 64 else ([64, 128] if d.b_major == CB_MAJOR_MN else [64, 128, 160])
     if d.N >= 256 and d.a_major != CB_MAJOR_MN and M >= 1024 and os.environ.get("CB_GEMM_TILE256", "1") != "0":
         bns = bns + [256]          # 128x256 tiles (4-stage ring, one CTA per SM): fewer operand bytes per flop for large GEMMs
-    cands = [(0, 0, 0, 0)]
+    cands = [(0, 0, 0, 0, 0)]
     for bn in bns:
         tiles = ((d.N + bn - 1) // bn) * ((M + 127) // 128) * d.batch
-        cands.append((bn, 1, 0, 0))
+        cands.append((bn, 1, 0, 0, 0))
         if tiles <= 148:
-            cands.append((bn, 1, 3, 0))          # 3-stage ring: leaves room for the next kernel's CTAs on the SM
+            cands.append((bn, 1, 3, 0, 0))          # 3-stage ring: leaves room for the next kernel's CTAs on the SM
         if tiles < 148:
             for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
                 if tiles * sp <= 320 and kiters // sp >= 2:
-                    cands.append((bn, sp, 0, 0))
+                    cands.append((bn, sp, 0, 0, 0))
                     if tiles * sp <= 148:
-                        cands.append((bn, sp, 3, 0))
+                        cands.append((bn, sp, 3, 0, 0))
+                    if CLUSTER_SK and sp <= 16 and not d.glu:
+                        # the k-slices as one cluster, reduced through distributed shared memory; the exchange buffer
+                        # (slices x owned 8-column groups x 4 KiB) must fit the TMA ring the kernel will run with
+                        ring = 4 if bn == 256 else (6 if tiles * sp <= 148 else 3)
+                        if sp * (-(-(bn // 8) // sp)) * 4096 <= ring * (128 + bn) * 128:
+                            cands.append((bn, sp, 0, 0, 1))
     if CTA_PAIR and d.a_major != CB_MAJOR_MN and M >= 2048 and d.N >= 128 and not d.d_transposed:
         # tcgen05 cta_group::2: a 2-CTA cluster per 256 x bn tile (half the B bytes per SM); large-M GEMMs only
-        cands.append((128, 1, 0, 1))
+        cands.append((128, 1, 0, 1, 0))
         if d.N >= 256:
-            cands.append((256, 1, 0, 1))
+            cands.append((256, 1, 0, 1, 0))
     if CTA_PAIR and PAIR_SPLITK and d.a_major != CB_MAJOR_MN and 256 <= M <= 4096 and d.N >= 256 and not d.d_transposed \
             and not d.glu and kiters >= 16:
         # small-M / deep-K layers (16^2 / 32^2 convolutions, FF projections): 256 x 256 pair tiles halve the operand bytes
@@ -137,7 +144,7 @@ def _autotune(d, key):
         ptiles = ((d.N + 255) // 256) * ((M + 255) // 256) * d.batch
         for sp in (2, 3, 4, 6, 8, 12, 16, 24, 32):
             if ptiles * sp <= 80 and kiters // sp >= 4:
-                cands.append((256, sp, 0, 1))
+                cands.append((256, sp, 0, 1, 0))
     t = GemmDesc.from_buffer_copy(bytes(d))
     # scratch output large enough for any addressing the descriptor can produce
     inner = d.batch_inner if d.batch_inner > 0 else d.batch
@@ -170,8 +177,8 @@ def _autotune(d, key):
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         sp_ = ctypes.c_void_p(side.cuda_stream)
-        for bn, sp, stg, pair in cands:
-            t.tile_n, t.splits, t.stages, t.cta_pair = bn, sp, stg, pair
+        for bn, sp, stg, pair, cl in cands:
+            t.tile_n, t.splits, t.stages, t.cta_pair, t.splitk_cluster = bn, sp, stg, pair, cl
             if L.cb_gemm(ctypes.byref(t), sp_) != 0:
                 continue
             g = torch.cuda.CUDAGraph()
@@ -190,23 +197,23 @@ def _autotune(d, key):
                 e1.record(side)
                 e1.synchronize()
                 best = min(best, e0.elapsed_time(e1) * 125.0)     # us per launch
-            times[(bn, sp, stg, pair)] = best
+            times[(bn, sp, stg, pair, cl)] = best
             del g
     cur.wait_stream(side)
-    base = times.get((0, 0, 0, 0), 1e9)
-    win = min(times, key=times.get) if times else (0, 0, 0, 0)
+    base = times.get((0, 0, 0, 0, 0), 1e9)
+    win = min(times, key=times.get) if times else (0, 0, 0, 0, 0)
     if times.get(win, 1e9) > 0.97 * base:     # keep the library's own choice unless the gain is real
-        win = (0, 0, 0, 0)
+        win = (0, 0, 0, 0, 0)
     _TUNE[key] = win
     if TUNE_LOG is not None:
-        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}": round(v, 2) for k, v in times.items()}, win))
+        TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}c{k[4]}": round(v, 2) for k, v in times.items()}, win))
     log_path = os.environ.get("CB_GEMM_TUNE_LOG")
     if log_path:
         import json
         with open(log_path, "a") as f:
             f.write(json.dumps({"M": M, "N": d.N, "K": d.K, "batch": d.batch, "conv": d.conv, "kh": d.kh, "b_major": d.b_major,
                                 "a_major": d.a_major, "d_dtype": d.d_dtype, "win": list(win),
-                                "us": {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}": round(v, 2) for k, v in times.items()}}) + "\n")
+                                "us": {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}c{k[4]}": round(v, 2) for k, v in times.items()}}) + "\n")
     return win
 
 
@@ -218,13 +225,13 @@ def _gemm(d, what):
     if FE_CTAS > 0 and _LANE in FE_LANES and d.cta_pair == 0 and d.a_major != CB_MAJOR_MN and d.N >= 64 \
             and not d.d_transposed and (d.img_n * d.out_h * d.out_w if d.conv else d.M) >= 2048:
         d.cta_pair, d.tile_n, d.splits = FE_CTAS, (256 if d.N >= 256 else 128), 1
-    if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0 and d.cta_pair == 0:
+    if AUTOTUNE and d.tile_n == 0 and d.splits == 0 and d.stages == 0 and d.cta_pair == 0 and d.splitk_cluster == 0:
         key = _tune_key(d)
         win = _TUNE.get(key)
         if win is None and not torch.cuda.is_current_stream_capturing():
             win = _autotune(d, key)
         if win is not None:
-            d.tile_n, d.splits, d.stages, d.cta_pair = win
+            d.tile_n, d.splits, d.stages, d.cta_pair, d.splitk_cluster = win
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
         M = d.img_n * d.out_h * d.out_w if d.conv else d.M

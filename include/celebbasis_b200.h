@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 3
+#define CB_ABI_VERSION 4
 #define CB_GN_WS_BYTES 131072
 
 /* element types */
@@ -167,6 +167,12 @@ typedef struct cb_gemm_desc {
     const float* act_param;
     const float* d2_scale;
     const float* d2_shift;
+    /* 1 = the `splits` k-slices of a tile form a thread-block cluster (1,1,splits; 2..16 slices) and reduce through
+     * distributed shared memory: every CTA sends the 8-column groups of its partial accumulator to the group's owner CTA
+     * (round-robin) and each owner runs the epilogue for its groups -- two cluster barriers instead of L2 reductions,
+     * fence, arrival counter and read-back.  Needs `splits` > 1 (caller-tuned) and an exchange buffer that fits the TMA
+     * ring (CB_ERR_ARG otherwise); ignored by the CTA-pair variant. */
+    int32_t splitk_cluster;
 } cb_gemm_desc;
 
 int cb_gemm(const cb_gemm_desc* desc, void* stream);

@@ -19,7 +19,7 @@ def test_library_loads_and_exports_header_symbols():
     assert len(syms) >= 35
     for s in syms:
         assert hasattr(L, s), f"symbol {s} declared in the header but not exported"
-    assert L.cb_abi_version() == 3
+    assert L.cb_abi_version() == 4
     assert isinstance(lib.last_error(), str)
 
 

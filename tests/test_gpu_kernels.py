@@ -558,6 +558,62 @@ def test_gemm_cta_pair_splitk(dev, splits, cap):
     assert rel(ops.linear(x, w, out_dtype=torch.float32), x.float() @ w.float().t()) < 2e-3
 
 
+@pytest.mark.parametrize("bn,splits", [(64, 2), (64, 6), (64, 16), (128, 5), (128, 8), (128, 12), (160, 8)])
+def test_gemm_cluster_splitk(dev, bn, splits):
+    """desc.splitk_cluster = 1: the k-slices of a tile are a thread-block cluster (1,1,splits) that exchanges 8-column
+    groups of the partial accumulators through distributed shared memory (no global workspace, no atomics).  Plain /
+    bias + residual / activation epilogues, fp16 and fp32 outputs, ragged M and N, MN-major operands, batched launches,
+    3x3 convolution and its dgrad; non-power-of-two and non-portable (16) cluster sizes."""
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import CB_ACT_SILU
+    orig = ops._gemm
+    seen = []
+
+    def forced(d, what):
+        d.tile_n, d.splits, d.splitk_cluster = bn, splits, 1
+        seen.append(d.N)
+        return orig(d, what)
+    ops._gemm = forced
+    try:
+        x, w = rnd(77, 3072), rnd(768, 3072) * 0.05
+        bias, res = rnd(768, dtype=torch.float32), rnd(77, 768, dtype=torch.float32)
+        ref = x.float() @ w.float().t()
+        for _ in range(2):
+            assert rel(ops.linear(x, w, bias, out_dtype=torch.float32, residual=res), ref + bias + res) < 2e-3
+        assert rel(ops.linear(x, w, bias, act=CB_ACT_SILU), F.silu(ref + bias)) < 2e-3
+        dy = rnd(300, 1000)                                                     # ragged M (3 m tiles) and N
+        w2 = rnd(1000, 1536) * 0.05
+        assert rel(ops.linear_dgrad(dy, w2, out_dtype=torch.float32), dy.float() @ w2.float()) < 2e-3     # MN-major B
+        x3 = rnd(300, 1536)
+        assert rel(ops.linear(x3, w2, out_dtype=torch.float16), x3.float() @ w2.float().t()) < 2e-3
+        g = ops.Geo(1, 16, 16)
+        xi = rnd(g.rows, 640)
+        wc = torch.randn(1280, 640, 3, 3, device="cuda") * 0.02
+        pk = ops.pack_conv_weight(wc, torch.float16)
+        bi = rnd(1280, dtype=torch.float32)
+        refc = F.conv2d(xi.float().view(1, 16, 16, 640).permute(0, 3, 1, 2), wc.half().float(), bias=bi, padding=1)
+        refc = refc.permute(0, 2, 3, 1).reshape(g.rows, 1280)
+        yc, _ = ops.conv2d(xi, g, pk, 1280, bias=bi, out_dtype=torch.float32)
+        assert rel(yc, refc) < 2e-3
+        dyc = rnd(g.rows, 1280)
+        dxc, _ = ops.conv2d_dgrad(dyc, g, pk, 640, out_dtype=torch.float16)
+        xr = xi.float().view(1, 16, 16, 640).permute(0, 3, 1, 2).requires_grad_(True)
+        F.conv2d(xr, wc.half().float(), padding=1).backward(dyc.float().view(1, 16, 16, 1280).permute(0, 3, 1, 2))
+        assert rel(dxc, xr.grad.permute(0, 2, 3, 1).reshape(g.rows, 640)) < 2e-3
+        # batched, both operands MN-major (cross-attention dV = P^T dO over 1024 queries, 8 heads)
+        heads, nq, nk, dh = 8, 1024, 77, 80
+        P, dO = rnd(heads * nq, 80) * 0.1, rnd(nq, heads * dh)
+        dv = torch.zeros(nk, heads * dh, dtype=torch.float16, device="cuda")
+        ops.bmm(P, dO, dv, M=nk, N=dh, K=nq, heads=heads, images=1, lda=80, ldb=dO.stride(0), ldd=dv.stride(0),
+                a_hs=nq * 80, b_hs=dh, d_hs=dh, a_is=heads * nq * 80, b_is=nq * dO.stride(0), d_is=nk * dv.stride(0),
+                a_major=ops.CB_MAJOR_MN, b_major=ops.CB_MAJOR_MN)
+        refv = torch.einsum("hqk,qhd->khd", P.float().view(heads, nq, 80)[:, :, :nk], dO.float().view(nq, heads, dh))
+        assert rel(dv.view(nk, heads, dh), refv) < 2e-3
+    finally:
+        ops._gemm = orig
+    assert len(seen) >= 8
+
+
 def test_front_end_sm_budget(dev):
     """ops.FE_CTAS (env CB_FE_CTAS): inside the front-end lane the large GEMMs run as persistent CTA-pair kernels on at
     most n CTAs (stride-2 / asymmetric padding of the VAE downsample included) and the streaming GroupNorm pair on at

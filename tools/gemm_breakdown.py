@@ -21,7 +21,7 @@ st_ = {"image": batch["image"].to(dev), "faces": batch["image_ori"]["faces"].to(
        "noise": draws["noise"].to(dev), "eps": draws["posterior_eps"].to(dev)}
 ids, map_np, _ = eng.prepare(batch["caption"])
 ids_dev, map_dev = ids.to(dev), torch.from_numpy(map_np).to(dev)
-ids_person = batch["image_ori"]["ids"]
+ids_person = batch["image_ori"]["ids"].to(dev)
 
 def step_device():
     return eng.run(st_["image"], st_["faces"], ids_person, ids_dev, map_dev, st_["t"], st_["noise"], st_["eps"])
@@ -66,7 +66,7 @@ for key, items in groups.items():
     rows.append(dict(M=key[0], N=key[1], K=key[2], batch=key[3], inner=key[4], conv=key[5], kh=key[6], stride=key[7], amaj=key[8],
                      bmaj=key[9], flip=key[10], dd=key[11], dT=key[12], R=key[13], act=key[14], h=key[15], count=len(items), us=round(us, 2),
                      total_us=round(us * len(items), 1), tflops=round(fl / us / 1e6, 1), gflop=round(fl / 1e9, 3),
-                     cfg=[g0.tile_n, g0.splits, g0.stages, g0.cta_pair]))
+                     cfg=[g0.tile_n, g0.splits, g0.stages, g0.cta_pair, g0.splitk_cluster]))
 rows.sort(key=lambda r: -r["total_us"])
 tot = sum(r["total_us"] for r in rows); totf = sum(r["gflop"] * r["count"] for r in rows)
 print(f"# {len(rec)} GEMMs, {len(rows)} shapes, sum of isolated times {tot/1000:.2f} ms, {totf:.0f} GFLOP -> {totf/tot*1e3/1e3:.1f} TFLOP/s")
