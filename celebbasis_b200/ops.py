@@ -73,7 +73,10 @@ def _splitk_workspace(device):
 AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
 CTA_PAIR = os.environ.get("CB_GEMM_CTA_PAIR", "1") != "0"      # let the autotuner try the tcgen05 cta_group::2 kernel
 PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "0") != "0"  # ... and its split-K form (measured: never wins)
-CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "1") != "0"    # split-K slices as a thread-block cluster reducing through DSMEM
+# split-K slices as a thread-block cluster reducing through DSMEM (desc.splitk_cluster).  Off by default: in isolation it
+# wins 0.5-3 us on the 2..6-slice launches (profiles/r02_tune_cluster_splitk.jsonl), but with cluster launches on every stream
+# the step hung against the lane-0 GroupNorm that spins on a grid-wide counter (see _gemm); =1 enables it on lane 0 only.
+CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "0") != "0"
 # Front-end SM budget (CB_FE_CTAS = n > 0): the software-pipelined front end (VAE encode of the NEXT batch, lane 2) runs
 # its large GEMMs as persistent CTA-pair kernels on at most n CTAs and its streaming GroupNorm on at most n CTAs, so the
 # latency-bound chain of small launches that trains the CURRENT batch always finds free SMs instead of queueing behind a
@@ -81,6 +84,7 @@ CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "1") != "0"    # split-K slice
 FE_CTAS = int(os.environ.get("CB_FE_CTAS", "0"))
 FE_LANES = (2,)
 _TUNE = {}
+_TUNE_NC = {}
 _tune_scratch = {}
 _tune_stream = {}
 TUNE_LOG = None     # set to a list to collect (key, table of candidate times)
@@ -205,6 +209,12 @@ def _autotune(d, key):
     if times.get(win, 1e9) > 0.97 * base:     # keep the library's own choice unless the gain is real
         win = (0, 0, 0, 0, 0)
     _TUNE[key] = win
+    # best configuration that does not launch a cluster of k-slices (see _gemm: lanes other than 0)
+    nc = {k: v for k, v in times.items() if k[4] == 0}
+    win_nc = min(nc, key=nc.get) if nc else (0, 0, 0, 0, 0)
+    if nc.get(win_nc, 1e9) > 0.97 * base:
+        win_nc = (0, 0, 0, 0, 0)
+    _TUNE_NC[key] = win_nc
     if TUNE_LOG is not None:
         TUNE_LOG.append((key, {f"{k[0]}x{k[1]}s{k[2]}p{k[3]}c{k[4]}": round(v, 2) for k, v in times.items()}, win))
     log_path = os.environ.get("CB_GEMM_TUNE_LOG")
@@ -231,6 +241,12 @@ def _gemm(d, what):
         if win is None and not torch.cuda.is_current_stream_capturing():
             win = _autotune(d, key)
         if win is not None:
+            # Cluster split-K only on the lane-0 stream: a cluster of 6..16 CTAs must be co-scheduled inside one GPC, and the
+            # single-kernel GroupNorm (lane 0 only) spins on a grid-wide arrival counter until all its CTAs are resident.  On
+            # one stream the two are ordered; on concurrent streams a pending cluster at the head of the block scheduler's
+            # queue and a half-resident spinning grid can wait for each other forever (observed: the step hangs).
+            if win[4] == 1 and _LANE != 0:
+                win = _TUNE_NC.get(key, (0, 0, 0, 0, 0))
             d.tile_n, d.splits, d.stages, d.cta_pair, d.splitk_cluster = win
     if GEMM_RECORD is not None:
         taps = d.kh * d.kw if d.conv else 1
