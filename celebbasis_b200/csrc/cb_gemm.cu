@@ -470,11 +470,17 @@ __device__ __forceinline__ void splitk_reduce_epilogue(const GemmParams& p, unsi
     if (!last) return;
     __threadfence();
     if (row_valid) {
+        // the sums of chunk c+1 are requested before chunk c is consumed: one L2 round trip for the whole tile instead of
+        // one per 32-column chunk (this CTA's tail is the critical path of the launch)
+        float4 v[8], vn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + j * gs));
 #pragma unroll 1
         for (int c = 0; c * 32 < ncols_tile; ++c) {
-            float4 v[8];
+            if ((c + 1) * 32 < ncols_tile) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(mine + (c * 8 + j) * gs));   // 8 loads in flight
+                for (int j = 0; j < 8; ++j) vn[j] = __ldcg(reinterpret_cast<const float4*>(mine + ((c + 1) * 8 + j) * gs));
+            }
             const bool pre = r_fast && ncols_tile - c * 32 >= 32;
             if (pre) residual_prefetch(p, r_row + c * 32, rc_cur);
 #pragma unroll
@@ -499,6 +505,8 @@ __device__ __forceinline__ void splitk_reduce_epilogue(const GemmParams& p, unsi
                     }
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = vn[j];
         }
     }
     if (threadIdx.x == 64) p.counters[tile_id] = 0u;   // self-cleaning for the next launch
