@@ -321,6 +321,19 @@ __device__ __forceinline__ void st_cluster_f32x8(uint32_t addr, uint32_t cta, co
         "r"(cta), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
         : "memory");
 }
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, uint32_t cta, float a, float b) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "st.shared::cluster.v2.f32 [ra], {%2, %3};\n"
+        "}\n" ::"r"(addr),
+        "r"(cta), "f"(a), "f"(b)
+        : "memory");
+}
+// split cluster barrier: arrive early (all CTAs of the cluster have started once everyone's wait returns), wait late
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_shared_f32x4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");

@@ -686,6 +686,268 @@ gn_fused_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const f
     }
 }
 
+// ---- GroupNorm on thread-block clusters: no grid-wide barrier ----------------------------------------------------------
+// A cluster owns a SLAB of `gpc` consecutive groups (cw = gpc * C/G channels) of one image for ALL rows; its S CTAs split
+// the rows.  Every CTA stages its rows x cw sub-matrix in shared memory (read once), the per-group partial sums of the S
+// CTAs meet through distributed shared memory (each CTA stores its gpc (sum, sumsq) pairs into every peer: S*gpc 8-byte
+// remote stores, one cluster barrier), and the normalised rows are written straight from shared memory.  Compared with the
+// single-kernel variant above there is no arrival counter to spin on, no 147-way fold of partial sets out of L2, and no
+// requirement that all CTAs of the grid be resident at once (util.py:199-216 GroupNorm32, openaimodel.py:201-241).
+constexpr int kGnClThreads = 512;
+constexpr int kGnClMaxS = 16;
+
+// 4 consecutive channels (16 bytes of fp32, 8 bytes of a 16-bit type) per access
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__half> {
+    static __device__ __forceinline__ float4 ld(const __half* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ void st(__half* p, float4 v) {
+        uint2 u;
+        *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+        uint2 u;
+        *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+
+// thread -> (channel quad `cq` of the slab, first row `ry`); rows advance by RY.  nq = quads per slab row.  The two channel
+// pairs of a quad may belong to different groups (C/G is even, not necessarily a multiple of 4): gA / gB.
+struct GnClMap { int cq, ry, RY, gA, gB; bool on; };
+__device__ __forceinline__ GnClMap gn_cl_map(int nq, int cpg) {
+    GnClMap m;
+    m.RY = kGnClThreads / nq;
+    m.cq = threadIdx.x % nq;
+    m.ry = threadIdx.x / nq;
+    m.on = m.ry < m.RY;
+    m.gA = (4 * m.cq) / cpg;
+    m.gB = (4 * m.cq + 2) / cpg;
+    return m;
+}
+
+// exchange of per-group partial pairs inside the cluster; returns the cluster totals in s_t1/s_t2 (double, [gpc])
+__device__ __forceinline__ void gn_cl_allreduce(float* s_a, float* s_b, float2 (*s_recv)[32], double* s_t1, double* s_t2,
+                                                int gpc, int S, int rank) {
+    __syncthreads();                               // s_a / s_b complete
+    cluster_wait();                                // (arrive was issued at kernel entry) every CTA of the cluster runs
+    for (int t = threadIdx.x; t < S * gpc; t += kGnClThreads) {
+        const int peer = t / gpc, g = t - peer * gpc;
+        st_cluster_f32x2(smem_u32(&s_recv[rank][g]), (uint32_t)peer, s_a[g], s_b[g]);
+    }
+    cluster_sync_all();                            // release our stores / acquire everyone else's
+    if (threadIdx.x < gpc) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int r = 0; r < S; ++r) { t1 += (double)s_recv[r][threadIdx.x].x; t2 += (double)s_recv[r][threadIdx.x].y; }
+        s_t1[threadIdx.x] = t1;
+        s_t2[threadIdx.x] = t2;
+    }
+    __syncthreads();
+}
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kGnClThreads)
+gn_cluster_fwd_kernel(const TX* __restrict__ x, TY* __restrict__ y, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int HW,
+                      int C, int G, float eps, int act, int gpc, int rows_per_cta) {
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    TX* sx = reinterpret_cast<TX*>(gn_smem);
+    __shared__ float s_a[32], s_b[32];
+    __shared__ __align__(8) float2 s_recv[kGnClMaxS][32];
+    __shared__ double s_t1[32], s_t2[32];
+    cluster_arrive_relaxed();
+    const int S = gridDim.x, rank = blockIdx.x, slab = blockIdx.y, n = blockIdx.z;
+    const int cpg = C / G, cw = gpc * cpg, nq = cw >> 2, c0 = slab * cw;
+    const int r0 = rank * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+    if (threadIdx.x < 32) { s_a[threadIdx.x] = 0.f; s_b[threadIdx.x] = 0.f; }
+    __syncthreads();
+    pdl_sync();
+    const GnClMap m = gn_cl_map(nq, cpg);
+    const size_t base = ((size_t)n * HW) * C + c0 + 4 * m.cq;
+    if (m.on) {
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll 8
+        for (int r = r0 + m.ry; r < r1; r += m.RY) {
+            const float4 v = Vec4<TX>::ld(x + base + (size_t)r * C);
+            Vec4<TX>::st(sx + (size_t)(r - r0) * cw + 4 * m.cq, v);
+            a1 += v.x + v.y;
+            a2 += v.x * v.x + v.y * v.y;
+            b1 += v.z + v.w;
+            b2 += v.z * v.z + v.w * v.w;
+        }
+        if (m.gA == m.gB) { a1 += b1; a2 += b2; b1 = 0.f; b2 = 0.f; }
+        group_accumulate(s_a, s_b, m.gA, a1, a2);
+        group_accumulate(s_a, s_b, m.gB, b1, b2);
+    }
+    gn_cl_allreduce(s_a, s_b, s_recv, s_t1, s_t2, gpc, S, rank);
+    if (threadIdx.x < gpc) {
+        const double cnt = (double)HW * cpg;
+        const double mu = s_t1[threadIdx.x] / cnt;
+        double var = s_t2[threadIdx.x] / cnt - mu * mu;
+        if (var < 0) var = 0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        s_a[threadIdx.x] = (float)mu;
+        s_b[threadIdx.x] = rs;
+        if (rank == 0) {
+            mean_out[n * G + slab * gpc + threadIdx.x] = (float)mu;
+            rstd_out[n * G + slab * gpc + threadIdx.x] = rs;
+        }
+    }
+    __syncthreads();
+    if (m.on) {
+        const int c = c0 + 4 * m.cq;
+        const float muA = s_a[m.gA], rsA = s_b[m.gA], muB = s_a[m.gB], rsB = s_b[m.gB];
+        const float g0 = gamma[c] * rsA, g1 = gamma[c + 1] * rsA, g2 = gamma[c + 2] * rsB, g3 = gamma[c + 3] * rsB;
+        const float b0 = beta[c] - muA * g0, b1 = beta[c + 1] - muA * g1, b2 = beta[c + 2] - muB * g2, b3 = beta[c + 3] - muB * g3;
+#pragma unroll 4
+        for (int r = r0 + m.ry; r < r1; r += m.RY) {
+            float4 v = Vec4<TX>::ld(sx + (size_t)(r - r0) * cw + 4 * m.cq);
+            v.x = v.x * g0 + b0;
+            v.y = v.y * g1 + b1;
+            v.z = v.z * g2 + b2;
+            v.w = v.w * g3 + b3;
+            if (act) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+            Vec4<TY>::st(y + base + (size_t)r * C, v);
+        }
+    }
+}
+
+template <typename TX, typename TG, typename TD>
+__global__ void __launch_bounds__(kGnClThreads)
+gn_cluster_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      TD* __restrict__ dx, TG* __restrict__ dx_lp, int HW, int C, int G, int act, int accumulate, int gpc,
+                      int rows_per_cta) {
+    // x and dy of this CTA's rows x slab are staged once; xhat and dz * gamma are recomputed from them in both passes
+    extern __shared__ __align__(128) unsigned char gn_smem[];
+    const int cpg = C / G, cw = gpc * cpg, nq = cw >> 2;
+    TX* sx = reinterpret_cast<TX*>(gn_smem);
+    TG* sdy = reinterpret_cast<TG*>(gn_smem + (((size_t)rows_per_cta * cw * sizeof(TX) + 127) & ~(size_t)127));
+    __shared__ float s_a[32], s_b[32];
+    __shared__ __align__(8) float2 s_recv[kGnClMaxS][32];
+    __shared__ double s_t1[32], s_t2[32];
+    cluster_arrive_relaxed();
+    const int S = gridDim.x, rank = blockIdx.x, slab = blockIdx.y, n = blockIdx.z;
+    const int c0 = slab * cw;
+    const int r0 = rank * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+    if (threadIdx.x < 32) { s_a[threadIdx.x] = 0.f; s_b[threadIdx.x] = 0.f; }
+    __syncthreads();
+    pdl_sync();
+    const GnClMap m = gn_cl_map(nq, cpg);
+    const size_t base = ((size_t)n * HW) * C + c0 + 4 * m.cq;
+    float mu[2] = {0.f, 0.f}, rs[2] = {0.f, 0.f}, ga[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+    // dz * gamma and xhat of one quad (activation gradient recomputed from xhat)
+    auto terms = [&](const float4& xv, const float4& dv, float (&t)[4], float (&xh)[4]) {
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float d[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xh[k] = (xs[k] - mu[k >> 1]) * rs[k >> 1];
+            if (act) d[k] *= silu_grad(xh[k] * ga[k] + be[k]);
+            t[k] = d[k] * ga[k];
+        }
+    };
+    if (m.on) {
+        const int c = c0 + 4 * m.cq;
+        mu[0] = mean[n * G + slab * gpc + m.gA]; rs[0] = rstd[n * G + slab * gpc + m.gA];
+        mu[1] = mean[n * G + slab * gpc + m.gB]; rs[1] = rstd[n * G + slab * gpc + m.gB];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { ga[k] = gamma[c + k]; be[k] = beta[c + k]; }
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll 4
+        for (int r = r0 + m.ry; r < r1; r += m.RY) {
+            const float4 xv = Vec4<TX>::ld(x + base + (size_t)r * C);
+            const float4 dv = Vec4<TG>::ld(dy + base + (size_t)r * C);
+            const size_t so = (size_t)(r - r0) * cw + 4 * m.cq;
+            Vec4<TX>::st(sx + so, xv);
+            Vec4<TG>::st(sdy + so, dv);
+            float t[4], xh[4];
+            terms(xv, dv, t, xh);
+            a1 += t[0] + t[1];
+            a2 += t[0] * xh[0] + t[1] * xh[1];
+            b1 += t[2] + t[3];
+            b2 += t[2] * xh[2] + t[3] * xh[3];
+        }
+        if (m.gA == m.gB) { a1 += b1; a2 += b2; b1 = 0.f; b2 = 0.f; }
+        group_accumulate(s_a, s_b, m.gA, a1, a2);
+        group_accumulate(s_a, s_b, m.gB, b1, b2);
+    }
+    gn_cl_allreduce(s_a, s_b, s_recv, s_t1, s_t2, gpc, S, rank);
+    if (threadIdx.x < gpc) {
+        const double cnt = (double)HW * cpg;
+        s_a[threadIdx.x] = (float)(s_t1[threadIdx.x] / cnt);
+        s_b[threadIdx.x] = (float)(s_t2[threadIdx.x] / cnt);
+    }
+    __syncthreads();
+    if (m.on) {
+        const float m1[2] = {s_a[m.gA], s_a[m.gB]}, m2[2] = {s_b[m.gA], s_b[m.gB]};
+#pragma unroll 4
+        for (int r = r0 + m.ry; r < r1; r += m.RY) {
+            const size_t so = (size_t)(r - r0) * cw + 4 * m.cq;
+            const float4 xv = Vec4<TX>::ld(sx + so);
+            const float4 dv = Vec4<TG>::ld(sdy + so);
+            float t[4], xh[4], o[4];
+            terms(xv, dv, t, xh);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = rs[k >> 1] * (t[k] - m1[k >> 1] - xh[k] * m2[k >> 1]);
+            const size_t off = base + (size_t)r * C;
+            if (accumulate) {
+                const float4 p = Vec4<TD>::ld(dx + off);
+                o[0] += p.x; o[1] += p.y; o[2] += p.z; o[3] += p.w;
+            }
+            const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+            Vec4<TD>::st(dx + off, ov);
+            if (dx_lp) Vec4<TG>::st(dx_lp + off, ov);      // 16-bit copy for the dgrad GEMM that consumes dx next
+        }
+    }
+}
+
+// cluster shape for (N images, HW rows, C channels, G groups): slabs of gpc groups, S CTAs per slab.  Returns false when
+// the staged rows do not fit in shared memory (the streaming / single-kernel variants take over).
+struct GnClPlan { int S, gpc, rows_per_cta; size_t smem; };
+static inline bool gn_cluster_plan(int N, int HW, int C, int G, size_t bytes_per_elem, GnClPlan* out) {
+    static const int on = getenv("CB_GN_CLUSTER") ? atoi(getenv("CB_GN_CLUSTER")) : 1;
+    if (!on || G > 32) return false;
+    const int cpg = C / G;
+    const int sms = device_sm_count();
+    for (int gpc : {4, 8, 2, 16, 1, 32}) {
+        if (G % gpc) continue;
+        const int cw = gpc * cpg;
+        const int nq = cw / 4;
+        if (cw % 4 || C % 4 || nq < 2 || nq > kGnClThreads) continue;      // thread map: 4-channel accesses, >= 1 row lane per quad
+        const long long slabs = (long long)N * (G / gpc);
+        int S = kGnClMaxS;
+        while (S > 1 && slabs * S > sms) S >>= 1;
+        if (slabs * S > 2 * sms) continue;
+        if (S > HW) S = 1;
+        const int rows = ceil_div(HW, S);
+        const size_t smem = (((size_t)rows * cw * bytes_per_elem) + 255) & ~(size_t)127;
+        if (smem > 200 * 1024) continue;
+        out->S = S; out->gpc = gpc; out->rows_per_cta = rows; out->smem = smem;
+        return true;
+    }
+    return false;
+}
+
 // ---- LayerNorm: one warp per row ------------------------------------------------------------------------
 constexpr int kLnMaxPairsPerLane = 32;  // C <= 2048
 
@@ -836,6 +1098,28 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     const GnShape gs = gn_shape(C);
     const int nthr = gs.pw * gs.ry;
     {
+        // cluster path: slabs of groups, statistics through distributed shared memory (no grid-wide barrier)
+        GnClPlan pl;
+        if (gn_cluster_plan(N, HW, C, G, x_dtype == CB_F32 ? 4 : 2, &pl)) {
+            dim3 gridc((unsigned)pl.S, (unsigned)(G / pl.gpc), (unsigned)N);
+            CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
+                auto kern = gn_cluster_fwd_kernel<TX, TY>;
+                static bool set = false;
+                if (!set) {
+                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                    set = true;
+                }
+                CB_CUDA(launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st, (const TX*)x,
+                                              (TY*)y, gamma, beta, mean_out, rstd_out, HW, C, G, eps, act_silu, pl.gpc,
+                                              pl.rows_per_cta));
+            }));
+            CB_CUDA(cudaGetLastError());
+            cb::count_launches(1);
+            return 0;
+        }
+    }
+    {
         // fused single-kernel path: all CTAs co-resident (<= 1 per SM) and each CTA's rows fit in shared memory
         const int sms = device_sm_count();
         const int nb = sms / N;
@@ -911,6 +1195,31 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     CB_REQUIRE(dx_dtype == CB_F32 || dx_dtype == dy_dtype, CB_ERR_ARG, "groupnorm_bwd: dx dtype must be f32 or equal dy dtype");
     const bool allow_fused = (act_silu & CB_GN_NO_GRID_BARRIER) == 0;
     act_silu &= 1;
+    {
+        GnClPlan pl;
+        if (gn_cluster_plan(N, HW, C, G, (x_dtype == CB_F32 ? 4 : 2) + (dy_dtype == CB_F32 ? 4 : 2), &pl)) {
+            dim3 gridc((unsigned)pl.S, (unsigned)(G / pl.gpc), (unsigned)N);
+#define CB_GN_BWD_CLUSTER(TDX)                                                                                                    \
+            CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG, {                                                              \
+                auto kern = gn_cluster_bwd_kernel<TX, TG, TDX>;                                                                   \
+                static bool set = false;                                                                                          \
+                if (!set) {                                                                                                       \
+                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                 \
+                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                       \
+                    set = true;                                                                                                   \
+                }                                                                                                                 \
+                CB_CUDA(launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st,           \
+                                              (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, (TDX*)dx, (TG*)dx_lp, HW, C,  \
+                                              G, act_silu, accumulate, pl.gpc, pl.rows_per_cta));                                 \
+            }))
+            if (dx_dtype == CB_F32) { CB_GN_BWD_CLUSTER(float); }
+            else { CB_GN_BWD_CLUSTER(TG); }
+#undef CB_GN_BWD_CLUSTER
+            CB_CUDA(cudaGetLastError());
+            cb::count_launches(1);
+            return 0;
+        }
+    }
     {
         const int sms = device_sm_count();
         const int nb = sms / N;

@@ -77,6 +77,7 @@ PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "0") != "0"  # ... and its s
 # wins 0.5-3 us on the 2..6-slice launches (profiles/r02_tune_cluster_splitk.jsonl), but with cluster launches on every stream
 # the step hung against the lane-0 GroupNorm that spins on a grid-wide counter (see _gemm); =1 enables it on lane 0 only.
 CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "0") != "0"
+CLUSTER_SK_ALL_LANES = os.environ.get("CB_GEMM_CLUSTER_SK", "0") == "2"   # A/B aid: also beside concurrent streams
 # Front-end SM budget (CB_FE_CTAS = n > 0): the software-pipelined front end (VAE encode of the NEXT batch, lane 2) runs
 # its large GEMMs as persistent CTA-pair kernels on at most n CTAs and its streaming GroupNorm on at most n CTAs, so the
 # latency-bound chain of small launches that trains the CURRENT batch always finds free SMs instead of queueing behind a
@@ -245,7 +246,7 @@ def _gemm(d, what):
             # single-kernel GroupNorm (lane 0 only) spins on a grid-wide arrival counter until all its CTAs are resident.  On
             # one stream the two are ordered; on concurrent streams a pending cluster at the head of the block scheduler's
             # queue and a half-resident spinning grid can wait for each other forever (observed: the step hangs).
-            if win[4] == 1 and _LANE != 0:
+            if win[4] == 1 and _LANE != 0 and not CLUSTER_SK_ALL_LANES:
                 win = _TUNE_NC.get(key, (0, 0, 0, 0, 0))
             d.tile_n, d.splits, d.stages, d.cta_pair, d.splitk_cluster = win
     if GEMM_RECORD is not None:

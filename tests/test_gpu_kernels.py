@@ -128,6 +128,12 @@ def test_attention_fwd_bwd(dev, nq, nk, dh, heads, images):
 @pytest.mark.parametrize("n,hw,c,silu,eps,xdt", [(1, 4096, 320, True, 1e-5, torch.float32), (2, 64, 1280, True, 1e-5, torch.float32),
                                                  (1, 1024, 960, False, 1e-6, torch.float32), (1, 4096, 128, True, 1e-6, torch.float16),
                                                  (1, 1, 256, True, 1e-5, torch.float32),
+                                                 # cluster variant (slabs of groups, statistics through DSMEM): the UNet's 16^2 /
+                                                 # 8^2 concat widths, 30- and 10-channel groups (quads straddle two groups),
+                                                 # several images, fewer rows than cluster CTAs
+                                                 (1, 256, 2560, True, 1e-5, torch.float32), (1, 64, 1280, True, 1e-5, torch.float16),
+                                                 (1, 1024, 1920, True, 1e-5, torch.float32), (4, 64, 320, False, 1e-5, torch.float32),
+                                                 (1, 4096, 640, True, 1e-5, torch.float16), (3, 9, 960, True, 1e-6, torch.float32),
                                                  # larger than the SMs' shared memory: TMA-streamed two-kernel path (VAE maps)
                                                  (1, 65536, 128, True, 1e-6, torch.float32), (2, 20001, 256, False, 1e-6, torch.float16)])
 def test_groupnorm_fwd_bwd(dev, n, hw, c, silu, eps, xdt):
