@@ -73,11 +73,13 @@ def _splitk_workspace(device):
 AUTOTUNE = os.environ.get("CB_GEMM_AUTOTUNE", "1") != "0"
 CTA_PAIR = os.environ.get("CB_GEMM_CTA_PAIR", "1") != "0"      # let the autotuner try the tcgen05 cta_group::2 kernel
 PAIR_SPLITK = os.environ.get("CB_GEMM_PAIR_SPLITK", "0") != "0"  # ... and its split-K form (measured: never wins)
-# split-K slices as a thread-block cluster reducing through DSMEM (desc.splitk_cluster).  Off by default: in isolation it
-# wins 0.5-3 us on the 2..6-slice launches (profiles/r02_tune_cluster_splitk.jsonl), but with cluster launches on every stream
-# the step hung against the lane-0 GroupNorm that spins on a grid-wide counter (see _gemm); =1 enables it on lane 0 only.
-CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "0") != "0"
-CLUSTER_SK_ALL_LANES = os.environ.get("CB_GEMM_CLUSTER_SK", "0") == "2"   # A/B aid: also beside concurrent streams
+# split-K slices as a thread-block cluster reducing through DSMEM (desc.splitk_cluster): an autotuner candidate on the lane-0
+# stream (=1, default), on every lane (=2) or never (=0).  History: with cluster launches on every stream the step hung against
+# the single-kernel GroupNorm that spun on a grid-wide counter; GroupNorm now runs on clusters too (no spinning kernel is left in
+# the bs=1 step) and both settings run clean (profiles/r02_ab_gn_cluster_and_cluster_splitk.jsonl); lane 0 stays the default
+# because a launch that falls back to the spinning GroupNorm is then ordered with the cluster GEMMs by the stream.
+CLUSTER_SK = os.environ.get("CB_GEMM_CLUSTER_SK", "1") != "0"
+CLUSTER_SK_ALL_LANES = os.environ.get("CB_GEMM_CLUSTER_SK", "1") == "2"   # A/B aid: also beside concurrent streams
 # Front-end SM budget (CB_FE_CTAS = n > 0): the software-pipelined front end (VAE encode of the NEXT batch, lane 2) runs
 # its large GEMMs as persistent CTA-pair kernels on at most n CTAs and its streaming GroupNorm on at most n CTAs, so the
 # latency-bound chain of small launches that trains the CURRENT batch always finds free SMs instead of queueing behind a
