@@ -157,6 +157,72 @@ def test_gemm_autotune_key_and_lanes():
     assert ops._LANE == 0
 
 
+def test_gemm_tuned_config_dispatch_per_lane(monkeypatch):
+    """The autotuner's winner reaches cb_gemm through the descriptor; a winner that launches a cluster of k-slices
+    (splitk_cluster) is only used on the lane-0 stream -- other lanes take the best non-cluster configuration -- and the
+    front-end SM budget turns large lane-2 GEMMs into capped CTA-pair launches (no GPU: cb_gemm is a recording stub)."""
+    import torch
+    from celebbasis_b200 import ops
+    from celebbasis_b200.lib import GemmDesc
+    seen = []
+
+    class FakeLib:
+        def cb_gemm(self, dref, stream):
+            d = dref._obj
+            seen.append((d.tile_n, d.splits, d.stages, d.cta_pair, d.splitk_cluster))
+            return 0
+
+    class FakeWs:
+        def data_ptr(self):
+            return 0x1000
+
+        def numel(self):
+            return 1 << 20
+    monkeypatch.setattr(ops, "_L", lambda: FakeLib())
+    monkeypatch.setattr(ops, "_st", lambda: None)
+    monkeypatch.setattr(ops, "_splitk_workspace", lambda dev: FakeWs())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)    # never autotune here
+    monkeypatch.setattr(ops, "AUTOTUNE", True)
+    monkeypatch.setattr(ops, "CLUSTER_SK_ALL_LANES", False)
+    monkeypatch.setattr(ops, "FE_CTAS", 0)
+
+    def desc(M=77, N=768, K=768):
+        d = GemmDesc()
+        d.M, d.N, d.K, d.batch, d.lda, d.ldb, d.ldd = M, N, K, 1, K, K, N
+        return d
+    key = ops._tune_key(desc())
+    monkeypatch.setitem(ops._TUNE, key, (64, 4, 0, 0, 1))
+    monkeypatch.setitem(ops._TUNE_NC, key, (64, 6, 0, 0, 0))
+    ops._gemm(desc(), "t")                                  # lane 0: the cluster winner
+    with ops.lane(3):
+        ops._gemm(desc(), "t")                              # text branch on its own stream: best non-cluster configuration
+    monkeypatch.setattr(ops, "CLUSTER_SK_ALL_LANES", True)
+    with ops.lane(3):
+        ops._gemm(desc(), "t")
+    assert seen == [(64, 4, 0, 0, 1), (64, 6, 0, 0, 0), (64, 4, 0, 0, 1)]
+    # an explicit configuration from the caller is never overridden
+    d = desc()
+    d.tile_n, d.splits = 128, 2
+    ops._gemm(d, "t")
+    assert seen[-1] == (128, 2, 0, 0, 0)
+    # untuned shape while capturing: the library's own cost model (all zeros)
+    ops._gemm(desc(M=4096, N=320, K=320), "t")
+    assert seen[-1] == (0, 0, 0, 0, 0)
+    # front-end SM budget: lane 2, M >= 2048, K-major A -> persistent CTA-pair kernel on at most FE_CTAS CTAs
+    monkeypatch.setattr(ops, "FE_CTAS", 64)
+    with ops.lane(2):
+        ops._gemm(desc(M=65536, N=256, K=256), "t")
+        ops._gemm(desc(M=65536, N=128, K=128), "t")
+        ops._gemm(desc(M=512, N=256, K=256), "t")           # small: untouched
+    assert seen[-3:] == [(256, 1, 0, 64, 0), (128, 1, 0, 64, 0), (0, 0, 0, 0, 0)]
+    ops._gemm(desc(M=65536, N=256, K=256), "t")              # lane 0: no budget
+    assert seen[-1] == (0, 0, 0, 0, 0)
+    assert ops._gn_flags(True) == 1
+    with ops.lane(2):
+        assert ops._gn_flags(True) == (1 | 2 | (64 << 8))    # SiLU | no grid barrier | CB_GN_CTA_CAP(64)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver times beside ours): the oracle port of the reference step on the host
     cores, one JSON line with the contract's keys (no GPU involved)."""
