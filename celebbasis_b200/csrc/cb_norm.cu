@@ -923,6 +923,7 @@ gn_cluster_bwd_kernel(const TG* __restrict__ dy, const TX* __restrict__ x, const
 
 // cluster shape for (N images, HW rows, C channels, G groups): slabs of gpc groups, S CTAs per slab.  Returns false when
 // the staged rows do not fit in shared memory (the streaming / single-kernel variants take over).
+static bool g_gn_cluster_unavailable = false;     // set when a cluster launch was refused: the other variants take over
 struct GnClPlan { int S, gpc, rows_per_cta; size_t smem; };
 static inline bool gn_cluster_plan(int N, int HW, int C, int G, size_t bytes_per_elem, GnClPlan* out) {
     static const int on = getenv("CB_GN_CLUSTER") ? atoi(getenv("CB_GN_CLUSTER")) : 1;
@@ -1100,23 +1101,31 @@ extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype
     {
         // cluster path: slabs of groups, statistics through distributed shared memory (no grid-wide barrier)
         GnClPlan pl;
-        if (gn_cluster_plan(N, HW, C, G, x_dtype == CB_F32 ? 4 : 2, &pl)) {
+        if (!g_gn_cluster_unavailable && gn_cluster_plan(N, HW, C, G, x_dtype == CB_F32 ? 4 : 2, &pl)) {
             dim3 gridc((unsigned)pl.S, (unsigned)(G / pl.gpc), (unsigned)N);
+            cudaError_t le = cudaSuccess;
             CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(y_dtype, TY, {
                 auto kern = gn_cluster_fwd_kernel<TX, TY>;
                 static bool set = false;
                 if (!set) {
-                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-                    set = true;
+                    le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                    if (le == cudaSuccess) le = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                    set = le == cudaSuccess;
                 }
-                CB_CUDA(launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st, (const TX*)x,
-                                              (TY*)y, gamma, beta, mean_out, rstd_out, HW, C, G, eps, act_silu, pl.gpc,
-                                              pl.rows_per_cta));
+                if (le == cudaSuccess)
+                    le = launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st,
+                                               (const TX*)x, (TY*)y, gamma, beta, mean_out, rstd_out, HW, C, G, eps, act_silu,
+                                               pl.gpc, pl.rows_per_cta);
             }));
-            CB_CUDA(cudaGetLastError());
-            cb::count_launches(1);
-            return 0;
+            if (le == cudaSuccess) {
+                CB_CUDA(cudaGetLastError());
+                cb::count_launches(1);
+                return 0;
+            }
+            // this device cannot co-schedule the cluster (or refuses the attributes): clear the launch error and use the
+            // single-kernel / streaming variants from now on
+            (void)cudaGetLastError();
+            g_gn_cluster_unavailable = true;
         }
     }
     {
@@ -1197,27 +1206,33 @@ extern "C" int cb_groupnorm_bwd(const void* dy, int dy_dtype, const void* x, int
     act_silu &= 1;
     {
         GnClPlan pl;
-        if (gn_cluster_plan(N, HW, C, G, (x_dtype == CB_F32 ? 4 : 2) + (dy_dtype == CB_F32 ? 4 : 2), &pl)) {
+        if (!g_gn_cluster_unavailable && gn_cluster_plan(N, HW, C, G, (x_dtype == CB_F32 ? 4 : 2) + (dy_dtype == CB_F32 ? 4 : 2), &pl)) {
             dim3 gridc((unsigned)pl.S, (unsigned)(G / pl.gpc), (unsigned)N);
+            cudaError_t le = cudaSuccess;
 #define CB_GN_BWD_CLUSTER(TDX)                                                                                                    \
             CB_DISPATCH_2(x_dtype, TX, CB_DISPATCH_2(dy_dtype, TG, {                                                              \
                 auto kern = gn_cluster_bwd_kernel<TX, TG, TDX>;                                                                   \
                 static bool set = false;                                                                                          \
                 if (!set) {                                                                                                       \
-                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                 \
-                    CB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));                       \
-                    set = true;                                                                                                   \
+                    le = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                     \
+                    if (le == cudaSuccess) le = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);    \
+                    set = le == cudaSuccess;                                                                                      \
                 }                                                                                                                 \
-                CB_CUDA(launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st,           \
-                                              (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, (TDX*)dx, (TG*)dx_lp, HW, C,  \
-                                              G, act_silu, accumulate, pl.gpc, pl.rows_per_cta));                                 \
+                if (le == cudaSuccess)                                                                                            \
+                    le = launch_kernel_cluster(kern, gridc, dim3(kGnClThreads), dim3((unsigned)pl.S, 1, 1), pl.smem, st,          \
+                                               (const TG*)dy, (const TX*)x, gamma, beta, mean, rstd, (TDX*)dx, (TG*)dx_lp, HW, C, \
+                                               G, act_silu, accumulate, pl.gpc, pl.rows_per_cta);                                 \
             }))
             if (dx_dtype == CB_F32) { CB_GN_BWD_CLUSTER(float); }
             else { CB_GN_BWD_CLUSTER(TG); }
 #undef CB_GN_BWD_CLUSTER
-            CB_CUDA(cudaGetLastError());
-            cb::count_launches(1);
-            return 0;
+            if (le == cudaSuccess) {
+                CB_CUDA(cudaGetLastError());
+                cb::count_launches(1);
+                return 0;
+            }
+            (void)cudaGetLastError();            // see cb_groupnorm_fwd
+            g_gn_cluster_unavailable = true;
         }
     }
     {

@@ -187,6 +187,11 @@ def _autotune(d, key):
         for bn, sp, stg, pair, cl in cands:
             t.tile_n, t.splits, t.stages, t.cta_pair, t.splitk_cluster = bn, sp, stg, pair, cl
             if L.cb_gemm(ctypes.byref(t), sp_) != 0:
+                # a refused launch (e.g. a cluster this device cannot co-schedule) leaves its code in CUDA's last-error slot;
+                # the library's own cudaGetLastError() check at the end of the next launch would report it for that launch.
+                # Absorb it with one launch of the library's default configuration whose return code is ignored.
+                t.tile_n, t.splits, t.stages, t.cta_pair, t.splitk_cluster = 0, 0, 0, 0, 0
+                L.cb_gemm(ctypes.byref(t), sp_)
                 continue
             g = torch.cuda.CUDAGraph()
             g.capture_begin()
