@@ -4,6 +4,7 @@ import ctypes as C
 _p, _i, _l, _f = C.c_void_p, C.c_int32, C.c_longlong, C.c_float
 
 SIGS = {
+    "cb_groupnorm_cluster_plan": [_i, _i, _i, _i, _i, _p],
     "cb_groupnorm_fwd": [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p],
     "cb_groupnorm_bwd": [_p, _i, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "cb_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _i, _i, _f, _p, _p, _p],

@@ -1080,6 +1080,16 @@ static int gn_check(int N, int HW, int C, int G) {
     return 0;
 }
 
+extern "C" int cb_groupnorm_cluster_plan(int N, int HW, int C, int G, int bytes_per_elem, int* plan) {
+    int rc = gn_check(N, HW, C, G);
+    if (rc) return rc;
+    CB_REQUIRE(plan != nullptr && bytes_per_elem > 0, CB_ERR_ARG, "cb_groupnorm_cluster_plan: bad arguments");
+    GnClPlan pl;
+    if (!gn_cluster_plan(N, HW, C, G, (size_t)bytes_per_elem, &pl)) return 0;
+    plan[0] = pl.S; plan[1] = pl.gpc; plan[2] = pl.rows_per_cta; plan[3] = (int)pl.smem;
+    return 1;
+}
+
 extern "C" int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
                                 int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
                                 double* ws, void* stream) {

@@ -193,6 +193,12 @@ int cb_gemm(const cb_gemm_desc* desc, void* stream);
  * dgrad GEMM that consumes dx next (saves a cast launch per ResBlock / transformer block of the backward pass). */
 #define CB_GN_NO_GRID_BARRIER 2 /* OR into act_silu: force the statistics + apply kernel pair (no grid-wide spin barrier) */
 #define CB_GN_CTA_CAP(n) (((n) & 0xFFFF) << 8) /* OR into act_silu (cb_groupnorm_fwd): at most n CTAs on the streaming kernel pair */
+/* How cb_groupnorm_fwd / _bwd would run a (N, HW, C, G) problem whose staged element costs `bytes_per_elem` bytes
+ * (fwd: sizeof(x); bwd: sizeof(x) + sizeof(dy)): returns 1 and fills plan[4] = {CTAs per cluster, groups per cluster slab,
+ * rows per CTA, dynamic shared memory bytes} when the thread-block-cluster variant applies (slabs of groups, statistics
+ * through distributed shared memory), 0 when the rows do not fit and the single-kernel / streaming variants take over.
+ * Host-only (no launch): lets integrators and the CPU tests see the launch geometry. */
+int cb_groupnorm_cluster_plan(int N, int HW, int C, int G, int bytes_per_elem, int* plan);
 int cb_groupnorm_fwd(const void* x, int x_dtype, void* y, int y_dtype, const float* gamma, const float* beta,
                      int N, int HW, int C, int G, float eps, int act_silu, float* mean_out, float* rstd_out,
                      double* ws, void* stream);

@@ -223,6 +223,50 @@ def test_gemm_tuned_config_dispatch_per_lane(monkeypatch):
         assert ops._gn_flags(True) == (1 | 2 | (64 << 8))    # SiLU | no grid barrier | CB_GN_CTA_CAP(64)
 
 
+def test_groupnorm_cluster_plan_covers_the_step():
+    """cb_groupnorm_cluster_plan (host-only entry point of the library): every GroupNorm of the bs=1 SD-v1 UNet step --
+    forward (fp32 or 16-bit input) and backward (input + 16-bit gradient staged) -- runs on the cluster variant: 128 CTAs as
+    8 slabs x 16, staged rows within 200 KiB; each CTA's thread map (4-channel accesses, row lanes) touches every element of
+    its rows x slab exactly once; tensors that do not fit (VAE 512^2 maps, a 16-image UNet batch) report 0."""
+    import ctypes
+    import numpy as np
+    from celebbasis_b200 import lib
+    L = lib.load()
+    plan = (ctypes.c_int32 * 4)()
+
+    def ask(N, HW, C, bpe):
+        rc = L.cb_groupnorm_cluster_plan(N, HW, C, 32, bpe, ctypes.cast(plan, ctypes.c_void_p))
+        assert rc in (0, 1), (rc, N, HW, C)
+        return tuple(plan) if rc == 1 else None
+    unet = [(4096, 320), (4096, 640), (4096, 960), (1024, 320), (1024, 640), (1024, 960), (1024, 1280), (1024, 1920),
+            (256, 640), (256, 1280), (256, 1920), (256, 2560), (64, 1280), (64, 2560)]
+    for hw, c in unet:
+        for bpe in (4, 2, 6, 4 + 4):                      # fwd fp32 / fwd 16-bit / bwd fp32 x + 16-bit dy / bwd fp32 + fp32
+            p = ask(1, hw, c, bpe)
+            if p is None:
+                assert bpe == 8 and hw * c * bpe > 128 * 200 * 1024      # only the all-fp32 backward of the widest 64^2 map
+                continue
+            S, gpc, rows, smem = p
+            cpg, cw = c // 32, gpc * (c // 32)
+            assert S * (32 // gpc) <= 148 and S * rows >= hw and S <= 16 and 32 % gpc == 0
+            assert rows * cw * bpe <= smem <= 200 * 1024 and cw % 4 == 0
+            # the kernels' thread map on one CTA: quad cq = tid % nq, row lane ry = tid // nq, RY = 512 // nq row lanes
+            nq = cw // 4
+            RY = 512 // nq
+            assert 1 <= RY and nq >= 2
+            cover = np.zeros((min(rows, 40), cw), dtype=np.int32)
+            for tid in range(512):
+                cq, ry = tid % nq, tid // nq
+                if ry >= RY:
+                    continue
+                assert (4 * cq) // cpg < gpc and (4 * cq + 2) // cpg < gpc
+                cover[ry::RY, 4 * cq:4 * cq + 4] += 1
+            assert (cover == 1).all()
+    assert ask(1, 512 * 512, 128, 4) is None and ask(16, 4096, 320, 4) is None and ask(2, 4096, 960, 4) is None
+    assert ask(2, 4096, 320, 4)[0] == 8 and ask(4, 64, 320, 4)[0] == 4 and ask(1, 1, 256, 4)[0] == 1
+    assert L.cb_groupnorm_cluster_plan(1, 64, 48, 32, 4, ctypes.cast(plan, ctypes.c_void_p)) < 0      # odd channels per group
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver times beside ours): the oracle port of the reference step on the host
     cores, one JSON line with the contract's keys (no GPU involved)."""
